@@ -1,0 +1,250 @@
+/*
+ * zbphys.h — C ABI of the B200-native batched Z-Bot rigid-body physics step.
+ *
+ * This is the drop-in boundary for the ONE hot path of schnetzlerjoe/ksim-gym-zbot:
+ * what ksim's MjxEngine.reset / MjxEngine.step do for every environment
+ * (upstream ksim 0.1.99 ksim/engine.py — un-vendored dependency pinned at
+ * /root/reference/uv.lock:1872-1873; physics = mujoco-mjx 3.3.4, uv.lock:2226-2227),
+ * with the reference's own per-substep servo model fused in
+ * (/root/reference/train.py:1137-1196 trapezoidal_step, :1242-1280 get_stateful_ctrl).
+ *
+ * Rules of the boundary (what an XLA-FFI / ctypes / cgo binding may rely on):
+ *   - plain C types only; every array pointer is CALLER-OWNED DEVICE memory, fp32/int32,
+ *     row-major with the environment index leading ([N, ...] — the layout jax.vmap gives);
+ *   - calls only enqueue work on the given cudaStream_t; they never synchronise, never
+ *     allocate and never throw.  Return value: 0 = ok, negative = ZB_E* error code;
+ *   - the state arrays are updated in place; outputs never alias state;
+ *   - there is NO CPU fallback: without a CUDA device zb_engine_create fails with ZB_ENODEV.
+ */
+#ifndef ZBPHYS_H_
+#define ZBPHYS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- compile-time sizes of the Z-Bot topology (train.py:27 NUM_JOINTS, :59-82 joint order,
+ *      :42-43 CRITIC_DIM com_inertia=250=10*25 bodies, com_velocity=150=6*25) ---------------- */
+#define ZB_NQ 27          /* 7 (free joint) + 20 hinges                       */
+#define ZB_NV 26          /* 6 + 20                                           */
+#define ZB_NU 20          /* actuators == hinge joints, train.py:27           */
+#define ZB_NBODY 26       /* world + 25 bodies                                */
+#define ZB_NSITE 3        /* imu_site, left_foot, right_foot  (train.py:1453, 1519-1520) */
+#define ZB_NBOX 2         /* foot collision boxes vs. the floor plane         */
+#define ZB_MAXCON 8       /* 4 manifold slots per foot box (MJX plane_convex) */
+#define ZB_NEFC_CON (4 * ZB_MAXCON) /* pyramidal condim-3 rows                */
+#define ZB_NSENSORDATA 18 /* quat4 acc3 gyro3 touchL touchR forceL3 forceR3   */
+
+enum { ZB_SOLVER_CG = 0, ZB_SOLVER_NEWTON = 1 };
+enum { ZB_INT_EULER = 0, ZB_INT_IMPLICITFAST = 1 };
+enum { ZB_ORDER_EVENT_ACT_STEP = 0, ZB_ORDER_ACT_EVENT_STEP = 1 };
+
+enum {
+  ZB_OK = 0,
+  ZB_EINVAL = -1,  /* null/ill-formed argument                      */
+  ZB_ENODEV = -2,  /* no CUDA device / wrong architecture           */
+  ZB_ECUDA = -3,   /* a CUDA runtime call failed (see zb_last_error)*/
+  ZB_EUNSUP = -4   /* option combination not built into the kernels */
+};
+
+/* Sensor layout inside sensordata[ZB_NSENSORDATA] (train.py:44-46,1495-1516,516-517,724-725) */
+enum {
+  ZB_SENS_IMU_QUAT = 0,   /* framequat imu_site (4) */
+  ZB_SENS_IMU_ACC = 4,    /* accelerometer (3)      */
+  ZB_SENS_IMU_GYRO = 7,   /* gyro (3)               */
+  ZB_SENS_TOUCH_L = 10,   /* left_foot_touch (1)    */
+  ZB_SENS_TOUCH_R = 11,   /* right_foot_touch (1)   */
+  ZB_SENS_FORCE_L = 12,   /* left_foot_force (3)    */
+  ZB_SENS_FORCE_R = 15    /* right_foot_force (3)   */
+};
+
+/* Physics options == the mjOption fields ksim sets from its config
+ * (train.py:1777-1780 dt/ctrl_dt/iterations/ls_iterations; the rest are ksim/MuJoCo defaults,
+ * each one a named parity switch, see PARITY_RISKS.md). */
+typedef struct ZbOpts {
+  float dt;            /* physics timestep                                   */
+  float tolerance;     /* solver tolerance (MuJoCo default 1e-8)             */
+  float ls_tolerance;  /* line-search tolerance (MuJoCo default 0.01)        */
+  float impratio;      /* MuJoCo default 1                                    */
+  float gravity[3];    /* (0,0,-9.81)                                         */
+  int32_t iterations;    /* train.py:1779 -> 8                                */
+  int32_t ls_iterations; /* train.py:1780 -> 8                                */
+  int32_t solver;        /* ZB_SOLVER_*                                       */
+  int32_t integrator;    /* ZB_INT_*                                          */
+  int32_t eulerdamp;     /* Euler only: 1 = implicit-in-damping               */
+  int32_t warmstart;     /* 1 = pick cheaper of qacc_warmstart / qacc_smooth  */
+  int32_t substep_order; /* ZB_ORDER_*                                        */
+  int32_t reserved;
+} ZbOpts;
+
+/* The compiled model (what mjx.put_model holds for the fields this path reads), fp32. */
+typedef struct ZbModel {
+  /* tree */
+  int32_t body_parent[ZB_NBODY];
+  int32_t body_dofadr[ZB_NBODY];  /* first dof of the body's joint, -1 = jointless  */
+  int32_t body_jnttype[ZB_NBODY]; /* 0 = none, 1 = free, 2 = hinge                  */
+  int32_t dof_body[ZB_NV];
+  int32_t dof_parent[ZB_NV];      /* parent dof in the kinematic chain, -1 = none   */
+  float body_pos[ZB_NBODY][3];
+  float body_quat[ZB_NBODY][4];
+  float body_ipos[ZB_NBODY][3];
+  float body_iquat[ZB_NBODY][4];
+  float body_mass[ZB_NBODY];
+  float body_inertia[ZB_NBODY][3];
+  float body_invweight0[ZB_NBODY][2];
+  float jnt_pos[ZB_NBODY][3];     /* hinge anchor in the body frame (per body)      */
+  float jnt_axis[ZB_NBODY][3];
+  /* per dof (hinge dofs 6..25 are meaningful for range/solref/solimp) */
+  float jnt_range[ZB_NV][2];
+  float jnt_margin[ZB_NV];
+  float jnt_solref[ZB_NV][2];
+  float jnt_solimp[ZB_NV][5];
+  int32_t jnt_limited[ZB_NV];
+  float dof_armature[ZB_NV];
+  float dof_damping[ZB_NV];
+  float dof_frictionloss[ZB_NV];
+  float dof_invweight0[ZB_NV];
+  float dof_solref[ZB_NV][2];
+  float dof_solimp[ZB_NV][5];
+  float qpos0[ZB_NQ];
+  /* motors: <joint>_ctrl, train.py:1358-1362 */
+  int32_t act_dof[ZB_NU];
+  float act_gear[ZB_NU];
+  float act_ctrlrange[ZB_NU][2];
+  float act_forcerange[ZB_NU][2];
+  int32_t act_ctrllimited[ZB_NU];
+  int32_t act_forcelimited[ZB_NU];
+  /* Feetech servo constants, train.py:1421-1431 (per joint, action order) */
+  float servo_kp[ZB_NU];
+  float servo_kd[ZB_NU];
+  float servo_max_pwm[ZB_NU];
+  float servo_vin[ZB_NU];
+  float servo_kt[ZB_NU];
+  float servo_R[ZB_NU];
+  float servo_vmax[ZB_NU];
+  float servo_amax[ZB_NU];
+  float servo_error_gain[ZB_NU];
+  float servo_deadband_pos; /* train.py:1111-1118 */
+  float servo_deadband_neg;
+  /* floor plane: geom "floor", priority 2 (train.py:1329-1330) */
+  float floor_pos[3];
+  float floor_normal[3];
+  float floor_friction[3];
+  float floor_solref[2];
+  float floor_solimp[5];
+  int32_t floor_priority;
+  float floor_margin;
+  float floor_gap;
+  /* foot collision boxes */
+  int32_t box_body[ZB_NBOX];
+  float box_pos[ZB_NBOX][3];
+  float box_quat[ZB_NBOX][4];
+  float box_size[ZB_NBOX][3];
+  float box_friction[ZB_NBOX][3];
+  float box_solref[ZB_NBOX][2];
+  float box_solimp[ZB_NBOX][5];
+  int32_t box_priority[ZB_NBOX];
+  float box_margin[ZB_NBOX];
+  float box_gap[ZB_NBOX];
+  /* sites: 0 = imu_site, 1 = left_foot, 2 = right_foot (box-shaped touch volumes) */
+  int32_t site_body[ZB_NSITE];
+  float site_pos[ZB_NSITE][3];
+  float site_quat[ZB_NSITE][4];
+  float site_size[ZB_NSITE][3];
+  /* statistics */
+  float meaninertia;
+  int32_t reserved;
+} ZbModel;
+
+/* Per-environment model overrides == the fields ksim's randomizers batch
+ * (train.py:1439-1455).  Any pointer may be NULL -> the ZbModel value is used. */
+typedef struct ZbEnvParams {
+  const float* body_mass;        /* [N, ZB_NBODY]    AllBodiesMassMultiplicationRandomizer */
+  const float* body_inertia;     /* [N, ZB_NBODY, 3]                                        */
+  const float* dof_armature;     /* [N, ZB_NV]       ArmatureRandomizer                     */
+  const float* dof_damping;      /* [N, ZB_NV]       JointDampingRandomizer                 */
+  const float* dof_frictionloss; /* [N, ZB_NV]       StaticFrictionRandomizer               */
+  const float* qpos0;            /* [N, ZB_NQ]       JointZeroPositionRandomizer            */
+  const float* floor_friction;   /* [N]              FloorFrictionRandomizer (sliding mu)   */
+  const float* imu_site_pos;     /* [N, 3]           IMUAlignmentRandomizer                 */
+  const float* imu_site_quat;    /* [N, 4]                                                  */
+} ZbEnvParams;
+
+/* ksim PhysicsState, flattened (data.qpos/qvel/qacc_warmstart/time, actuator_state ==
+ * PlannerState train.py:1103-1108, event_states == PushEvent time remaining). In/out. */
+typedef struct ZbState {
+  float* qpos;            /* [N, ZB_NQ] */
+  float* qvel;            /* [N, ZB_NV] */
+  float* qacc_warmstart;  /* [N, ZB_NV] */
+  float* act_pos;         /* [N, ZB_NU] PlannerState.position             */
+  float* act_vel;         /* [N, ZB_NU] PlannerState.velocity             */
+  float* act_torque;      /* [N, ZB_NU] PlannerState.last_computed_torque */
+  float* push_t_rem;      /* [N]        PushEvent state                   */
+  float* time;            /* [N]                                          */
+} ZbState;
+
+/* mjx.Data fields the task reads (train.py:452-461, 476, 681, 854, 882, 1252-1253, 1307),
+ * produced by forward() of the LAST substep, i.e. at the pre-integration state exactly as
+ * mjx.step leaves them.  Any pointer may be NULL (that output is skipped). */
+typedef struct ZbOut {
+  float* xpos;            /* [N, ZB_NBODY, 3]  */
+  float* xquat;           /* [N, ZB_NBODY, 4]  */
+  float* cinert;          /* [N, ZB_NBODY, 10] */
+  float* cvel;            /* [N, ZB_NBODY, 6]  */
+  float* qacc;            /* [N, ZB_NV]        */
+  float* qfrc_constraint; /* [N, ZB_NV]        */
+  float* actuator_force;  /* [N, ZB_NU]        */
+  float* ctrl;            /* [N, ZB_NU]        */
+  float* sensordata;      /* [N, ZB_NSENSORDATA] */
+  float* site_xpos;       /* [N, ZB_NSITE, 3]  */
+  float* site_xmat;       /* [N, ZB_NSITE, 9]  */
+  float* contact_dist;    /* [N, ZB_MAXCON]    */
+  float* contact_pos;     /* [N, ZB_MAXCON, 3] */
+  float* efc_force;       /* [N, ZB_NV*2 + ZB_NEFC_CON]  friction | limit | contact rows */
+  int32_t* contact_mask;  /* [N] bit c set <=> contact slot c active (dist < margin)    */
+  int32_t* solver_niter;  /* [N]                                                         */
+  int32_t* flags;         /* [N] bit0: non-finite state detected                         */
+} ZbOut;
+
+typedef struct ZbEngine ZbEngine; /* opaque: device copy of ZbModel + ZbOpts */
+
+/* Engine construction == mjx.put_model + ksim.get_physics_engine(...) for this path. */
+int zb_engine_create(const ZbModel* model, const ZbOpts* opts, int device, ZbEngine** out);
+int zb_engine_destroy(ZbEngine* engine);
+int zb_engine_set_opts(ZbEngine* engine, const ZbOpts* opts);
+
+/* MjxEngine.step: n_substeps x { PushEvent -> FeetechActuators.get_stateful_ctrl -> mjx.step }.
+ *   action    [N, ZB_NU]   position targets (train.py:1252-1260)
+ *   push_rand [N, 7] (push_per_substep == 0) or [N, n_substeps, 7]: pre-sampled
+ *             (dqvel[6], next interval) consumed when the push timer expires; NULL = no PushEvent. */
+int zb_step_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, const ZbState* state,
+                const float* action, const float* push_rand, int push_per_substep, const ZbOut* out,
+                int n_envs, int n_substeps);
+
+/* mjx.forward on the current state (no integration, state untouched except the free-joint
+ * quaternion normalisation MJX writes back) — what MjxEngine.reset runs after the resets. */
+int zb_forward_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, const ZbState* state,
+                   const ZbOut* out, int n_envs);
+
+/* MjxEngine.reset for the environments with done[i] != 0 (done == NULL: all):
+ * qpos/qvel <- reset_qpos/reset_qvel (host-sampled per ksim resets, train.py:1471-1476),
+ * PlannerState <- (qpos[7:], qvel[6:], 0) (train.py:1293-1298), push_t_rem <- reset_t_rem,
+ * time <- 0, qacc_warmstart <- 0, then forward() for those environments. */
+int zb_reset_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, const ZbState* state,
+                 const uint8_t* done, const float* reset_qpos, const float* reset_qvel,
+                 const float* reset_t_rem, const ZbOut* out, int n_envs);
+
+/* Introspection for bindings and tests. */
+int zb_abi_version(void);
+int zb_sizeof_model(void);
+int zb_sizeof_opts(void);
+const char* zb_last_error(void);
+/* Number of kernel launches issued through this library since load (bench accounting). */
+long long zb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZBPHYS_H_ */

@@ -1,0 +1,244 @@
+"""ctypes front-end of the CPU oracle (oracle/zb_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Allowed importers: tests/, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of bench.py.  The product package never imports this module.
+
+PARITY UNPINNED — see the header of zb_oracle.c: the restated algorithm lives in mujoco-mjx 3.3.4 and
+ksim 0.1.99 (/root/reference/uv.lock:2226-2227, 1872-1873), neither vendored nor installable here, and
+the reference has no tests or golden vectors for this path.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+NQ, NV, NU, NBODY, NSITE, NBOX, MAXCON = 27, 26, 20, 26, 3, 2, 8
+NEFC = 2 * NV + 4 * MAXCON
+NSENSORDATA = 18
+STAGES = [
+    "kinematics", "com_pos", "crb", "factor_m", "collision", "make_constraint", "com_vel", "rne",
+    "actuation", "fwd_acceleration", "solver", "sensor", "integrate",
+]
+
+_REAL_FIELDS = [
+    ("qpos", (NQ,)), ("qvel", (NV,)), ("ctrl", (NU,)), ("qacc_warmstart", (NV,)),
+    ("xpos", (NBODY, 3)), ("xquat", (NBODY, 4)), ("xmat", (NBODY, 9)), ("xipos", (NBODY, 3)), ("ximat", (NBODY, 9)),
+    ("xanchor", (NBODY, 3)), ("xaxis", (NBODY, 3)), ("subtree_com", (NBODY, 3)),
+    ("cinert", (NBODY, 10)), ("crb", (NBODY, 10)), ("cdof", (NV, 6)), ("cdof_dot", (NV, 6)), ("cvel", (NBODY, 6)),
+    ("qM", (NV, NV)), ("qL", (NV, NV)),
+    ("qfrc_passive", (NV,)), ("qfrc_bias", (NV,)), ("qfrc_actuator", (NV,)), ("qfrc_smooth", (NV,)), ("qacc_smooth", (NV,)),
+    ("actuator_force", (NU,)),
+    ("site_xpos", (NSITE, 3)), ("site_xmat", (NSITE, 9)), ("box_xpos", (NBOX, 3)), ("box_xmat", (NBOX, 9)),
+    ("con_dist", (MAXCON,)), ("con_pos", (MAXCON, 3)), ("con_frame", (MAXCON, 9)), ("con_mu", (MAXCON,)),
+    ("con_includemargin", (MAXCON,)), ("con_solref", (MAXCON, 2)), ("con_solimp", (MAXCON, 5)),
+    ("efc_J", (NEFC, NV)), ("efc_pos", (NEFC,)), ("efc_D", (NEFC,)), ("efc_R", (NEFC,)), ("efc_aref", (NEFC,)),
+    ("efc_floss", (NEFC,)), ("efc_force", (NEFC,)),
+    ("qfrc_constraint", (NV,)), ("qacc", (NV,)),
+    ("cacc", (NBODY, 6)), ("cfrc_int", (NBODY, 6)), ("cfrc_ext", (NBODY, 6)),
+    ("sensordata", (NSENSORDATA,)),
+    ("solver_cost", ()),
+]
+_INT_FIELDS = [
+    ("con_body", (MAXCON,)), ("con_vert", (MAXCON,)), ("con_active", (MAXCON,)), ("efc_type", (NEFC,)),
+    ("solver_niter", ()), ("ls_evals", ()), ("ls_iters", ()), ("flags", ()),
+]
+
+
+def _ctype(base, shape):
+    t = base
+    for n in reversed(shape):
+        t = t * n
+    return t
+
+
+def _make_data(real):
+    class ZboData(ctypes.Structure):
+        _fields_ = [(n, _ctype(real, s)) for n, s in _REAL_FIELDS] + [(n, _ctype(ctypes.c_int32, s)) for n, s in _INT_FIELDS]
+
+        def get(self, name):
+            v = getattr(self, name)
+            if isinstance(v, (int, float)):
+                return v
+            return np.ctypeslib.as_array(v).copy()
+
+        def set(self, name, value):
+            np.ctypeslib.as_array(getattr(self, name))[...] = value
+
+    return ZboData
+
+
+ZboDataF32 = _make_data(ctypes.c_float)
+ZboDataF64 = _make_data(ctypes.c_double)
+
+_PARAM_FIELDS = ["body_mass", "body_inertia", "dof_armature", "dof_damping", "dof_frictionloss", "qpos0",
+                 "floor_friction", "imu_site_pos", "imu_site_quat"]
+_STATE_FIELDS = ["qpos", "qvel", "qacc_warmstart", "act_pos", "act_vel", "act_torque", "push_t_rem", "time"]
+_OUT_REAL = ["xpos", "xquat", "cinert", "cvel", "qacc", "qfrc_constraint", "actuator_force", "ctrl", "sensordata",
+             "site_xpos", "site_xmat", "contact_dist", "contact_pos", "efc_force"]
+_OUT_INT = ["contact_mask", "solver_niter", "flags"]
+OUT_SHAPES = {
+    "xpos": (NBODY, 3), "xquat": (NBODY, 4), "cinert": (NBODY, 10), "cvel": (NBODY, 6), "qacc": (NV,),
+    "qfrc_constraint": (NV,), "actuator_force": (NU,), "ctrl": (NU,), "sensordata": (NSENSORDATA,),
+    "site_xpos": (NSITE, 3), "site_xmat": (NSITE, 9), "contact_dist": (MAXCON,), "contact_pos": (MAXCON, 3),
+    "efc_force": (NEFC,), "contact_mask": (), "solver_niter": (), "flags": (),
+}
+STATE_SHAPES = {"qpos": (NQ,), "qvel": (NV,), "qacc_warmstart": (NV,), "act_pos": (NU,), "act_vel": (NU,),
+                "act_torque": (NU,), "push_t_rem": (), "time": ()}
+
+
+class _Ptrs(ctypes.Structure):
+    pass
+
+
+def _ptr_struct(names):
+    return type("S", (ctypes.Structure,), {"_fields_": [(n, ctypes.c_void_p) for n in names]})
+
+
+_ZboParams = _ptr_struct(_PARAM_FIELDS)
+_ZboState = _ptr_struct(_STATE_FIELDS)
+_ZboOut = _ptr_struct(_OUT_REAL + _OUT_INT)
+
+
+def build(force: bool = False) -> None:
+    """Compile oracle/_build/libzb_oracle*.so with gcc (oracle/Makefile)."""
+    if force or not os.path.exists(os.path.join(_BUILD, "libzb_oracle.so")) or (
+        os.path.getmtime(os.path.join(_BUILD, "libzb_oracle.so")) < os.path.getmtime(os.path.join(_HERE, "zb_oracle.c"))
+    ):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+
+
+_libs: dict[str, ctypes.CDLL] = {}
+
+
+def lib(count: bool = False) -> ctypes.CDLL:
+    key = "cnt" if count else "std"
+    if key not in _libs:
+        path = os.path.join(_BUILD, "libzb_oracle_cnt.so" if count else "libzb_oracle.so")
+        if not os.path.exists(path):
+            build()
+        _libs[key] = ctypes.CDLL(path)
+    return _libs[key]
+
+
+class Oracle:
+    """Batched CPU oracle in one precision (``np.float32`` — JAX's dtype — or ``np.float64``)."""
+
+    def __init__(self, model, opts, dtype=np.float32, count: bool = False, threads: int = 1):
+        self.model, self.opts = model, opts
+        self.dtype = np.dtype(dtype)
+        self.suf = "_f64" if self.dtype == np.float64 else "_f32"
+        self.lib = lib(count)
+        self.count = count
+        self.threads = threads
+        self.Data = ZboDataF64 if self.dtype == np.float64 else ZboDataF32
+        assert getattr(self.lib, "zbo_sizeof_data" + self.suf)() == ctypes.sizeof(self.Data)
+
+    # ---- helpers -------------------------------------------------------------------------
+    def _arr(self, a):
+        return None if a is None else np.ascontiguousarray(a, dtype=self.dtype)
+
+    def _params(self, params):
+        keep, s = [], _ZboParams()
+        if params:
+            for k in _PARAM_FIELDS:
+                if params.get(k) is not None:
+                    a = self._arr(params[k])
+                    keep.append(a)
+                    setattr(s, k, a.ctypes.data)
+        return s, keep
+
+    def new_state(self, n):
+        st = {k: np.zeros((n,) + STATE_SHAPES[k], dtype=self.dtype) for k in _STATE_FIELDS}
+        return st
+
+    def new_out(self, n):
+        out = {k: np.zeros((n,) + OUT_SHAPES[k], dtype=self.dtype) for k in _OUT_REAL}
+        out.update({k: np.zeros((n,), dtype=np.int32) for k in _OUT_INT})
+        return out
+
+    def _state(self, st):
+        s = _ZboState()
+        for k in _STATE_FIELDS:
+            a = st[k]
+            assert a.dtype == self.dtype and a.flags.c_contiguous, k
+            setattr(s, k, a.ctypes.data)
+        return s
+
+    def _out(self, out):
+        s = _ZboOut()
+        if out is not None:
+            for k in _OUT_REAL + _OUT_INT:
+                if out.get(k) is not None:
+                    setattr(s, k, out[k].ctypes.data)
+        return s
+
+    # ---- single-environment, full intermediates ------------------------------------------
+    def forward_one(self, qpos, qvel, ctrl=None, warmstart=None, params=None, env=0):
+        d = self.Data()
+        ps, keep = self._params(params)
+        q, v = self._arr(qpos), self._arr(qvel)
+        c, w = self._arr(ctrl), self._arr(warmstart)
+        fn = getattr(self.lib, "zbo_forward_one" + self.suf)
+        rc = fn(ctypes.byref(self.model), ctypes.byref(self.opts), ctypes.byref(ps), env, q.ctypes.data_as(ctypes.c_void_p),
+                v.ctypes.data_as(ctypes.c_void_p), None if c is None else c.ctypes.data_as(ctypes.c_void_p),
+                None if w is None else w.ctypes.data_as(ctypes.c_void_p), ctypes.byref(d))
+        assert rc == 0
+        return d
+
+    def step_one(self, d, params=None, env=0):
+        """mjx.step on a ZboData holding qpos/qvel/ctrl/qacc_warmstart (in place)."""
+        ps, keep = self._params(params)
+        fn = getattr(self.lib, "zbo_step_one" + self.suf)
+        rc = fn(ctypes.byref(self.model), ctypes.byref(self.opts), ctypes.byref(ps), env, ctypes.byref(d))
+        assert rc == 0
+        return d
+
+    # ---- batched engine entry points (same semantics as include/zbphys.h) -----------------
+    def step(self, state, action, n_substeps, params=None, push_rand=None, push_per_substep=False, out=None):
+        n = state["qpos"].shape[0]
+        ps, keep = self._params(params)
+        a, pr = self._arr(action), self._arr(push_rand)
+        fn = getattr(self.lib, "zbo_step" + self.suf)
+        rc = fn(ctypes.byref(self.model), ctypes.byref(self.opts), ctypes.byref(ps), ctypes.byref(self._state(state)),
+                a.ctypes.data_as(ctypes.c_void_p), None if pr is None else pr.ctypes.data_as(ctypes.c_void_p),
+                int(bool(push_per_substep)), ctypes.byref(self._out(out)), n, int(n_substeps), self.threads)
+        assert rc == 0, rc
+        return out
+
+    def forward(self, state, params=None, out=None):
+        n = state["qpos"].shape[0]
+        ps, keep = self._params(params)
+        fn = getattr(self.lib, "zbo_forward" + self.suf)
+        rc = fn(ctypes.byref(self.model), ctypes.byref(self.opts), ctypes.byref(ps), ctypes.byref(self._state(state)),
+                ctypes.byref(self._out(out)), n, self.threads)
+        assert rc == 0, rc
+        return out
+
+    def reset(self, state, reset_qpos, reset_qvel, reset_t_rem=None, done=None, params=None, out=None):
+        n = state["qpos"].shape[0]
+        ps, keep = self._params(params)
+        rq, rv, rt = self._arr(reset_qpos), self._arr(reset_qvel), self._arr(reset_t_rem)
+        dn = None if done is None else np.ascontiguousarray(done, dtype=np.uint8)
+        fn = getattr(self.lib, "zbo_reset" + self.suf)
+        rc = fn(ctypes.byref(self.model), ctypes.byref(self.opts), ctypes.byref(ps), ctypes.byref(self._state(state)),
+                None if dn is None else dn.ctypes.data_as(ctypes.c_void_p), rq.ctypes.data_as(ctypes.c_void_p),
+                rv.ctypes.data_as(ctypes.c_void_p), None if rt is None else rt.ctypes.data_as(ctypes.c_void_p),
+                ctypes.byref(self._out(out)), n, self.threads)
+        assert rc == 0, rc
+        return out
+
+    # ---- flop counters (count build only) ------------------------------------------------
+    def flops_reset(self):
+        self.lib.zbo_flops_reset()
+
+    def flops(self) -> dict[str, float]:
+        buf = (ctypes.c_double * len(STAGES))()
+        self.lib.zbo_flops_get(buf)
+        return dict(zip(STAGES, list(buf)))
