@@ -1,0 +1,1053 @@
+// zb_kernel.cuh — the fused Z-Bot physics step: ONE WARP PER ENVIRONMENT.
+//
+// What it replaces: ksim MjxEngine.step / reset (ksim 0.1.99, un-vendored:
+// /root/reference/uv.lock:1872-1873) around mjx.step (mujoco-mjx 3.3.4, uv.lock:2226-2227), with the
+// reference's own servo model fused in (/root/reference/train.py:1137-1196 trapezoidal_step,
+// :1242-1280 FeetechActuators.get_stateful_ctrl) and PushEvent (train.py:1459-1468).
+//
+// Lane mapping (ZB_NBODY + 6 == 32):
+//   lane b  in [0, 26)  : body b; if the body has a hinge joint the lane also owns that dof
+//   lane 26+a, a in [0,6): the six dofs of the free joint (base body = lane 1)
+//   lane r  in [0, 32)  : contact row r = pyramid edge (r & 3) of contact slot (r >> 2); box = r >> 4
+// Tree structure exploited: floating base + serial chains hanging off it (validated on the host).
+//   chain scans  : Hillis-Steele over contiguous body lanes with shfl_up / shfl_down
+//   mass matrix  : M = [[A, B^T], [B, C]], C block-diagonal per chain -> block Cholesky
+//                  (chain factors in parallel, Schur complement S = A - W^T W on the base lanes)
+//   constraints  : friction-loss / limit rows are single-entry rows owned by the dof lane; contact rows
+//                  are applied matrix-free: J[r, :] = w_r . cdof[:] (w_r = contact wrench direction), so
+//                  J v = w_r . V_foot(v) and J^T f = cdof . sum_r f_r w_r.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/zbphys.h"
+#include "zb_math.cuh"
+
+#define NQ ZB_NQ
+#define NV ZB_NV
+#define NU ZB_NU
+#define NB ZB_NBODY
+#define BL0 (32 - 6) /* first base-dof lane */
+#define CHD 6        /* dof positions per chain group (legs: 6, arms: 4) */
+#define ZB_WPB 4     /* warps (environments) per CTA */
+#define ZB_SCR 8     /* scratch floats per lane */
+
+static_assert(ZB_NBODY + 6 == 32, "lane mapping assumes 26 bodies + 6 free-joint dofs == one warp");
+
+#define MJ_MINVAL 1e-15f
+#define MJ_MINIMP 0.0001f
+#define MJ_MAXIMP 0.9999f
+
+enum { ZB_MODE_STEP = 0, ZB_MODE_FORWARD = 1, ZB_MODE_RESET = 2 };
+
+// Host-derived tables (zb_engine_create) living in device global memory next to the model.
+struct ZbDev {
+  ZbModel m;
+  ZbOpts o;
+  int cs[32], ce[32];   // body-chain start / end lane (self for world, base, base-dof lanes)
+  int gs[32], gp[32];   // dof-group start lane and my position in it (chains: cs; base dofs: BL0)
+  int gn[32];           // dof positions in my group (0: lane owns no dof)
+  int lane_dof[32];     // dof index owned by the lane, -1 none
+  int lane_act[32];     // actuator index driving that dof, -1 none
+  int lane_box[32];     // hinge lanes: foot box whose body descends from my dof, -1 none
+  int body_site[32];    // site carried by body lane, -1 none
+  int body_box[32];     // box geom carried by body lane, -1 none
+  float bpj[32][3];     // body_pos + R(body_quat) jnt_pos
+  float frame[9];       // make_frame(floor_normal): rows n, t1, t2
+  int box_site[ZB_NBOX];
+  int any_damping;
+};
+
+struct Factor {
+  float lc[CHD];  // row gp of the group's Cholesky factor (entries k <= gp)
+  float lt[CHD];  // column gp (entries k >= gp)
+  float inv;      // 1 / L[gp][gp]
+  float W[6];     // hinge lanes: row of W = L_c^-1 B
+};
+
+struct LSPoint {
+  float alpha, cost, d0, d1;
+};
+
+struct WarpEnv {
+  const ZbDev* D;
+  float* scr;  // per-warp scratch, 32 * ZB_SCR floats
+  int L;
+  // topology of this lane
+  int cs, ce, gs, gp, gn, dof, act, lbox, boxlane;
+  bool isbody, hinge, bdof, hasdof, chainbody;
+  // per-environment model (randomizers, train.py:1439-1455)
+  float mass, inertia[3], arm, damp, floss, q0, mu, mass_tot;
+  float spos[3], squat[4];
+  // state
+  float q, qv, warm, bq[7];
+  float apos, avel, atq, tgt, ctrl;
+  // kinematics
+  float xpos[3], xquat[4], xmat[9], xipos[3], xb[3], Rb[9], c0[3];
+  float cinert[10], cdof[6], cdofd[6], cvel[6], cb3[3][6];
+  float sxpos[3], sxmat[9];
+  // dynamics
+  float Bm[6], C[CHD];
+  Factor F0, F1;
+  float qfrc_smooth, qacc_smooth, act_force, qfrc_bias;
+  // constraint rows
+  bool fr_on, lm_on, c_on;
+  float fr_D, fr_rf, fr_f, fr_aref, lm_sign, lm_D, lm_aref, c_D, c_aref, w[6];
+  float cdist, cpos[3];
+  // solver
+  float qacc, Ma, grad, Mgrad, search, mv, qfrc_c;
+  float fr_ja, lm_ja, c_ja, fr_jv, lm_jv, c_jv, fr_force, lm_force, c_force;
+  float Wf[6];  // total contact wrench of my half's foot (row lanes)
+  float gauss, cost, prev_cost;
+  int niter;
+
+  // ------------------------------------------------------------------------------------------
+  ZB_DI void init_topology(const ZbDev* D_, float* scr_, int lane) {
+    D = D_; scr = scr_; L = lane;
+    isbody = L < NB;
+    const int jt = isbody ? D->m.body_jnttype[L] : 0;
+    hinge = jt == 2;
+    bdof = L >= BL0;
+    cs = D->cs[L]; ce = D->ce[L]; gs = D->gs[L]; gp = D->gp[L]; gn = D->gn[L];
+    dof = D->lane_dof[L]; act = D->lane_act[L]; lbox = D->lane_box[L];
+    hasdof = dof >= 0;
+    chainbody = isbody && L >= 2;
+    boxlane = D->m.box_body[L >> 4];
+  }
+
+  // chain-scan helpers (bodies of one chain are contiguous lanes)
+  template <int N>
+  ZB_DI void chain_prefix(float (&v)[N]) {  // inclusive, root -> leaf
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+      const bool take = chainbody && (L - d >= cs);
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        const float u = __shfl_up_sync(ZB_FULL, v[k], d);
+        if (take) v[k] += u;
+      }
+    }
+  }
+  template <int N>
+  ZB_DI void chain_suffix(float (&v)[N]) {  // inclusive, leaf -> root
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+      const bool take = chainbody && (L + d <= ce);
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        const float u = __shfl_down_sync(ZB_FULL, v[k], d);
+        if (take) v[k] += u;
+      }
+    }
+  }
+
+  // spatial velocity of the base body produced by generalized base velocity vb[6] (uniform compute)
+  ZB_DI void base_motion(float* V, const float* vb) const {
+    float om[3], r[3], c[3];
+    mat_vec(om, Rb, vb + 3);
+    r[0] = c0[0] - xb[0]; r[1] = c0[1] - xb[1]; r[2] = c0[2] - xb[2];
+    cross3(c, om, r);
+    V[0] = om[0]; V[1] = om[1]; V[2] = om[2];
+    V[3] = vb[0] + c[0]; V[4] = vb[1] + c[1]; V[5] = vb[2] + c[2];
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // smooth.kinematics + smooth.com_pos
+  // ------------------------------------------------------------------------------------------
+  ZB_DI void kinematics() {
+    const ZbModel& m = D->m;
+    normalize4(bq + 3);  // MJX normalises the free-joint quaternion in qpos
+    xb[0] = bq[0]; xb[1] = bq[1]; xb[2] = bq[2];
+    quat_to_mat(Rb, bq + 3);
+    float lp[3] = {0.f, 0.f, 0.f}, lq[4] = {1.f, 0.f, 0.f, 0.f};
+    const int b = isbody ? L : 0;
+    if (chainbody) {
+      const float bqt[4] = {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]};
+      lp[0] = D->bpj[b][0]; lp[1] = D->bpj[b][1]; lp[2] = D->bpj[b][2];
+      if (hinge) {
+        float s, c;
+        sincosf((q - q0) * 0.5f, &s, &c);
+        const float aa[4] = {c, m.jnt_axis[b][0] * s, m.jnt_axis[b][1] * s, m.jnt_axis[b][2] * s};
+        quat_mul(lq, bqt, aa);
+        float R[9], r[3];
+        const float jp[3] = {m.jnt_pos[b][0], m.jnt_pos[b][1], m.jnt_pos[b][2]};
+        quat_to_mat(R, lq);
+        mat_vec(r, R, jp);
+        lp[0] -= r[0]; lp[1] -= r[1]; lp[2] -= r[2];
+      } else {
+        lq[0] = bqt[0]; lq[1] = bqt[1]; lq[2] = bqt[2]; lq[3] = bqt[3];
+      }
+    }
+    // compose local transforms down each chain (pointer doubling)
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+      float up[3], uq[4];
+#pragma unroll
+      for (int k = 0; k < 3; k++) up[k] = __shfl_up_sync(ZB_FULL, lp[k], d);
+#pragma unroll
+      for (int k = 0; k < 4; k++) uq[k] = __shfl_up_sync(ZB_FULL, lq[k], d);
+      if (chainbody && (L - d >= cs)) {
+        float R[9], r[3], nq[4];
+        quat_to_mat(R, uq);
+        mat_vec(r, R, lp);
+        lp[0] = up[0] + r[0]; lp[1] = up[1] + r[1]; lp[2] = up[2] + r[2];
+        quat_mul(nq, uq, lq);
+        lq[0] = nq[0]; lq[1] = nq[1]; lq[2] = nq[2]; lq[3] = nq[3];
+      }
+    }
+    if (chainbody) {
+      float r[3];
+      mat_vec(r, Rb, lp);
+      xpos[0] = xb[0] + r[0]; xpos[1] = xb[1] + r[1]; xpos[2] = xb[2] + r[2];
+      quat_mul(xquat, bq + 3, lq);
+      normalize4(xquat);
+    } else if (L == 1) {
+      xpos[0] = xb[0]; xpos[1] = xb[1]; xpos[2] = xb[2];
+      xquat[0] = bq[3]; xquat[1] = bq[4]; xquat[2] = bq[5]; xquat[3] = bq[6];
+    } else {
+      xpos[0] = xpos[1] = xpos[2] = 0.f;
+      xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f;
+    }
+    quat_to_mat(xmat, xquat);
+    {
+      const float ip[3] = {m.body_ipos[b][0], m.body_ipos[b][1], m.body_ipos[b][2]};
+      float r[3];
+      mat_vec(r, xmat, ip);
+      xipos[0] = xpos[0] + r[0]; xipos[1] = xpos[1] + r[1]; xipos[2] = xpos[2] + r[2];
+    }
+    // tree centre of mass (the only subtree_com the pipeline needs: body_rootid is the base)
+    {
+      float s[3] = {isbody ? mass * xipos[0] : 0.f, isbody ? mass * xipos[1] : 0.f, isbody ? mass * xipos[2] : 0.f};
+#pragma unroll
+      for (int k = 0; k < 3; k++) c0[k] = wsum(s[k]) / mass_tot;
+    }
+    // cinert about c0
+    {
+      float iq[4] = {1.f, 0.f, 0.f, 0.f}, qq[4], R[9];
+      if (isbody && L > 0) { iq[0] = m.body_iquat[b][0]; iq[1] = m.body_iquat[b][1]; iq[2] = m.body_iquat[b][2]; iq[3] = m.body_iquat[b][3]; }
+      quat_mul(qq, xquat, iq);
+      quat_to_mat(R, qq);
+      const float off[3] = {xipos[0] - c0[0], xipos[1] - c0[1], xipos[2] - c0[2]};
+      const float o2 = dot3(off, off);
+      const float I0 = inertia[0], I1 = inertia[1], I2 = inertia[2];
+      cinert[0] = R[0] * I0 * R[0] + R[1] * I1 * R[1] + R[2] * I2 * R[2] + mass * (o2 - off[0] * off[0]);
+      cinert[1] = R[3] * I0 * R[3] + R[4] * I1 * R[4] + R[5] * I2 * R[5] + mass * (o2 - off[1] * off[1]);
+      cinert[2] = R[6] * I0 * R[6] + R[7] * I1 * R[7] + R[8] * I2 * R[8] + mass * (o2 - off[2] * off[2]);
+      cinert[3] = R[0] * I0 * R[3] + R[1] * I1 * R[4] + R[2] * I2 * R[5] - mass * off[0] * off[1];
+      cinert[4] = R[0] * I0 * R[6] + R[1] * I1 * R[7] + R[2] * I2 * R[8] - mass * off[0] * off[2];
+      cinert[5] = R[3] * I0 * R[6] + R[4] * I1 * R[7] + R[5] * I2 * R[8] - mass * off[1] * off[2];
+      cinert[6] = off[0] * mass; cinert[7] = off[1] * mass; cinert[8] = off[2] * mass; cinert[9] = mass;
+      if (!isbody) {
+#pragma unroll
+        for (int k = 0; k < 10; k++) cinert[k] = 0.f;
+      }
+    }
+    // cdof.  The three rotational free-joint dofs are computed by every lane (uniform): cb3
+    {
+      const float r[3] = {c0[0] - xb[0], c0[1] - xb[1], c0[2] - xb[2]};
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const float col[3] = {Rb[i], Rb[3 + i], Rb[6 + i]};
+        float c[3];
+        cross3(c, col, r);
+        cb3[i][0] = col[0]; cb3[i][1] = col[1]; cb3[i][2] = col[2];
+        cb3[i][3] = c[0]; cb3[i][4] = c[1]; cb3[i][5] = c[2];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) cdof[k] = 0.f;
+      if (hinge) {
+        const float jp[3] = {m.jnt_pos[b][0], m.jnt_pos[b][1], m.jnt_pos[b][2]};
+        const float ax[3] = {m.jnt_axis[b][0], m.jnt_axis[b][1], m.jnt_axis[b][2]};
+        float a[3], an[3], c[3];
+        mat_vec(a, xmat, jp);
+        mat_vec(an, xmat, ax);
+        const float o[3] = {c0[0] - (xpos[0] + a[0]), c0[1] - (xpos[1] + a[1]), c0[2] - (xpos[2] + a[2])};
+        cross3(c, an, o);
+        cdof[0] = an[0]; cdof[1] = an[1]; cdof[2] = an[2]; cdof[3] = c[0]; cdof[4] = c[1]; cdof[5] = c[2];
+      } else if (bdof) {
+        const int a = L - BL0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          cdof[3 + i] = (a == i) ? 1.f : cdof[3 + i];
+#pragma unroll
+          for (int k = 0; k < 6; k++) cdof[k] = (a == 3 + i) ? cb3[i][k] : cdof[k];
+        }
+      }
+    }
+    // site carried by this body (imu_site pose is per-env)
+    if (isbody && D->body_site[L] >= 0) {
+      float r[3], qq[4];
+      mat_vec(r, xmat, spos);
+      sxpos[0] = xpos[0] + r[0]; sxpos[1] = xpos[1] + r[1]; sxpos[2] = xpos[2] + r[2];
+      quat_mul(qq, xquat, squat);
+      quat_to_mat(sxmat, qq);
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // smooth.crb + support.make_m in block form
+  // ------------------------------------------------------------------------------------------
+  ZB_DI void mass_matrix() {
+    float crb[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) crb[k] = cinert[k];
+    chain_suffix<10>(crb);
+    {
+      // composite inertia of the whole tree for the base dofs (world's cinert is zero)
+      float tot[16];
+#pragma unroll
+      for (int k = 0; k < 10; k++) tot[k] = cinert[k];
+#pragma unroll
+      for (int k = 10; k < 16; k++) tot[k] = 0.f;
+      reduce_scatter<16>(tot, L);  // lane L holds total of index L >> 1
+#pragma unroll
+      for (int k = 0; k < 10; k++) {
+        const float t = shf(tot[0], 2 * k);
+        if (bdof) crb[k] = t;
+      }
+    }
+    float f[6];
+    inert_mul(f, crb, cdof);
+    // chain block C: entries k <= gp from cdof of the ancestors, upper part by symmetry (scratch transpose)
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      float ck[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) ck[j] = shf(cdof[j], gs + k);
+      C[k] = (hinge && k <= gp) ? dot6(ck, f) : 0.f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHD; k++) scr[L * ZB_SCR + k] = C[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      const float t = scr[((gs + k) & 31) * ZB_SCR + gp];
+      if (hinge && k > gp && k < gn) C[k] = t;
+    }
+    __syncwarp();
+    // coupling to the base dofs (hinge lanes: B row; base lanes: A row)
+    Bm[0] = f[3]; Bm[1] = f[4]; Bm[2] = f[5];
+    Bm[3] = dot6(cb3[0], f); Bm[4] = dot6(cb3[1], f); Bm[5] = dot6(cb3[2], f);
+    if (!hasdof) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) Bm[k] = 0.f;
+    }
+    // armature on the diagonal
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      // (select form on purpose: `if (k == gp) C[k] += ..` gets turned into a dynamic index -> local memory)
+      C[k] += (hinge && k == gp) ? arm : 0.f;
+      Bm[k] += (bdof && k == gp) ? arm : 0.f;
+    }
+  }
+
+  // in-group right-looking Cholesky on the rows held in r[] (lower part), lanes gs..gs+gn-1
+  ZB_DI void group_chol(float (&r)[CHD], float& inv, bool valid) {
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      float d = shf(r[k], gs + k);
+      if (!(valid && k < gn)) d = 1.f;
+      const float lkk = sqrtf(d);
+      const float ik = 1.f / lkk;
+      const bool piv = valid && gp == k;
+      r[k] = piv ? lkk : ((valid && gp > k) ? r[k] * ik : r[k]);
+      inv = piv ? ik : inv;
+#pragma unroll
+      for (int j = k + 1; j < CHD; j++) {
+        const float ljk = shf(r[k], gs + j);
+        if (valid && gp >= j && j < gn) r[j] -= r[k] * ljk;
+      }
+    }
+  }
+
+  // smooth.factor_m as a block Cholesky of (M + diag(extra))
+  ZB_DI void factor(Factor& F, float extra) {
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      F.lc[k] = hinge ? C[k] + (k == gp ? extra : 0.f) : 0.f;
+      F.lt[k] = 0.f;
+    }
+    F.inv = 1.f;
+    group_chol(F.lc, F.inv, hinge);
+    // W = L_c^-1 B by forward substitution, six right-hand sides
+#pragma unroll
+    for (int a = 0; a < 6; a++) F.W[a] = hinge ? Bm[a] : 0.f;
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      if (hinge && gp == k) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) F.W[a] *= F.inv;
+      }
+      if (k < CHD - 1) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          const float wk = shf(F.W[a], gs + k);
+          if (hinge && gp > k && k < gn) F.W[a] -= F.lc[k] * wk;
+        }
+      }
+    }
+    // Schur complement S = A - W^T W: 21 unique sums over the hinge lanes, one result per lane
+    {
+      float p[32];
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = a; b < 6; b++) p[t++] = F.W[a] * F.W[b];
+#pragma unroll
+      for (int k = 21; k < 32; k++) p[k] = 0.f;
+      reduce_scatter<32>(p, L);  // lane t holds sum_t
+      const int a = bdof ? L - BL0 : 0;
+#pragma unroll
+      for (int b = 0; b < 6; b++) {
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        const int idx = lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);
+        const float s = shf(p[0], idx);
+        F.lc[b] = bdof ? Bm[b] - s + (b == gp ? extra : 0.f) : F.lc[b];
+      }
+    }
+    group_chol(F.lc, F.inv, bdof);
+    // column copies for the back substitutions
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHD; k++) scr[L * ZB_SCR + k] = F.lc[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      const float t = scr[((gs + k) & 31) * ZB_SCR + gp];
+      F.lt[k] = (hasdof && k >= gp && k < gn) ? t : 0.f;
+    }
+    __syncwarp();
+  }
+
+  // smooth.solve_m: x <- (M + diag)^-1 x, x distributed over the dof lanes
+  ZB_DI float solve(const Factor& F, float x) {
+    if (!hasdof) x = 0.f;
+    // chains: forward substitution
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      if (hinge && gp == k) x *= F.inv;
+      if (k < CHD - 1) {
+        const float yk = shf(x, gs + k);
+        if (hinge && gp > k && k < gn) x -= F.lc[k] * yk;
+      }
+    }
+    // base right-hand side: r_a - sum_i W_i[a] y_i
+    {
+      float p[8];
+#pragma unroll
+      for (int a = 0; a < 6; a++) p[a] = hinge ? F.W[a] * x : 0.f;
+      p[6] = p[7] = 0.f;
+      reduce_scatter<8>(p, L);  // lanes 4a..4a+3 hold total a
+      const float t = shf(p[0], bdof ? 4 * (L - BL0) : 0);
+      if (bdof) x -= t;
+    }
+    // base group: forward then backward (the backward pulls also broadcast x_base to every lane)
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      if (bdof && gp == k) x *= F.inv;
+      if (k < 5) {
+        const float yk = shf(x, BL0 + k);
+        if (bdof && gp > k) x -= F.lc[k] * yk;
+      }
+    }
+    float xbv[6];
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {
+      if (bdof && gp == k) x *= F.inv;
+      xbv[k] = shf(x, BL0 + k);
+      if (bdof && gp < k) x -= F.lt[k] * xbv[k];
+    }
+    // chains: remove the base coupling, backward substitution
+    if (hinge) {
+#pragma unroll
+      for (int a = 0; a < 6; a++) x -= F.W[a] * xbv[a];
+    }
+#pragma unroll
+    for (int k = CHD - 1; k >= 0; k--) {
+      if (hinge && gp == k) x *= F.inv;
+      if (k > 0) {
+        const float xk = shf(x, gs + k);
+        if (hinge && gp < k && k < gn) x -= F.lt[k] * xk;
+      }
+    }
+    return x;
+  }
+
+  // support.mul_m: y = M v; also returns the broadcast base part of v
+  ZB_DI float mul_m(float v, float (&vb)[6]) {
+    if (!hasdof) v = 0.f;
+#pragma unroll
+    for (int a = 0; a < 6; a++) vb[a] = shf(v, BL0 + a);
+    float y = 0.f;
+#pragma unroll
+    for (int a = 0; a < 6; a++) y += Bm[a] * vb[a];
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      const float vk = shf(v, gs + k);
+      if (hinge && k < gn) y += C[k] * vk;
+    }
+    float p[8];
+#pragma unroll
+    for (int a = 0; a < 6; a++) p[a] = hinge ? Bm[a] * v : 0.f;
+    p[6] = p[7] = 0.f;
+    reduce_scatter<8>(p, L);
+    const float t = shf(p[0], bdof ? 4 * (L - BL0) : 0);
+    if (bdof) y += t;
+    return hasdof ? y : 0.f;
+  }
+
+  // contact rows: jv[r] = w_r . V_box(v), V_box = spatial velocity of the box body under v
+  ZB_DI float contact_jv(float v, const float (&vb)[6]) {
+    float pre[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) pre[k] = hinge ? cdof[k] * v : 0.f;
+    chain_prefix<6>(pre);
+    float Vb[6], Vf[6];
+    base_motion(Vb, vb);
+#pragma unroll
+    for (int k = 0; k < 6; k++) Vf[k] = shf(pre[k], boxlane) + Vb[k];
+    return dot6(w, Vf);
+  }
+
+  // J^T f for the contact rows: per-box total wrench, projected on the dofs
+  ZB_DI float contact_jtf(float f) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      float t = c_on ? f * w[k] : 0.f;
+      t += shx(t, 8); t += shx(t, 4); t += shx(t, 2); t += shx(t, 1);
+      Wf[k] = t;
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const float mine = shf(Wf[k], lbox >= 0 ? 16 * lbox : 0);
+      const float both = Wf[k] + shx(Wf[k], 16);
+      if (hinge && lbox >= 0) r += cdof[k] * mine;
+      if (bdof) r += cdof[k] * both;
+    }
+    return r;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // smooth.com_vel (A.4), passive, smooth.rne (A.5)
+  // ------------------------------------------------------------------------------------------
+  float cvel_base[6], cacc_base_lin[3];
+  ZB_DI void velocity(float& qfrc_passive) {
+    float vb[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) vb[a] = shf(qv, BL0 + a);
+    base_motion(cvel_base, vb);
+    float pre[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) pre[k] = hinge ? cdof[k] * qv : 0.f;
+    chain_prefix<6>(pre);
+#pragma unroll
+    for (int k = 0; k < 6; k++) cvel[k] = (isbody && L >= 1) ? cvel_base[k] + (chainbody ? pre[k] : 0.f) : 0.f;
+    // cdof_dot: hinge = cvel(parent) x cdof == cvel(body) x cdof; free rotations = [0; v_lin] x cdof
+#pragma unroll
+    for (int k = 0; k < 6; k++) cdofd[k] = 0.f;
+    if (hinge) motion_cross(cdofd, cvel, cdof);
+    if (bdof && L - BL0 >= 3) {
+      const float u[6] = {0.f, 0.f, 0.f, vb[0], vb[1], vb[2]};
+      motion_cross(cdofd, u, cdof);
+    }
+    // base part of cacc (gravity + free-joint cdof_dot * qvel): [0; -g + v_lin x omega_world]
+    {
+      const float vl[3] = {vb[0], vb[1], vb[2]};
+      float c[3];
+      cross3(c, vl, cvel_base);
+      cacc_base_lin[0] = -D->o.gravity[0] + c[0];
+      cacc_base_lin[1] = -D->o.gravity[1] + c[1];
+      cacc_base_lin[2] = -D->o.gravity[2] + c[2];
+    }
+    qfrc_passive = hasdof ? -damp * qv : 0.f;
+  }
+
+  ZB_DI void bias_forces() {
+    float pre[6], cacc[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) pre[k] = hinge ? cdofd[k] * qv : 0.f;
+    chain_prefix<6>(pre);
+#pragma unroll
+    for (int k = 0; k < 6; k++) cacc[k] = chainbody ? pre[k] : 0.f;
+    if (L == 0) { cacc[3] = -D->o.gravity[0]; cacc[4] = -D->o.gravity[1]; cacc[5] = -D->o.gravity[2]; }
+    else if (isbody) { cacc[3] += cacc_base_lin[0]; cacc[4] += cacc_base_lin[1]; cacc[5] += cacc_base_lin[2]; }
+    float cfrc[6], t[6], u[6];
+    inert_mul(cfrc, cinert, cacc);
+    inert_mul(t, cinert, cvel);
+    motion_cross_force(u, cvel, t);
+#pragma unroll
+    for (int k = 0; k < 6; k++) cfrc[k] = isbody ? cfrc[k] + u[k] : 0.f;
+    float tot[8];
+#pragma unroll
+    for (int k = 0; k < 6; k++) tot[k] = (isbody && L >= 1) ? cfrc[k] : 0.f;
+    tot[6] = tot[7] = 0.f;
+    chain_suffix<6>(cfrc);
+    reduce_scatter<8>(tot, L);
+    float r = hinge ? dot6(cdof, cfrc) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const float tk = shf(tot[0], 4 * k);
+      if (bdof) r += cdof[k] * tk;
+    }
+    qfrc_bias = r;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // FeetechActuators.get_stateful_ctrl + trapezoidal_step (train.py:1137-1196, 1242-1280)
+  // ------------------------------------------------------------------------------------------
+  ZB_DI void actuator(float dt) {
+    if (act < 0) return;
+    const ZbModel& m = D->m;
+    const float vmax = m.servo_vmax[act], amax = m.servo_amax[act];
+    const float err = tgt - apos;
+    const float thr = err >= 0.f ? m.servo_deadband_pos : m.servo_deadband_neg;
+    const bool in_db = fabsf(err) <= thr;
+    const float db_v = avel * 0.8f;
+    const float db_p = apos + db_v * dt;
+    const float tdir = signf(err);
+    const float stop = fabsf(avel * avel) / (2.f * amax);
+    const float vdir = signf(avel);
+    const bool towards = vdir * tdir >= 0.f;
+    const bool accel = towards && fabsf(err) > stop;
+    float acc = accel ? tdir * amax : -vdir * amax;
+    if (fabsf(avel) < 1e-6f) acc = tdir * amax;
+    float pv = avel + acc * dt;
+    pv = clampf(pv, -vmax, vmax);
+    const float pp = apos + pv * dt;
+    avel = in_db ? db_v : pv;
+    apos = in_db ? db_p : pp;
+    const float perr = apos - q, verr = avel - qv;
+    float duty = m.servo_kp[act] * m.servo_error_gain[act] * perr + m.servo_kd[act] * verr;
+    duty = clampf(duty, -m.servo_max_pwm[act], m.servo_max_pwm[act]);
+    const float volts = duty * m.servo_vin[act];
+    atq = volts * m.servo_kt[act] / m.servo_R[act];
+    ctrl = atq;
+  }
+
+  // forward.fwd_actuation for motors (A.6)
+  ZB_DI float actuation() {
+    act_force = 0.f;
+    if (act < 0) return 0.f;
+    const ZbModel& m = D->m;
+    float c = ctrl;
+    if (m.act_ctrllimited[act]) c = clampf(c, m.act_ctrlrange[act][0], m.act_ctrlrange[act][1]);
+    float f = c;
+    if (m.act_forcelimited[act]) f = clampf(f, m.act_forcerange[act][0], m.act_forcerange[act][1]);
+    act_force = f;
+    return m.act_gear[act] * f;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // collision: plane_convex for the foot boxes + _manifold_points (A.7).  Every lane evaluates
+  // vertex (L & 7) of box (L >> 4); 8-lane groups pick the manifold; lane r then becomes row r.
+  // ------------------------------------------------------------------------------------------
+  ZB_DI int gargmax(float val, int idx) {
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+      const float ov = shx(val, d);
+      const int oi = __shfl_xor_sync(ZB_FULL, idx, d);
+      if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+    return idx;
+  }
+  ZB_DI void collision() {
+    const ZbModel& m = D->m;
+    const int g = L >> 4;
+    float gpos[3] = {0.f, 0.f, 0.f}, gmat[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    if (isbody && D->body_box[L] >= 0) {
+      const int gb = D->body_box[L];
+      const float bp[3] = {m.box_pos[gb][0], m.box_pos[gb][1], m.box_pos[gb][2]};
+      const float bqq[4] = {m.box_quat[gb][0], m.box_quat[gb][1], m.box_quat[gb][2], m.box_quat[gb][3]};
+      float r[3], qq[4];
+      mat_vec(r, xmat, bp);
+      gpos[0] = xpos[0] + r[0]; gpos[1] = xpos[1] + r[1]; gpos[2] = xpos[2] + r[2];
+      quat_mul(qq, xquat, bqq);
+      quat_to_mat(gmat, qq);
+    }
+    float bp[3], bm[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) bp[k] = shf(gpos[k], boxlane);
+#pragma unroll
+    for (int k = 0; k < 9; k++) bm[k] = shf(gmat[k], boxlane);
+    const float pn[3] = {m.floor_normal[0], m.floor_normal[1], m.floor_normal[2]};
+    const float rel[3] = {m.floor_pos[0] - bp[0], m.floor_pos[1] - bp[1], m.floor_pos[2] - bp[2]};
+    float ppl[3], nl[3];
+    matT_vec(ppl, bm, rel);
+    matT_vec(nl, bm, pn);
+    const float sz[3] = {m.box_size[g][0], m.box_size[g][1], m.box_size[g][2]};
+#define ZB_VERT(o, i) { o[0] = ((i) & 4) ? sz[0] : -sz[0]; o[1] = ((i) & 2) ? sz[1] : -sz[1]; o[2] = ((i) & 1) ? sz[2] : -sz[2]; }
+#define ZB_SUPPORT(vv) ((ppl[0] - vv[0]) * nl[0] + (ppl[1] - vv[1]) * nl[1] + (ppl[2] - vv[2]) * nl[2])
+    const int v = L & 7;
+    float pv[3];
+    ZB_VERT(pv, v);
+    const float sup = ZB_SUPPORT(pv);
+    float smax = sup;
+    smax = fmaxf(smax, shx(smax, 1)); smax = fmaxf(smax, shx(smax, 2)); smax = fmaxf(smax, shx(smax, 4));
+    const float thr = fmaxf(0.f, smax - 1e-3f);
+    const float dm = sup > thr ? 0.f : -1e6f;
+    const int ia = gargmax(dm, v);
+    float a[3]; ZB_VERT(a, ia);
+    const float ap[3] = {a[0] - pv[0], a[1] - pv[1], a[2] - pv[2]};
+    const int ib = gargmax(dot3(ap, ap) + dm, v);
+    float b[3]; ZB_VERT(b, ib);
+    const float amb[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    float ab[3]; cross3(ab, nl, amb);
+    const int ic = gargmax(fabsf(dot3(ap, ab)) + dm, v);
+    float c[3]; ZB_VERT(c, ic);
+    const float amc[3] = {a[0] - c[0], a[1] - c[1], a[2] - c[2]}, bmc[3] = {b[0] - c[0], b[1] - c[1], b[2] - c[2]};
+    float ac[3], bc[3];
+    cross3(ac, nl, amc); cross3(bc, nl, bmc);
+    const float bpv[3] = {b[0] - pv[0], b[1] - pv[1], b[2] - pv[2]};
+    const float v1 = fabsf(dot3(bpv, bc)) + dm, v2 = fabsf(dot3(ap, ac)) + dm;
+    const int id = gargmax(v2 > v1 ? v2 : v1, v2 > v1 ? 8 + v : v) & 7;
+    // this lane as contact row: slot s of box g
+    const int s = (L >> 2) & 3;
+    const int mi = s == 0 ? ia : (s == 1 ? ib : (s == 2 ? ic : id));
+    const bool uniq = s == 0 ? true : (s == 1 ? ib != ia : (s == 2 ? (ic != ia && ic != ib) : (id != ia && id != ib && id != ic)));
+    float mvv[3]; ZB_VERT(mvv, mi);
+    const float dist = uniq ? -ZB_SUPPORT(mvv) : 1.f;
+    float vw[3];
+    mat_vec(vw, bm, mvv);
+    cdist = dist;
+    cpos[0] = bp[0] + vw[0] - 0.5f * dist * pn[0];
+    cpos[1] = bp[1] + vw[1] - 0.5f * dist * pn[1];
+    cpos[2] = bp[2] + vw[2] - 0.5f * dist * pn[2];
+#undef ZB_VERT
+#undef ZB_SUPPORT
+  }
+
+  // constraint._kbi + row finish (A.8)
+  ZB_DI void kbi(const float* solref, const float* solimp, float pos, float& k, float& b, float& imp) const {
+    float timeconst = fmaxf(solref[0], 2.f * D->o.dt);
+    const float dampratio = solref[1];
+    const float dmin = clampf(solimp[0], MJ_MINIMP, MJ_MAXIMP), dmax = clampf(solimp[1], MJ_MINIMP, MJ_MAXIMP);
+    const float width = fmaxf(MJ_MINVAL, solimp[2]);
+    const float mid = clampf(solimp[3], MJ_MINIMP, MJ_MAXIMP);
+    const float power = fmaxf(1.f, solimp[4]);
+    k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+    b = 2.f / (dmax * timeconst);
+    if (solref[0] <= 0.f) { k = -solref[0] / (dmax * dmax); b = -solref[1] / dmax; }
+    const float x = fabsf(pos) / width;
+    float y;
+    if (power == 2.f) {
+      y = x < mid ? (1.f / mid) * (x * x) : 1.f - (1.f / (1.f - mid)) * ((1.f - x) * (1.f - x));
+    } else {
+      y = x < mid ? (1.f / powf(mid, power - 1.f)) * powf(x, power) : 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+    }
+    imp = dmin + y * (dmax - dmin);
+    imp = clampf(imp, dmin, dmax);
+    if (x > 1.f) imp = dmax;
+  }
+
+  ZB_DI void make_constraint() {
+    const ZbModel& m = D->m;
+    const int d = hasdof ? dof : 0;
+    // friction-loss row of my dof
+    fr_on = hasdof && m.dof_frictionloss[d] > 0.f;
+    fr_D = 0.f; fr_rf = 0.f; fr_f = 0.f; fr_aref = 0.f;
+    if (fr_on) {
+      const float sr[2] = {m.dof_solref[d][0], m.dof_solref[d][1]};
+      const float si[5] = {m.dof_solimp[d][0], m.dof_solimp[d][1], m.dof_solimp[d][2], m.dof_solimp[d][3], m.dof_solimp[d][4]};
+      float k, b, imp;
+      kbi(sr, si, 0.f, k, b, imp);
+      const float R = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, MJ_MINVAL);
+      fr_D = 1.f / R;
+      fr_f = floss;
+      fr_rf = R * floss;
+      fr_aref = -b * qv;
+    }
+    // joint-limit row of my hinge
+    lm_on = false; lm_D = 0.f; lm_aref = 0.f; lm_sign = 1.f;
+    if (hinge && m.jnt_limited[d]) {
+      const float dmin = q - m.jnt_range[d][0], dmax = m.jnt_range[d][1] - q;
+      const float pos = fminf(dmin, dmax) - m.jnt_margin[d];
+      if (pos < 0.f) {
+        const float sr[2] = {m.jnt_solref[d][0], m.jnt_solref[d][1]};
+        const float si[5] = {m.jnt_solimp[d][0], m.jnt_solimp[d][1], m.jnt_solimp[d][2], m.jnt_solimp[d][3], m.jnt_solimp[d][4]};
+        float k, b, imp;
+        kbi(sr, si, pos, k, b, imp);
+        lm_on = true;
+        lm_sign = dmin < dmax ? 1.f : -1.f;
+        const float R = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, MJ_MINVAL);
+        lm_D = 1.f / R;
+        lm_aref = -b * (lm_sign * qv) - k * imp * pos;
+      }
+    }
+    // contact row r = L: pyramid edge (L & 3) of slot (L >> 2)
+    {
+      const int g = L >> 4;
+      const float margin = fmaxf(m.floor_margin, m.box_margin[g]), gap = fmaxf(m.floor_gap, m.box_gap[g]);
+      const bool floor_wins = m.floor_priority >= m.box_priority[g];
+      float cmu = floor_wins ? mu : m.box_friction[g][0];
+      if (m.floor_priority == m.box_priority[g]) cmu = fmaxf(mu, m.box_friction[g][0]);
+      const float* srp = m.floor_priority >= m.box_priority[g] ? m.floor_solref : m.box_solref[g];
+      const float* sip = m.floor_priority >= m.box_priority[g] ? m.floor_solimp : m.box_solimp[g];
+      const float dist = cdist - (margin - gap);
+      c_on = dist < 0.f;
+      const int e = L & 3;
+      const float sgn = (e & 1) ? -1.f : 1.f;
+      const float* fr = D->frame;
+      const float* tt = fr + 3 * (1 + (e >> 1));
+      const float dir[3] = {fr[0] + sgn * cmu * tt[0], fr[1] + sgn * cmu * tt[1], fr[2] + sgn * cmu * tt[2]};
+      const float off[3] = {cpos[0] - c0[0], cpos[1] - c0[1], cpos[2] - c0[2]};
+      float tq[3];
+      cross3(tq, off, dir);
+      w[0] = tq[0]; w[1] = tq[1]; w[2] = tq[2]; w[3] = dir[0]; w[4] = dir[1]; w[5] = dir[2];
+      // velocity of the box body (needs velocity() first)
+      float vf[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) vf[k] = shf(cvel[k], boxlane);
+      c_D = 0.f; c_aref = 0.f;
+      if (c_on) {
+        const float sr[2] = {srp[0], srp[1]};
+        const float si[5] = {sip[0], sip[1], sip[2], sip[3], sip[4]};
+        float k, b, imp;
+        kbi(sr, si, dist, k, b, imp);
+        const float t = m.body_invweight0[0][0] + m.body_invweight0[m.box_body[g]][0];
+        const float invweight = (t + cmu * cmu * t) * 2.f * cmu * cmu / D->o.impratio;
+        const float R = fmaxf(invweight * (1.f - imp) / imp, MJ_MINVAL);
+        c_D = 1.f / R;
+        c_aref = -b * dot6(w, vf) - k * imp * dist;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // solver.solve, CG (A.9)
+  // ------------------------------------------------------------------------------------------
+  // row costs/forces at the current Jaref; returns this lane's partial constraint cost
+  ZB_DI float row_update() {
+    float cst = 0.f;
+    fr_force = 0.f; lm_force = 0.f; c_force = 0.f;
+    if (fr_on) {
+      const float x = fr_ja;
+      if (x <= -fr_rf && fr_f > 0.f) { fr_force = fr_f; cst += fr_f * (-0.5f * fr_rf - x); }
+      else if (x >= fr_rf && fr_f > 0.f) { fr_force = -fr_f; cst += fr_f * (-0.5f * fr_rf + x); }
+      else { fr_force = -fr_D * x; cst += 0.5f * fr_D * x * x; }
+    }
+    if (lm_on && lm_ja < 0.f) { lm_force = -lm_D * lm_ja; cst += 0.5f * lm_D * lm_ja * lm_ja; }
+    if (c_on && c_ja < 0.f) { c_force = -c_D * c_ja; cst += 0.5f * c_D * c_ja * c_ja; }
+    return cst;
+  }
+  // Context.create without gradient: Jaref, Ma and the cost at qacc = a
+  ZB_DI void ctx_create(float a, float& Ma_, float& frja, float& lmja, float& cja, float& cost_) {
+    float vb[6];
+    Ma_ = mul_m(a, vb);
+    const float cj = contact_jv(a, vb);
+    frja = a - fr_aref;
+    lmja = lm_sign * a - lm_aref;
+    cja = cj - c_aref;
+    const float s1 = fr_ja, s2 = lm_ja, s3 = c_ja;
+    fr_ja = frja; lm_ja = lmja; c_ja = cja;
+    float part = row_update();
+    fr_ja = s1; lm_ja = s2; c_ja = s3;
+    if (hasdof) part += 0.5f * (Ma_ - qfrc_smooth) * (a - qacc_smooth);
+    cost_ = wsum(part);
+  }
+  ZB_DI void update_constraint() {
+    float part = row_update();
+    float g = hasdof ? 0.5f * (Ma - qfrc_smooth) * (qacc - qacc_smooth) : 0.f;
+    // two sums: gauss is needed separately by the line search
+    float p2[2] = {part, g};
+    reduce_scatter<2>(p2, L);
+    const float csum = shf(p2[0], 0), gsum = shf(p2[0], 16);
+    gauss = gsum;
+    prev_cost = cost;
+    cost = gsum + csum;
+    const float jt = contact_jtf(c_force);
+    qfrc_c = hasdof ? jt + (fr_on ? fr_force : 0.f) + (lm_on ? lm_sign * lm_force : 0.f) : 0.f;
+  }
+  ZB_DI void update_gradient() {
+    grad = hasdof ? Ma - qfrc_smooth - qfrc_c : 0.f;
+    Mgrad = solve(F0, grad);
+  }
+  ZB_DI LSPoint ls_point(float alpha, const float (&qg)[3]) {
+    float q0_ = 0.f, q1 = 0.f, q2 = 0.f;
+    if (fr_on) {
+      const float x0 = fr_ja, jv = fr_jv, x = x0 + alpha * jv;
+      if (x <= -fr_rf && fr_f > 0.f) { q0_ += fr_f * (-0.5f * fr_rf - x0); q1 += -fr_f * jv; }
+      else if (x >= fr_rf && fr_f > 0.f) { q0_ += fr_f * (-0.5f * fr_rf + x0); q1 += fr_f * jv; }
+      else { q0_ += 0.5f * fr_D * x0 * x0; q1 += fr_D * x0 * jv; q2 += 0.5f * fr_D * jv * jv; }
+    }
+    if (lm_on && (lm_ja + alpha * lm_jv) < 0.f) { q0_ += 0.5f * lm_D * lm_ja * lm_ja; q1 += lm_D * lm_ja * lm_jv; q2 += 0.5f * lm_D * lm_jv * lm_jv; }
+    if (c_on && (c_ja + alpha * c_jv) < 0.f) { q0_ += 0.5f * c_D * c_ja * c_ja; q1 += c_D * c_ja * c_jv; q2 += 0.5f * c_D * c_jv * c_jv; }
+    float p[4] = {q0_, q1, q2, 0.f};
+    reduce_scatter<4>(p, L);  // lanes 8k..8k+7 hold total k
+    const float t0 = shf(p[0], 0) + qg[0], t1 = shf(p[0], 8) + qg[1], t2 = shf(p[0], 16) + qg[2];
+    LSPoint r;
+    r.alpha = alpha;
+    r.cost = alpha * alpha * t2 + alpha * t1 + t0;
+    r.d0 = 2.f * alpha * t2 + t1;
+    r.d1 = 2.f * t2 + (t2 == 0.f ? MJ_MINVAL : 0.f);
+    return r;
+  }
+  static ZB_DI bool in_bracket(float x, float y) { return (x < y && y < 0.f) || (x > y && y > 0.f); }
+
+  ZB_DI void linesearch() {
+    const ZbOpts& o = D->o;
+    float vb[6];
+    mv = mul_m(search, vb);
+    c_jv = contact_jv(search, vb);
+    fr_jv = search;
+    lm_jv = lm_sign * search;
+    float p[4] = {search * search, search * Ma - search * qfrc_smooth, search * mv, 0.f};
+    if (!hasdof) { p[0] = p[1] = p[2] = 0.f; }
+    reduce_scatter<4>(p, L);
+    const float snorm = shf(p[0], 0);
+    const float qg[3] = {gauss, shf(p[0], 8), 0.5f * shf(p[0], 16)};
+    const float smag = sqrtf(snorm) * D->m.meaninertia * (float)NV;
+    const float gtol = o.tolerance * o.ls_tolerance * smag;
+    const LSPoint p0 = ls_point(0.f, qg);
+    LSPoint lo = ls_point(p0.alpha - p0.d0 / p0.d1, qg), hi;
+    if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+    bool swap = true;
+    int it = 0;
+    while (true) {
+      bool done = it >= o.ls_iterations;
+      done |= !swap;
+      done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
+      done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
+      if (done) break;
+      const LSPoint lo_next = ls_point(lo.alpha - lo.d0 / lo.d1, qg);
+      const LSPoint hi_next = ls_point(hi.alpha - hi.d0 / hi.d1, qg);
+      const LSPoint mid = ls_point(0.5f * (lo.alpha + hi.alpha), qg);
+      const bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
+      const bool s2 = in_bracket(lo.d0, mid.d0); if (s2) lo = mid;
+      const bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) lo = hi_next;
+      const bool s4 = in_bracket(hi.d0, hi_next.d0); if (s4) hi = hi_next;
+      const bool s5 = in_bracket(hi.d0, mid.d0); if (s5) hi = mid;
+      const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) hi = lo_next;
+      swap = s1 | s2 | s3 | s4 | s5 | s6;
+      it++;
+    }
+    const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+    const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+    if (improved) {
+      qacc += search * alpha;
+      Ma += mv * alpha;
+      fr_ja += fr_jv * alpha;
+      lm_ja += lm_jv * alpha;
+      c_ja += c_jv * alpha;
+    }
+  }
+
+  ZB_DI void solve_constraints() {
+    const ZbOpts& o = D->o;
+    // warm start: the cheaper of qacc_warmstart and qacc_smooth
+    float Ma_s, fj_s, lj_s, cj_s, cost_s;
+    ctx_create(qacc_smooth, Ma_s, fj_s, lj_s, cj_s, cost_s);
+    qacc = qacc_smooth; Ma = Ma_s; fr_ja = fj_s; lm_ja = lj_s; c_ja = cj_s;
+    if (o.warmstart) {
+      float Ma_w, fj_w, lj_w, cj_w, cost_w;
+      ctx_create(warm, Ma_w, fj_w, lj_w, cj_w, cost_w);
+      if (cost_w < cost_s) { qacc = hasdof ? warm : 0.f; Ma = Ma_w; fr_ja = fj_w; lm_ja = lj_w; c_ja = cj_w; }
+    }
+    cost = INFINITY; prev_cost = 0.f; niter = 0;
+    update_constraint();
+    update_gradient();
+    search = -Mgrad;
+    const float scale = 1.f / (D->m.meaninertia * (float)NV);
+    while (true) {
+      const float improvement = scale * (prev_cost - cost);
+      const float gradient = scale * sqrtf(wsum(grad * grad));
+      bool done = niter >= o.iterations;
+      done |= improvement < o.tolerance;
+      done |= gradient < o.tolerance;
+      if (done) break;
+      linesearch();
+      const float pg = grad, pMg = Mgrad;
+      update_constraint();
+      update_gradient();
+      float p2[2] = {grad * (Mgrad - pMg), pg * pMg};
+      reduce_scatter<2>(p2, L);
+      const float num = shf(p2[0], 0), den = shf(p2[0], 16);
+      const float beta = fmaxf(0.f, num / fmaxf(MJ_MINVAL, den));
+      search = -Mgrad + beta * search;
+      niter++;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // sensors + rne_postconstraint (A.11); only evaluated when outputs are written
+  // ------------------------------------------------------------------------------------------
+  ZB_DI void sensors(float* sd /* global [18] or nullptr */) {
+    if (!sd) return;
+    const ZbModel& m = D->m;
+    // cacc with qacc: base part uniform, chain part by prefix scan
+    float ab[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) ab[a] = shf(qacc, BL0 + a);
+    float Ab[6];
+    base_motion(Ab, ab);  // sum_a cdof_a qacc_a
+    float pre[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) pre[k] = hinge ? cdofd[k] * qv + cdof[k] * qacc : 0.f;
+    chain_prefix<6>(pre);
+    float cacc[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cacc[k] = (chainbody ? pre[k] : 0.f) + Ab[k];
+    cacc[3] += cacc_base_lin[0]; cacc[4] += cacc_base_lin[1]; cacc[5] += cacc_base_lin[2];
+    if (L == 0) { cacc[0] = cacc[1] = cacc[2] = 0.f; cacc[3] = -D->o.gravity[0]; cacc[4] = -D->o.gravity[1]; cacc[5] = -D->o.gravity[2]; }
+    // cfrc_int = local - cfrc_ext, accumulated leaf -> root along the chains
+    float cf[6], t[6], u[6];
+    inert_mul(cf, cinert, cacc);
+    inert_mul(t, cinert, cvel);
+    motion_cross_force(u, cvel, t);
+    const int mybox = isbody ? D->body_box[L] : -1;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const float ext = shf(Wf[k], mybox >= 0 ? 16 * mybox : 0);
+      cf[k] = isbody ? cf[k] + u[k] - (mybox >= 0 ? ext : 0.f) : 0.f;
+    }
+    chain_suffix<6>(cf);
+    const int s = isbody ? D->body_site[L] : -1;
+    if (s == 0) {  // imu_site: framequat, accelerometer, gyro
+      float qq[4];
+      quat_mul(qq, xquat, squat);
+      normalize4(qq);
+      sd[ZB_SENS_IMU_QUAT + 0] = qq[0]; sd[ZB_SENS_IMU_QUAT + 1] = qq[1]; sd[ZB_SENS_IMU_QUAT + 2] = qq[2]; sd[ZB_SENS_IMU_QUAT + 3] = qq[3];
+      float gy[3];
+      matT_vec(gy, sxmat, cvel);
+      sd[ZB_SENS_IMU_GYRO + 0] = gy[0]; sd[ZB_SENS_IMU_GYRO + 1] = gy[1]; sd[ZB_SENS_IMU_GYRO + 2] = gy[2];
+      const float diff[3] = {sxpos[0] - c0[0], sxpos[1] - c0[1], sxpos[2] - c0[2]};
+      float ang[3], lin[3], acc[3], tt[3], uu[3], corr[3];
+      matT_vec(ang, sxmat, cvel);
+      cross3(tt, diff, cvel);
+      uu[0] = cvel[3] - tt[0]; uu[1] = cvel[4] - tt[1]; uu[2] = cvel[5] - tt[2];
+      matT_vec(lin, sxmat, uu);
+      cross3(tt, diff, cacc);
+      uu[0] = cacc[3] - tt[0]; uu[1] = cacc[4] - tt[1]; uu[2] = cacc[5] - tt[2];
+      matT_vec(acc, sxmat, uu);
+      cross3(corr, ang, lin);
+      sd[ZB_SENS_IMU_ACC + 0] = acc[0] + corr[0]; sd[ZB_SENS_IMU_ACC + 1] = acc[1] + corr[1]; sd[ZB_SENS_IMU_ACC + 2] = acc[2] + corr[2];
+    }
+    if (s == 1 || s == 2) {  // foot force sensors
+      float fo[3];
+      matT_vec(fo, sxmat, cf + 3);
+      const int o = s == 1 ? ZB_SENS_FORCE_L : ZB_SENS_FORCE_R;
+      sd[o] = fo[0]; sd[o + 1] = fo[1]; sd[o + 2] = fo[2];
+    }
+    // touch: normal force (= sum of the four edge forces) of my half's contacts that lie inside the site box
+    {
+      const int g = L >> 4;
+      const int ts = D->box_site[g];
+      const int sl = ts >= 0 ? m.site_body[ts] : 0;
+      float sp[3], sm[9];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sp[k] = shf(sxpos[k], sl);
+#pragma unroll
+      for (int k = 0; k < 9; k++) sm[k] = shf(sxmat[k], sl);
+      float val = 0.f;
+      if (ts >= 0 && c_on) {
+        const float rel[3] = {cpos[0] - sp[0], cpos[1] - sp[1], cpos[2] - sp[2]};
+        float loc[3];
+        matT_vec(loc, sm, rel);
+        if (fabsf(loc[0]) <= m.site_size[ts][0] && fabsf(loc[1]) <= m.site_size[ts][1] && fabsf(loc[2]) <= m.site_size[ts][2]) val = c_force;
+      }
+      val += shx(val, 8); val += shx(val, 4); val += shx(val, 2); val += shx(val, 1);
+      if ((L & 15) == 0 && ts >= 0) sd[ts == 1 ? ZB_SENS_TOUCH_L : ZB_SENS_TOUCH_R] = val;
+    }
+  }
+};

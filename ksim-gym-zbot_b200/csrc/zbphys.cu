@@ -1,0 +1,464 @@
+// zbphys.cu — kernels + the C ABI of include/zbphys.h (libzbphys.so).
+//
+// Drop-in boundary for ksim's MjxEngine.reset/step (ksim 0.1.99 ksim/engine.py, un-vendored:
+// /root/reference/uv.lock:1872-1873).  Plain C entry points, caller-owned device memory, no torch.
+// There is NO CPU fallback: without a CUDA device zb_engine_create returns ZB_ENODEV.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "../../include/zbphys.h"
+#include "zb_kernel.cuh"
+
+#define ZB_ABI_VERSION 1
+
+struct ZbEngine {
+  ZbDev host;
+  ZbDev* dev;
+  int device;
+};
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(ZB_WPB * 32) zb_kernel(const ZbDev* __restrict__ D, ZbEnvParams P, ZbState S,
+                                                       const float* __restrict__ action, const float* __restrict__ push_rand,
+                                                       int push_per_substep, ZbOut O, int n_envs, int n_substeps,
+                                                       const uint8_t* __restrict__ done, const float* __restrict__ rq,
+                                                       const float* __restrict__ rv, const float* __restrict__ rt) {
+  __shared__ float scratch[ZB_WPB][32 * ZB_SCR];
+  const int L = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int env = blockIdx.x * ZB_WPB + wib;
+  if (env >= n_envs) return;
+  if (MODE == ZB_MODE_RESET && done && !done[env]) return;
+  const ZbModel& m = D->m;
+  const ZbOpts& o = D->o;
+  WarpEnv E;
+  E.init_topology(D, scratch[wib], L);
+  const int b = E.isbody ? L : 0;
+  const int d = E.hasdof ? E.dof : 0;
+  // ---- per-environment model (randomizers, train.py:1439-1455) ----
+  E.mass = E.isbody ? (P.body_mass ? P.body_mass[(size_t)env * NB + b] : m.body_mass[b]) : 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    E.inertia[k] = E.isbody ? (P.body_inertia ? P.body_inertia[((size_t)env * NB + b) * 3 + k] : m.body_inertia[b][k]) : 0.f;
+  E.arm = E.hasdof ? (P.dof_armature ? P.dof_armature[(size_t)env * NV + d] : m.dof_armature[d]) : 0.f;
+  E.damp = E.hasdof ? (P.dof_damping ? P.dof_damping[(size_t)env * NV + d] : m.dof_damping[d]) : 0.f;
+  E.floss = E.hasdof ? (P.dof_frictionloss ? P.dof_frictionloss[(size_t)env * NV + d] : m.dof_frictionloss[d]) : 0.f;
+  E.q0 = E.hinge ? (P.qpos0 ? P.qpos0[(size_t)env * NQ + d + 1] : m.qpos0[d + 1]) : 0.f;
+  E.mu = P.floor_friction ? P.floor_friction[env] : m.floor_friction[0];
+  E.mass_tot = wsum(E.mass);
+  {
+    const int s = E.isbody ? D->body_site[L] : -1;
+    const int ss = s >= 0 ? s : 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) E.spos[k] = (s == 0 && P.imu_site_pos) ? P.imu_site_pos[(size_t)env * 3 + k] : m.site_pos[ss][k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) E.squat[k] = (s == 0 && P.imu_site_quat) ? P.imu_site_quat[(size_t)env * 4 + k] : m.site_quat[ss][k];
+  }
+  // ---- state ----
+  const float* qsrc = MODE == ZB_MODE_RESET ? rq : S.qpos;
+  const float* vsrc = MODE == ZB_MODE_RESET ? rv : S.qvel;
+#pragma unroll
+  for (int k = 0; k < 7; k++) E.bq[k] = qsrc[(size_t)env * NQ + k];
+  E.q = E.hinge ? qsrc[(size_t)env * NQ + d + 1] : 0.f;
+  E.qv = E.hasdof ? vsrc[(size_t)env * NV + d] : 0.f;
+  E.warm = (MODE != ZB_MODE_RESET && E.hasdof && S.qacc_warmstart) ? S.qacc_warmstart[(size_t)env * NV + d] : 0.f;
+  const int a = E.act >= 0 ? E.act : 0;
+  E.apos = E.avel = E.atq = E.tgt = E.ctrl = 0.f;
+  if (E.act >= 0) {
+    if (MODE == ZB_MODE_RESET) {  // get_initial_state train.py:1293-1298
+      E.apos = E.q; E.avel = E.qv; E.atq = 0.f;
+    } else {
+      E.apos = S.act_pos[(size_t)env * NU + a]; E.avel = S.act_vel[(size_t)env * NU + a]; E.atq = S.act_torque[(size_t)env * NU + a];
+    }
+    if (MODE == ZB_MODE_STEP) E.tgt = action[(size_t)env * NU + a];
+    if (MODE == ZB_MODE_FORWARD) E.ctrl = E.atq;
+  }
+  float trem = 0.f, tm = 0.f;
+  if (MODE == ZB_MODE_STEP) {
+    trem = S.push_t_rem ? S.push_t_rem[env] : 0.f;
+    tm = S.time ? S.time[env] : 0.f;
+  }
+  const float dt = o.dt;
+  const bool implicit_damp = o.integrator == ZB_INT_IMPLICITFAST || (o.integrator == ZB_INT_EULER && o.eulerdamp && D->any_damping);
+  const int nsub = MODE == ZB_MODE_STEP ? n_substeps : 1;
+  float* sd = O.sensordata ? O.sensordata + (size_t)env * ZB_NSENSORDATA : nullptr;
+
+  for (int s = 0; s < nsub; s++) {
+    const bool last = s == nsub - 1;
+    if (MODE == ZB_MODE_STEP) {
+#pragma unroll
+      for (int phase = 0; phase < 2; phase++) {
+        const bool do_event = (o.substep_order == ZB_ORDER_EVENT_ACT_STEP) ? phase == 0 : phase == 1;
+        if (do_event) {
+          if (push_rand && S.push_t_rem) {  // PushEvent (train.py:1459-1468)
+            const float* pr = push_rand + ((size_t)env * (push_per_substep ? n_substeps : 1) + (push_per_substep ? s : 0)) * 7;
+            float t = trem - dt;
+            if (t <= 0.f) {
+              if (E.bdof) E.qv += pr[L - BL0];
+              t = pr[6];
+            }
+            trem = t;
+          }
+        } else {
+          E.actuator(dt);
+        }
+      }
+    }
+    // ---- mjx.forward ----
+    E.kinematics();
+    E.mass_matrix();
+    E.factor(E.F0, 0.f);
+    if (implicit_damp && MODE == ZB_MODE_STEP) E.factor(E.F1, dt * E.damp);
+    E.collision();
+    float qfrc_passive;
+    E.velocity(qfrc_passive);
+    E.make_constraint();
+    E.bias_forces();
+    const float qfrc_act = E.actuation();
+    E.qfrc_smooth = E.hasdof ? qfrc_passive - E.qfrc_bias + qfrc_act : 0.f;
+    E.qacc_smooth = E.solve(E.F0, E.qfrc_smooth);
+    E.solve_constraints();
+    if (last) E.sensors(sd);
+    if (MODE == ZB_MODE_STEP) {
+      // ---- euler / implicitfast + _advance ----
+      float qa = E.qacc;
+      if (implicit_damp) qa = E.solve(E.F1, E.qfrc_smooth + E.qfrc_c);
+      if (E.hasdof) E.qv += dt * qa;
+      if (E.hinge) E.q += dt * E.qv;
+      float vb[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) vb[k] = shf(E.qv, BL0 + k);
+      E.bq[0] += dt * vb[0]; E.bq[1] += dt * vb[1]; E.bq[2] += dt * vb[2];
+      {  // math.quat_integrate
+        const float n = sqrtf(vb[3] * vb[3] + vb[4] * vb[4] + vb[5] * vb[5]);
+        const float sc = 1.f / (n + 1e-6f * (n == 0.f));
+        float sn, cs;
+        sincosf(dt * n * 0.5f, &sn, &cs);
+        const float qr[4] = {cs, vb[3] * sc * sn, vb[4] * sc * sn, vb[5] * sc * sn};
+        float q2[4];
+        quat_mul(q2, E.bq + 3, qr);
+        normalize4(q2);
+        E.bq[3] = q2[0]; E.bq[4] = q2[1]; E.bq[5] = q2[2]; E.bq[6] = q2[3];
+      }
+      E.warm = E.qacc;
+      tm += dt;
+    }
+  }
+
+  // ---- state write-back ----
+  {  // base pose (MJX writes the normalised free-joint quaternion back into qpos, also in forward())
+    float v = E.bq[0];
+#pragma unroll
+    for (int k = 1; k < 7; k++) v = (L == k) ? E.bq[k] : v;
+    if (L < 7) S.qpos[(size_t)env * NQ + L] = v;
+  }
+  if (MODE != ZB_MODE_FORWARD) {
+    if (E.hinge) S.qpos[(size_t)env * NQ + d + 1] = E.q;
+    if (E.hasdof) {
+      S.qvel[(size_t)env * NV + d] = E.qv;
+      if (S.qacc_warmstart) S.qacc_warmstart[(size_t)env * NV + d] = MODE == ZB_MODE_RESET ? 0.f : E.warm;
+    }
+    if (E.act >= 0) {
+      S.act_pos[(size_t)env * NU + a] = E.apos; S.act_vel[(size_t)env * NU + a] = E.avel; S.act_torque[(size_t)env * NU + a] = E.atq;
+    }
+    if (L == 0) {
+      if (S.push_t_rem) S.push_t_rem[env] = MODE == ZB_MODE_RESET ? (rt ? rt[env] : 0.f) : trem;
+      if (S.time) S.time[env] = MODE == ZB_MODE_RESET ? 0.f : tm;
+    }
+  }
+  // ---- outputs: mjx.Data fields as forward() of the last substep left them ----
+  if (E.isbody) {
+    if (O.xpos) { float* p = O.xpos + ((size_t)env * NB + L) * 3; p[0] = E.xpos[0]; p[1] = E.xpos[1]; p[2] = E.xpos[2]; }
+    if (O.xquat) { float* p = O.xquat + ((size_t)env * NB + L) * 4; p[0] = E.xquat[0]; p[1] = E.xquat[1]; p[2] = E.xquat[2]; p[3] = E.xquat[3]; }
+    if (O.cinert) {
+      float* p = O.cinert + ((size_t)env * NB + L) * 10;
+#pragma unroll
+      for (int k = 0; k < 10; k++) p[k] = E.cinert[k];
+    }
+    if (O.cvel) {
+      float* p = O.cvel + ((size_t)env * NB + L) * 6;
+#pragma unroll
+      for (int k = 0; k < 6; k++) p[k] = E.cvel[k];
+    }
+    const int st = D->body_site[L];
+    if (st >= 0) {
+      if (O.site_xpos) { float* p = O.site_xpos + ((size_t)env * ZB_NSITE + st) * 3; p[0] = E.sxpos[0]; p[1] = E.sxpos[1]; p[2] = E.sxpos[2]; }
+      if (O.site_xmat) {
+        float* p = O.site_xmat + ((size_t)env * ZB_NSITE + st) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; k++) p[k] = E.sxmat[k];
+      }
+    }
+  }
+  if (E.hasdof) {
+    if (O.qacc) O.qacc[(size_t)env * NV + d] = E.qacc;
+    if (O.qfrc_constraint) O.qfrc_constraint[(size_t)env * NV + d] = E.qfrc_c;
+    if (O.efc_force) {
+      O.efc_force[(size_t)env * (2 * NV + ZB_NEFC_CON) + d] = E.fr_force;
+      O.efc_force[(size_t)env * (2 * NV + ZB_NEFC_CON) + NV + d] = E.lm_force;
+    }
+  }
+  if (E.act >= 0) {
+    if (O.actuator_force) O.actuator_force[(size_t)env * NU + a] = E.act_force;
+    if (O.ctrl) O.ctrl[(size_t)env * NU + a] = E.ctrl;
+  }
+  if (O.efc_force) O.efc_force[(size_t)env * (2 * NV + ZB_NEFC_CON) + 2 * NV + L] = E.c_force;
+  if ((L & 3) == 0) {
+    if (O.contact_dist) O.contact_dist[(size_t)env * ZB_MAXCON + (L >> 2)] = E.cdist;
+    if (O.contact_pos) { float* p = O.contact_pos + ((size_t)env * ZB_MAXCON + (L >> 2)) * 3; p[0] = E.cpos[0]; p[1] = E.cpos[1]; p[2] = E.cpos[2]; }
+  }
+  {
+    const unsigned bal = __ballot_sync(ZB_FULL, E.c_on && (L & 3) == 0);
+    const bool bad = !(isfinite(E.q) && isfinite(E.qv) && isfinite(E.bq[0]) && isfinite(E.bq[1]) && isfinite(E.bq[2]) && isfinite(E.bq[3]));
+    const unsigned nb = __ballot_sync(ZB_FULL, bad);
+    if (L == 0) {
+      int mask = 0;
+#pragma unroll
+      for (int c = 0; c < ZB_MAXCON; c++) mask |= ((bal >> (4 * c)) & 1u) << c;
+      if (O.contact_mask) O.contact_mask[env] = mask;
+      if (O.solver_niter) O.solver_niter[env] = E.niter;
+      if (O.flags) O.flags[env] = nb ? 1 : 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: model validation + derived tables (what mjx.put_model + ksim.get_physics_engine do)
+// ---------------------------------------------------------------------------------------------
+static void h_quat_to_mat(float* m, const float* q) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+
+static int derive(ZbDev* D) {
+  const ZbModel& m = D->m;
+  if (m.body_jnttype[0] != 0 || m.body_jnttype[1] != 1 || m.body_parent[1] != 0 || m.body_dofadr[1] != 0)
+    return fail(ZB_EUNSUP, "model: body 1 must be the free-joint base attached to the world%s");
+  for (int L = 0; L < 32; L++) {
+    D->cs[L] = D->ce[L] = D->gs[L] = L;
+    D->gp[L] = 0; D->gn[L] = 0;
+    D->lane_dof[L] = D->lane_act[L] = D->lane_box[L] = D->body_site[L] = D->body_box[L] = -1;
+    D->bpj[L][0] = D->bpj[L][1] = D->bpj[L][2] = 0.f;
+  }
+  for (int a = 0; a < 6; a++) { D->lane_dof[BL0 + a] = a; D->gs[BL0 + a] = BL0; D->gp[BL0 + a] = a; D->gn[BL0 + a] = 6; }
+  // chains: every body b >= 2 hangs off the base or continues the chain of body b-1
+  for (int b = 2; b < NB; b++) {
+    if (m.body_jnttype[b] == 1) return fail(ZB_EUNSUP, "model: only one free joint supported%s");
+    if (m.body_parent[b] == 1) D->cs[b] = b;
+    else if (m.body_parent[b] == b - 1) D->cs[b] = D->cs[b - 1];
+    else return fail(ZB_EUNSUP, "model: tree must be a floating base with serial chains%s");
+  }
+  for (int b = NB - 1; b >= 2; b--) D->ce[b] = (b + 1 < NB && D->cs[b + 1] == D->cs[b]) ? D->ce[b + 1] : b;
+  for (int b = 2; b < NB; b++) {
+    if (D->ce[b] - D->cs[b] + 1 > 8) return fail(ZB_EUNSUP, "model: chains longer than 8 bodies unsupported%s");
+    float R[9];
+    h_quat_to_mat(R, m.body_quat[b]);
+    for (int r = 0; r < 3; r++)
+      D->bpj[b][r] = m.body_pos[b][r] + R[r * 3] * m.jnt_pos[b][0] + R[r * 3 + 1] * m.jnt_pos[b][1] + R[r * 3 + 2] * m.jnt_pos[b][2];
+    if (m.body_jnttype[b] == 2) {
+      const int pos = b - D->cs[b];
+      if (pos >= CHD) return fail(ZB_EUNSUP, "model: more than 6 hinge dofs in one chain%s");
+      // every body between the chain start and a hinge body must carry a hinge (contiguous dof positions)
+      for (int c = D->cs[b]; c < b; c++)
+        if (m.body_jnttype[c] != 2) return fail(ZB_EUNSUP, "model: jointless body inside a chain before a hinge%s");
+      D->lane_dof[b] = m.body_dofadr[b];
+      D->gs[b] = D->cs[b]; D->gp[b] = pos;
+      if (m.dof_body[m.body_dofadr[b]] != b) return fail(ZB_EINVAL, "model: dof_body inconsistent%s");
+    }
+  }
+  for (int b = 2; b < NB; b++)
+    if (m.body_jnttype[b] == 2) {
+      int n = 0;
+      for (int c = D->cs[b]; c <= D->ce[b]; c++) n += m.body_jnttype[c] == 2;
+      D->gn[b] = n;
+    }
+  for (int j = 0; j < NU; j++) {
+    const int dof = m.act_dof[j];
+    if (dof < 6 || dof >= NV) return fail(ZB_EINVAL, "model: act_dof out of range%s");
+    D->lane_act[m.dof_body[dof]] = j;
+  }
+  for (int g = 0; g < ZB_NBOX; g++) {
+    const int bb = m.box_body[g];
+    if (bb < 2 || bb >= NB) return fail(ZB_EUNSUP, "model: foot box must sit on a chain body%s");
+    if (D->body_box[bb] >= 0) return fail(ZB_EUNSUP, "model: one box per body%s");
+    D->body_box[bb] = g;
+    for (int c = D->cs[bb]; c <= bb; c++)
+      if (m.body_jnttype[c] == 2) {
+        if (D->lane_box[c] >= 0) return fail(ZB_EUNSUP, "model: one box per chain%s");
+        D->lane_box[c] = g;
+      }
+    D->box_site[g] = -1;
+  }
+  for (int s = 0; s < ZB_NSITE; s++) {
+    const int sb = m.site_body[s];
+    if (sb < 1 || sb >= NB || D->body_site[sb] >= 0) return fail(ZB_EUNSUP, "model: one site per (non-world) body%s");
+    D->body_site[sb] = s;
+    if (s > 0 && D->body_box[sb] >= 0) D->box_site[D->body_box[sb]] = s;
+  }
+  {  // math.make_frame(floor_normal)
+    float a[3] = {m.floor_normal[0], m.floor_normal[1], m.floor_normal[2]};
+    float n = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (!(n > 0)) return fail(ZB_EINVAL, "model: floor_normal is zero%s");
+    for (int k = 0; k < 3; k++) a[k] /= n;
+    float bb[3] = {0, 0, 0};
+    if (-0.5f < a[1] && a[1] < 0.5f) bb[1] = 1; else bb[2] = 1;
+    const float ab = a[0] * bb[0] + a[1] * bb[1] + a[2] * bb[2];
+    for (int k = 0; k < 3; k++) bb[k] -= a[k] * ab;
+    n = sqrtf(bb[0] * bb[0] + bb[1] * bb[1] + bb[2] * bb[2]);
+    for (int k = 0; k < 3; k++) bb[k] /= n;
+    const float c[3] = {a[1] * bb[2] - a[2] * bb[1], a[2] * bb[0] - a[0] * bb[2], a[0] * bb[1] - a[1] * bb[0]};
+    for (int k = 0; k < 3; k++) { D->frame[k] = a[k]; D->frame[3 + k] = bb[k]; D->frame[6 + k] = c[k]; }
+  }
+  D->any_damping = 0;
+  for (int i = 0; i < NV; i++) D->any_damping |= m.dof_damping[i] > 0;
+  return ZB_OK;
+}
+
+static int check_opts(const ZbOpts* o) {
+  if (!(o->dt > 0) || o->iterations < 0 || o->ls_iterations < 0 || !(o->impratio > 0)) return fail(ZB_EINVAL, "opts: dt/iterations/impratio invalid%s");
+  if (o->solver != ZB_SOLVER_CG) return fail(ZB_EUNSUP, "opts: only ZB_SOLVER_CG is built into the kernels%s");
+  if (o->integrator != ZB_INT_EULER && o->integrator != ZB_INT_IMPLICITFAST) return fail(ZB_EINVAL, "opts: unknown integrator%s");
+  if (o->substep_order != ZB_ORDER_EVENT_ACT_STEP && o->substep_order != ZB_ORDER_ACT_EVENT_STEP) return fail(ZB_EINVAL, "opts: unknown substep_order%s");
+  return ZB_OK;
+}
+
+extern "C" {
+
+int zb_abi_version(void) { return ZB_ABI_VERSION; }
+int zb_sizeof_model(void) { return (int)sizeof(ZbModel); }
+int zb_sizeof_opts(void) { return (int)sizeof(ZbOpts); }
+const char* zb_last_error(void) { return g_err; }
+long long zb_launch_count(void) { return g_launches.load(); }
+
+int zb_engine_create(const ZbModel* model, const ZbOpts* opts, int device, ZbEngine** out) {
+  if (!model || !opts || !out) return fail(ZB_EINVAL, "zb_engine_create: null argument%s");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(ZB_ENODEV, "zb_engine_create: no CUDA device (there is no CPU fallback)%s");
+  }
+  if (device < 0 || device >= ndev) return fail(ZB_EINVAL, "zb_engine_create: bad device index%s");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(ZB_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(cudaGetLastError()));
+  if (prop.major != 10) return fail(ZB_ENODEV, "zb_engine_create: kernels are built for sm_100a only%s");
+  int rc = check_opts(opts);
+  if (rc) return rc;
+  ZbEngine* e = new (std::nothrow) ZbEngine;
+  if (!e) return fail(ZB_EINVAL, "out of host memory%s");
+  memset(&e->host, 0, sizeof(e->host));
+  e->host.m = *model;
+  e->host.o = *opts;
+  e->device = device;
+  e->dev = nullptr;
+  rc = derive(&e->host);
+  if (rc) { delete e; return rc; }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  cudaError_t ce = cudaMalloc(&e->dev, sizeof(ZbDev));
+  if (ce == cudaSuccess) ce = cudaMemcpy(e->dev, &e->host, sizeof(ZbDev), cudaMemcpyHostToDevice);
+  cudaSetDevice(prev);
+  if (ce != cudaSuccess) {
+    if (e->dev) cudaFree(e->dev);
+    delete e;
+    return fail(ZB_ECUDA, "zb_engine_create: %s", cudaGetErrorString(ce));
+  }
+  *out = e;
+  return ZB_OK;
+}
+
+int zb_engine_destroy(ZbEngine* e) {
+  if (!e) return ZB_OK;
+  if (e->dev) cudaFree(e->dev);
+  delete e;
+  return ZB_OK;
+}
+
+int zb_engine_set_opts(ZbEngine* e, const ZbOpts* opts) {
+  if (!e || !opts) return fail(ZB_EINVAL, "zb_engine_set_opts: null argument%s");
+  int rc = check_opts(opts);
+  if (rc) return rc;
+  e->host.o = *opts;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(e->device);
+  cudaError_t ce = cudaMemcpy(&e->dev->o, &e->host.o, sizeof(ZbOpts), cudaMemcpyHostToDevice);
+  cudaSetDevice(prev);
+  if (ce != cudaSuccess) return fail(ZB_ECUDA, "zb_engine_set_opts: %s", cudaGetErrorString(ce));
+  return ZB_OK;
+}
+
+static int check_state(const ZbState* s) {
+  if (!s || !s->qpos || !s->qvel || !s->act_pos || !s->act_vel || !s->act_torque) return fail(ZB_EINVAL, "state: qpos/qvel/act_* must be non-null%s");
+  return ZB_OK;
+}
+static int after_launch(const char* what) {
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(ZB_ECUDA, what, cudaGetErrorString(ce));
+  g_launches.fetch_add(1);
+  return ZB_OK;
+}
+
+int zb_step_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
+                const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps) {
+  if (!e || !action) return fail(ZB_EINVAL, "zb_step_f32: null engine/action%s");
+  if (n_envs < 0 || n_substeps < 1) return fail(ZB_EINVAL, "zb_step_f32: n_envs >= 0 and n_substeps >= 1 required%s");
+  int rc = check_state(state);
+  if (rc) return rc;
+  if (n_envs == 0) return ZB_OK;
+  ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
+  ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
+  const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
+  zb_kernel<ZB_MODE_STEP><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, P, *state, action, push_rand, push_per_substep, O,
+                                                                         n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr);
+  return after_launch("zb_step_f32 launch: %s");
+}
+
+int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const ZbOut* out, int n_envs) {
+  if (!e) return fail(ZB_EINVAL, "zb_forward_f32: null engine%s");
+  if (n_envs < 0) return fail(ZB_EINVAL, "zb_forward_f32: n_envs < 0%s");
+  int rc = check_state(state);
+  if (rc) return rc;
+  if (n_envs == 0) return ZB_OK;
+  ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
+  ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
+  const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
+  zb_kernel<ZB_MODE_FORWARD><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+                                                                            nullptr, nullptr, nullptr, nullptr);
+  return after_launch("zb_forward_f32 launch: %s");
+}
+
+int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const uint8_t* done,
+                 const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem, const ZbOut* out, int n_envs) {
+  if (!e || !reset_qpos || !reset_qvel) return fail(ZB_EINVAL, "zb_reset_f32: null engine/reset_qpos/reset_qvel%s");
+  if (n_envs < 0) return fail(ZB_EINVAL, "zb_reset_f32: n_envs < 0%s");
+  int rc = check_state(state);
+  if (rc) return rc;
+  if (n_envs == 0) return ZB_OK;
+  ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
+  ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
+  const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
+  zb_kernel<ZB_MODE_RESET><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
+                                                                          reset_qpos, reset_qvel, reset_t_rem);
+  return after_launch("zb_reset_f32 launch: %s");
+}
+
+}  // extern "C"
