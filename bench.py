@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — Z-Bot physics env-steps/s on B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (default N=1)
+    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host cores (oracle port)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU, weak scaling
+
+A "step" is ONE CONTROL STEP of the whole batch: S fused physics substeps (PushEvent -> Feetech servo -> mjx.step)
+in one kernel launch, followed by the termination check and the partial reset of finished environments — the body of
+ksim's rollout scan around the engine.  One env-step = one physics substep of one environment.
+Default workload = BASELINE.json configs[1]: 4096 envs, random actions, ctrl_dt = 0.02 s with 4 substeps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "zbot_physics_env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)  # rollout length of the reference: 4.0 s / 0.02 s (train.py:1775)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="BASELINE.json configs[1] / configs[2]")
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="0 = 4096 (c2) / 16384 (c3)")
+    ap.add_argument("--substeps", type=int, default=4, help="physics substeps per control step (BASELINE config: 4; train.py:1777: 20)")
+    ap.add_argument("--ctrl-dt", type=float, default=0.02)
+    ap.add_argument("--solver-iterations", type=int, default=8)
+    ap.add_argument("--ls-iterations", type=int, default=8)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+# -------------------------------------------------------------------------------------------------
+# clocks sampler (recipe: /opt/skills/guides/B200_PROFILING.md)
+# -------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------------------------------------
+# workload pieces shared by both arms
+# -------------------------------------------------------------------------------------------------
+def workload_config(a):
+    n = a.envs_per_gpu or (4096 if a.workload == "c2" else 16384)
+    return n
+
+
+def cpu_oracle_rate(model, opts, state_np, actions_np, S, params, seconds, threads, push_rand=None):
+    """env-steps/s of the fp32 oracle (OpenMP over environments) on a bounded sample."""
+    import zb_oracle
+
+    o = zb_oracle.Oracle(model, opts, np.float32, threads=threads)
+    st = {k: np.ascontiguousarray(v, dtype=np.float32).copy() for k, v in state_np.items()}
+    n = st["qpos"].shape[0]
+    o.step(st, actions_np[0], S, params=params)  # warm-up (page-in, thread pool)
+    t0, steps, i = time.perf_counter(), 0, 1
+    while True:
+        o.step(st, actions_np[i % len(actions_np)], S, params=params)
+        steps += 1
+        i += 1
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    return n * S * steps / dt, steps, dt
+
+
+def oracle_flops_per_env_step(model, opts, state_np, actions_np, S, params):
+    import zb_oracle
+
+    o = zb_oracle.Oracle(model, opts, np.float32, count=True, threads=1)
+    n = min(64, state_np["qpos"].shape[0])
+    st = {k: np.ascontiguousarray(v[:n], dtype=np.float32).copy() for k, v in state_np.items()}
+    pp = {k: v[:n] for k, v in params.items()} if params else None
+    out = o.new_out(n)
+    o.flops_reset()
+    o.step(st, actions_np[0][:n], S, params=pp, out=out)
+    fl = o.flops()
+    return sum(fl.values()) / (n * S), {k: v / (n * S) for k, v in fl.items()}, float(out["solver_niter"].mean())
+
+
+# bytes per control step per env that MUST cross HBM: state in/out + action + per-env model + outputs
+def algorithmic_bytes_per_ctrl_step(randomized: bool, push: bool) -> int:
+    state = 27 + 26 + 26 + 60 + 2  # qpos qvel warmstart planner(3x20) t_rem time
+    rd = state + 20 + (7 if push else 0) + (165 if randomized else 0)
+    wr = state + (78 + 104 + 260 + 156 + 26 + 26 + 20 + 20 + 18 + 9 + 27 + 8 + 24 + 84 + 3)  # every ZbOut array
+    return 4 * (rd + wr)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    S = a.substeps
+    n_env = workload_config(a)
+    import ksim_gym_zbot_b200  # noqa: F401
+    from ksim_gym_zbot_b200 import model as M
+
+    model = M.build_zbot_syn()
+    opts = M.make_opts(dt=a.ctrl_dt / S, iterations=a.solver_iterations, ls_iterations=a.ls_iterations)
+    randomized = a.workload == "c3"
+    config = {
+        "workload": ("BASELINE.json configs[1]: Z-Bot 4096 envs random-action rollout, ctrl_dt=0.02, 4 substeps" if a.workload == "c2"
+                     else "BASELINE.json configs[2]: Z-Bot 16384 envs, push + friction/mass randomization + resets"),
+        "model": "zbot_syn v1 (synthetic Z-Bot topology; the real MJCF is not shipped with the reference)",
+        "envs_per_gpu": n_env, "substeps": S, "dt": a.ctrl_dt / S, "ctrl_dt": a.ctrl_dt, "solver": "cg",
+        "iterations": a.solver_iterations, "ls_iterations": a.ls_iterations, "integrator": "implicitfast",
+        "actions": "bias + 0.3*U(-1,1), torch Philox seed %d" % a.seed, "terminations": "z in [0.05,0.5], tilt<60deg -> in-place reset",
+        "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "parallelism": f"dp{world} (envs sharded, no collective in the physics step)",
+    }
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        run_reference(a, model, opts, S, n_env, randomized, config, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the physics step has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ksim_gym_zbot_b200.engine import EnvParams, PushEventConfig, ZbotCudaEngine
+
+    push_cfg = PushEventConfig() if randomized else None
+    eng = ZbotCudaEngine(model, n_env, device=local, opts=opts, ctrl_dt=a.ctrl_dt, push=push_cfg, seed=a.seed + rank)
+    params_np = M.randomize_env_params(model, n_env, a.seed + 100 + rank) if randomized else None
+    ep = EnvParams(n_env, dev, **params_np) if randomized else None
+    K, W = a.steps, a.warmup
+    g = torch.Generator(device=dev)
+    g.manual_seed(a.seed + rank)
+    bias = torch.tensor(M.BIAS_POSE, dtype=torch.float32, device=dev)
+    actions = bias + 0.3 * (torch.rand((K + W, n_env, M.NU), generator=g, device=dev) * 2 - 1)
+    pushes = torch.stack([eng.sample_push(n_env) for _ in range(K + W)]) if randomized else None
+    rq, rv, rt = eng.sample_reset(n_env)
+    ps = eng.reset(ep, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
+    done = torch.zeros((n_env,), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n_done = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def ctrl_step(t, act):
+        eng.step(act, ep, ps, push_rand=None if pushes is None else pushes[t])
+        eng.terminations(ps, done)
+        eng.reset(ep, physics_state=ps, done=done, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
+
+    for t in range(W):
+        ctrl_step(t, actions[t])
+    torch.cuda.synchronize()
+    # snapshot for the CPU baseline: the state distribution the timed region starts from
+    snap = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        ns = min(512, n_env)
+        snap = {"qpos": ps.data.qpos[:ns].cpu().numpy(), "qvel": ps.data.qvel[:ns].cpu().numpy(),
+                "qacc_warmstart": ps.data.qacc_warmstart[:ns].cpu().numpy(), "act_pos": ps.actuator_state.position[:ns].cpu().numpy(),
+                "act_vel": ps.actuator_state.velocity[:ns].cpu().numpy(), "act_torque": ps.actuator_state.last_computed_torque[:ns].cpu().numpy(),
+                "push_t_rem": np.full(ns, 1e9, np.float32), "time": np.zeros(ns, np.float32)}
+        snap_actions = actions[W:W + 8, :ns].cpu().numpy()
+
+    # ---------------- timed region 1: inputs resident in HBM ----------------
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    launches0 = eng.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    niter_sum, ncon_sum, ndone = 0.0, 0.0, 0
+    for i in range(K):
+        t = W + i
+        flush.zero_()  # L2 flush, outside the event pair
+        ev[i][0].record()
+        eng.step(actions[t], ep, ps, push_rand=None if pushes is None else pushes[t])
+        ev[i][1].record()
+        eng.terminations(ps, done)
+        eng.reset(ep, physics_state=ps, done=done, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
+        ev[i][2].record()
+        n_done += done.sum()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.launch_count() - launches0
+    step_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
+    total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = world * n_env * S * K / (total_ms_max * 1e-3)
+    niter_mean = float(ps.data.solver_niter.float().mean().item())
+    ncon_mean = float(sum(((ps.data.contact_mask >> c) & 1).float().mean().item() for c in range(8)))
+    resets_per_step = float(n_done.item()) / K
+
+    # ---------------- timed region 2: end to end through the public API with HOST buffers ----------------
+    h_act = actions[W:W + K].cpu().pin_memory()
+    out_fields = ("qpos", "qvel", "xpos", "xquat", "cinert", "cvel", "qacc", "actuator_force", "sensordata")
+    h_out = {k: torch.empty_like(getattr(ps.data, k), device="cpu").pin_memory() for k in out_fields}
+    h_out["act_torque"] = torch.empty_like(ps.actuator_state.last_computed_torque, device="cpu").pin_memory()
+    h_done = torch.empty_like(done, device="cpu").pin_memory()
+    d_act = torch.empty((n_env, M.NU), dtype=torch.float32, device=dev)
+    h2d = h_act[0].numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in h_out.values()) + h_done.numel()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        d_act.copy_(h_act[i], non_blocking=True)
+        ctrl_step(W + i, d_act)
+        for k in out_fields:
+            h_out[k].copy_(getattr(ps.data, k), non_blocking=True)
+        h_out["act_torque"].copy_(ps.actuator_state.last_computed_torque, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result of step i before issuing step i+1
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_env * S * K / (float(e2e_ms.item()) * 1e-3)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------- FP32 peak probe (roofline denominator; not in MEASURED_PEAKS.json) ----------------
+    import ctypes
+
+    scratch = torch.empty(148 * 16 * 256, dtype=torch.float32, device=dev)
+    best = 0.0
+    for _ in range(4):
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        eng.lib.zb_bench_ffma(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), ctypes.c_void_p(scratch.data_ptr()), 148 * 16, 20000)
+        p1.record()
+        torch.cuda.synchronize()
+        best = max(best, 148 * 16 * 256 * 20000 * 32 / (p0.elapsed_time(p1) * 1e-3) / 1e12)
+    fp32_peak = best
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline + algorithmic flops (rank 0, N=1 only) ----------------
+    cpu, flops_per, flops_stage, niter_cpu = None, None, None, None
+    cores = os.cpu_count() or 1
+    if snap is not None:
+        sp = {k: v[:snap["qpos"].shape[0]] for k, v in params_np.items()} if params_np else None
+        rate, nst, secs = cpu_oracle_rate(model, opts, snap, snap_actions, S, sp, a.cpu_baseline_seconds, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{snap['qpos'].shape[0]} envs x {nst} control steps ({secs:.1f} s) from the bench's post-warm-up state, fp32 oracle, OpenMP",
+               "note": "CPU restatement (MJX/JAX not installable in this image)"}
+        flops_per, flops_stage, niter_cpu = oracle_flops_per_env_step(model, opts, snap, snap_actions, S, sp)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_ctrl = algorithmic_bytes_per_ctrl_step(randomized, randomized)
+    step_s = step_ms * 1e-3 / K  # average duration of the dominant kernel (zb_kernel<STEP>)
+    roof = {
+        "bound": "fp32", "unit": "TFLOP/s", "kernel": "zb_kernel<ZB_MODE_STEP>",
+        "achieved": None if flops_per is None else flops_per * n_env * S / step_s / 1e12,
+        "peak": fp32_peak, "peak_source": "measured in this run (FFMA probe zb_bench_ffma; MEASURED_PEAKS.json has no FP32 figure)",
+        "frac": None if flops_per is None else flops_per * n_env * S / step_s / 1e12 / fp32_peak,
+        "traffic": None, "flops_per_env_step": flops_per, "flops_source": "oracle op counters (fp32, 64-env sample of this workload)",
+        "kernel_ms_per_launch": step_ms / K, "kernel_share_of_step": step_ms / total_ms,
+        "hbm": {"bound": "hbm", "unit": "GB/s", "achieved": bytes_ctrl * n_env / step_s / 1e9, "peak": hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "frac": bytes_ctrl * n_env / step_s / 1e9 / hbm_peak,
+                "bytes_per_env_ctrl_step": bytes_ctrl},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        "stats": {"solver_niter_mean_last_step": niter_mean, "active_contacts_mean_last_step": ncon_mean, "resets_per_step": resets_per_step,
+                  "ctrl_steps_per_s": value / S, "solver_niter_mean_cpu_sample": niter_cpu, "flops_per_stage": flops_stage},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(a, model, opts, S, n_env, randomized, config, world):
+    """The reference arm: the reference's algorithm for this path on the host cores.  MJX/JAX cannot be installed here
+    (no wheels, no network), so this times the oracle port (oracle/zb_oracle.c, fp32, OpenMP over environments)."""
+    from ksim_gym_zbot_b200 import model as M
+
+    cores = os.cpu_count() or 1
+    n = min(512, n_env)  # bounded sample of the workload per step
+    import zb_oracle
+
+    o = zb_oracle.Oracle(model, opts, np.float32, threads=cores)
+    rng = np.random.default_rng(a.seed)
+    st = o.new_state(n)
+    q = np.repeat(M.default_qpos(model)[None], n, 0).astype(np.float32)
+    v = np.zeros((n, M.NV), np.float32)
+    v[:, 6:] = rng.uniform(-0.01, 0.01, (n, M.NU))
+    params = {k: x for k, x in M.randomize_env_params(model, n, a.seed + 100).items()} if randomized else None
+    o.reset(st, q, v, np.full(n, 1e9, np.float32), params=params)
+    K, W = a.steps, a.warmup
+    acts = (M.BIAS_POSE[None, None] + 0.3 * rng.uniform(-1, 1, (K + W, n, M.NU))).astype(np.float32)
+
+    def term(s):
+        qq = s["qpos"]
+        up = qq[:, 3] ** 2 - qq[:, 4] ** 2 - qq[:, 5] ** 2 + qq[:, 6] ** 2
+        return ((qq[:, 2] < 0.05) | (qq[:, 2] > 0.5) | (up < 0.5) | ~np.isfinite(qq[:, 2])).astype(np.uint8)
+
+    def ctrl_step(t):
+        o.step(st, acts[t], S, params=params)
+        d = term(st)
+        if d.any():
+            o.reset(st, q, v, np.full(n, 1e9, np.float32), done=d, params=params)
+
+    for t in range(W):
+        ctrl_step(t)
+    t0 = time.perf_counter()
+    for t in range(W, W + K):
+        ctrl_step(t)
+    dt = time.perf_counter() - t0
+    value = n * S * K / dt
+    sample = f"{n} envs per step (bounded sample of the {n_env}-env workload), {K} control steps, fp32 oracle port, OpenMP {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dt * 1e3 / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of mjx.step + MjxEngine.step (MJX/JAX/ksim not installable: no wheels, no network)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

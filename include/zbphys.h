@@ -35,6 +35,7 @@ extern "C" {
 #define ZB_NBOX 2         /* foot collision boxes vs. the floor plane         */
 #define ZB_MAXCON 8       /* 4 manifold slots per foot box (MJX plane_convex) */
 #define ZB_NEFC_CON (4 * ZB_MAXCON) /* pyramidal condim-3 rows                */
+#define ZB_NTRACE 128     /* solver_trace floats per environment              */
 #define ZB_NSENSORDATA 18 /* quat4 acc3 gyro3 touchL touchR forceL3 forceR3   */
 
 enum { ZB_SOLVER_CG = 0, ZB_SOLVER_NEWTON = 1 };
@@ -206,6 +207,7 @@ typedef struct ZbOut {
   int32_t* contact_mask;  /* [N] bit c set <=> contact slot c active (dist < margin)    */
   int32_t* solver_niter;  /* [N]                                                         */
   int32_t* flags;         /* [N] bit0: non-finite state detected                         */
+  float* solver_trace;    /* [N, ZB_NTRACE] diagnostics: per solver iteration i (alpha, cost, ls_iters, |search|) at 4i; from 32 on the (alpha, d0, d1) of every point the FIRST line search evaluates */
 } ZbOut;
 
 typedef struct ZbEngine ZbEngine; /* opaque: device copy of ZbModel + ZbOpts */
@@ -243,6 +245,16 @@ int zb_sizeof_opts(void);
 const char* zb_last_error(void);
 /* Number of kernel launches issued through this library since load (bench accounting). */
 long long zb_launch_count(void);
+
+/* ksim.BadZTermination(z_lo, z_hi) | ksim.NotUprightTermination(max_tilt) as the task configures them
+ * (/root/reference/train.py:1588-1593) plus the non-finite guard (flags from ZbOut, may be NULL): done[i] = 1 when
+ * environment i terminates.  Feeds zb_reset_f32's done mask without a host round trip. */
+int zb_terminations_f32(void* cuda_stream, const float* qpos, const int32_t* flags, uint8_t* done, int n_envs, float z_lo,
+                        float z_hi, float max_tilt_rad);
+
+/* FP32 FFMA throughput probe (bench.py: the FP32 roofline denominator).  Enqueues grid x 256 threads doing
+ * iters x 16 independent FMAs each; scratch needs grid * 256 floats.  flops = grid * 256 * iters * 32. */
+int zb_bench_ffma(void* cuda_stream, float* scratch, int grid, int iters);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,8 @@ struct WarpEnv {
   float Wf[6];  // total contact wrench of my half's foot (row lanes)
   float gauss, cost, prev_cost;
   int niter;
+  float* trace;  // optional global [ZB_NTRACE] solver trace (diagnostics), nullptr in production
+  int lscount;
 
   // ------------------------------------------------------------------------------------------
   ZB_DI void init_topology(const ZbDev* D_, float* scr_, int lane) {
@@ -878,9 +880,17 @@ struct WarpEnv {
     const float t0 = shf(p[0], 0) + qg[0], t1 = shf(p[0], 8) + qg[1], t2 = shf(p[0], 16) + qg[2];
     LSPoint r;
     r.alpha = alpha;
-    r.cost = alpha * alpha * t2 + alpha * t1 + t0;
-    r.d0 = 2.f * alpha * t2 + t1;
-    r.d1 = 2.f * t2 + (t2 == 0.f ? MJ_MINVAL : 0.f);
+    // NOT fused on purpose (__fmul_rn/__fadd_rn are never contracted into FMA): when the active set did not change, the
+    // Newton point alpha = -t1 / (2 t2) makes 2*alpha*t2 + t1 round to EXACTLY 0 with separately rounded products, and the
+    // reference's bracket logic treats an exact zero as "not in bracket" (the point is rejected).  An FMA would return the
+    // tiny residual instead and flip that decision in ~14 % of the states (tests/gpu_probe3.py).
+    r.cost = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(alpha, alpha), t2), __fmul_rn(alpha, t1)), t0);
+    r.d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, alpha), t2), t1);
+    r.d1 = __fadd_rn(__fmul_rn(2.f, t2), (t2 == 0.f ? MJ_MINVAL : 0.f));
+    if (trace && niter == 0 && L == 0 && 32 + 3 * lscount + 2 < ZB_NTRACE) {
+      trace[32 + 3 * lscount] = alpha; trace[32 + 3 * lscount + 1] = r.d0; trace[32 + 3 * lscount + 2] = r.d1;
+    }
+    lscount++;
     return r;
   }
   static ZB_DI bool in_bracket(float x, float y) { return (x < y && y < 0.f) || (x > y && y > 0.f); }
@@ -899,6 +909,7 @@ struct WarpEnv {
     const float qg[3] = {gauss, shf(p[0], 8), 0.5f * shf(p[0], 16)};
     const float smag = sqrtf(snorm) * D->m.meaninertia * (float)NV;
     const float gtol = o.tolerance * o.ls_tolerance * smag;
+    lscount = 0;
     const LSPoint p0 = ls_point(0.f, qg);
     LSPoint lo = ls_point(p0.alpha - p0.d0 / p0.d1, qg), hi;
     if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
@@ -924,6 +935,11 @@ struct WarpEnv {
     }
     const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
     const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+    if (trace && L == 0 && 4 * niter + 3 < ZB_NTRACE) {
+      trace[4 * niter] = improved ? alpha : 0.f;
+      trace[4 * niter + 2] = (float)it;
+      trace[4 * niter + 3] = sqrtf(snorm);
+    }
     if (improved) {
       qacc += search * alpha;
       Ma += mv * alpha;
@@ -959,6 +975,7 @@ struct WarpEnv {
       linesearch();
       const float pg = grad, pMg = Mgrad;
       update_constraint();
+      if (trace && L == 0 && 4 * niter + 3 < ZB_NTRACE) trace[4 * niter + 1] = cost;
       update_gradient();
       float p2[2] = {grad * (Mgrad - pMg), pg * pMg};
       reduce_scatter<2>(p2, L);

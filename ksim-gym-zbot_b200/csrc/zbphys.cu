@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zb_kernel(const ZbDev* __restrict
   const bool implicit_damp = o.integrator == ZB_INT_IMPLICITFAST || (o.integrator == ZB_INT_EULER && o.eulerdamp && D->any_damping);
   const int nsub = MODE == ZB_MODE_STEP ? n_substeps : 1;
   float* sd = O.sensordata ? O.sensordata + (size_t)env * ZB_NSENSORDATA : nullptr;
+  E.trace = O.solver_trace ? O.solver_trace + (size_t)env * ZB_NTRACE : nullptr;
 
   for (int s = 0; s < nsub; s++) {
     const bool last = s == nsub - 1;
@@ -235,6 +236,35 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zb_kernel(const ZbDev* __restrict
       if (O.flags) O.flags[env] = nb ? 1 : 0;
     }
   }
+}
+
+// ksim BadZTermination + NotUprightTermination as configured at train.py:1588-1593 (+ non-finite guard), one thread per env.
+__global__ void zb_term_kernel(const float* __restrict__ qpos, const int32_t* __restrict__ flags, uint8_t* __restrict__ done,
+                               int n_envs, float z_lo, float z_hi, float cos_tilt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_envs) return;
+  const float* q = qpos + (size_t)i * NQ;
+  const float z = q[2], w = q[3], x = q[4], y = q[5], zz = q[6];
+  const float up = w * w - x * x - y * y + zz * zz;  // R[2][2]: world z-axis component of the base z-axis
+  bool bad = (z < z_lo) || (z > z_hi) || (up < cos_tilt) || !isfinite(z) || !isfinite(up);
+  if (flags) bad = bad || flags[i] != 0;
+  done[i] = bad ? 1 : 0;
+}
+
+// FP32 FFMA throughput probe: the roofline denominator for this path is the CUDA-core FP32 peak, which
+// MEASURED_PEAKS.json does not carry (it has HBM GB/s and bf16 tensor TF/s only).  16 independent FMA chains per thread.
+__global__ void __launch_bounds__(256) zb_ffma_kernel(float* __restrict__ out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = fmaf(x[k], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; k++) s += x[k];
+  if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -459,6 +489,24 @@ int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbS
   zb_kernel<ZB_MODE_RESET><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
                                                                           reset_qpos, reset_qvel, reset_t_rem);
   return after_launch("zb_reset_f32 launch: %s");
+}
+
+int zb_terminations_f32(void* stream, const float* qpos, const int32_t* flags, uint8_t* done, int n_envs, float z_lo,
+                        float z_hi, float max_tilt_rad) {
+  if (!qpos || !done || n_envs < 0) return fail(ZB_EINVAL, "zb_terminations_f32: bad argument%s");
+  if (n_envs == 0) return ZB_OK;
+  zb_term_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(qpos, flags, done, n_envs, z_lo, z_hi, cosf(max_tilt_rad));
+  return after_launch("zb_terminations_f32 launch: %s");
+}
+
+/* Launches the FFMA probe: grid x 256 threads, `iters` x 16 FMAs per thread.  The caller times it with CUDA events;
+ * flops = grid * 256 * iters * 16 * 2. */
+int zb_bench_ffma(void* stream, float* scratch, int grid, int iters) {
+  if (!scratch || grid <= 0 || iters <= 0) return fail(ZB_EINVAL, "zb_bench_ffma: bad argument%s");
+  zb_ffma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999f, 1e-3f);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(ZB_ECUDA, "zb_bench_ffma launch: %s", cudaGetErrorString(ce));
+  return ZB_OK;
 }
 
 }  // extern "C"

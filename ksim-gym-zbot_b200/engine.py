@@ -53,11 +53,11 @@ def _ptr_struct(name, names):
 
 ZbEnvParams = _ptr_struct("ZbEnvParams", _PARAM_FIELDS)
 ZbState = _ptr_struct("ZbState", _STATE_FIELDS)
-ZbOut = _ptr_struct("ZbOut", _OUT_F32 + _OUT_I32)
+ZbOut = _ptr_struct("ZbOut", _OUT_F32 + _OUT_I32 + ["solver_trace"])
 
 ZB_OK, ZB_EINVAL, ZB_ENODEV, ZB_ECUDA, ZB_EUNSUP = 0, -1, -2, -3, -4
 EXPORTS = ["zb_engine_create", "zb_engine_destroy", "zb_engine_set_opts", "zb_step_f32", "zb_forward_f32", "zb_reset_f32",
-           "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count"]
+           "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count", "zb_bench_ffma", "zb_terminations_f32"]
 
 
 class ZbError(RuntimeError):
@@ -89,6 +89,9 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.zb_forward_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     lib.zb_reset_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    lib.zb_terminations_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    lib.zb_bench_ffma.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     assert lib.zb_sizeof_model() == ctypes.sizeof(M.ZbModel), "ZbModel layout mismatch between model.py and zbphys.h"
     assert lib.zb_sizeof_opts() == ctypes.sizeof(M.ZbOpts), "ZbOpts layout mismatch between model.py and zbphys.h"
     if path is None:
@@ -227,6 +230,7 @@ class ZbotCudaEngine:
         rc = self.lib.zb_engine_create(ctypes.byref(model), ctypes.byref(self.opts), self.device.index or 0, ctypes.byref(handle))
         self._check(rc)
         self._h = handle
+        self.trace: torch.Tensor | None = None  # set to a [N, 64] float32 CUDA tensor to record the solver trace
         self._default_qpos = torch.tensor(M.default_qpos(model), dtype=torch.float32, device=self.device)
 
     # ---- plumbing ------------------------------------------------------------------------
@@ -273,6 +277,8 @@ class ZbotCudaEngine:
 
     def _c_out(self, ps: PhysicsState) -> ZbOut:
         o = ZbOut()
+        if self.trace is not None:
+            o.solver_trace = self.trace.data_ptr()
         for k in self.outputs:
             t = getattr(ps.data, k)
             assert t.is_cuda and t.is_contiguous(), k
@@ -376,6 +382,18 @@ class ZbotCudaEngine:
                                      ps.data.qpos.shape[0])
         self._check(rc)
         return ps
+
+    def terminations(self, physics_state: PhysicsState, done: torch.Tensor | None = None, z_lo: float = 0.05,
+                     z_hi: float = 0.5, max_tilt: float = math.radians(60)) -> torch.Tensor:
+        """BadZTermination | NotUprightTermination (train.py:1588-1593) as one kernel; returns a uint8 [N] mask."""
+        n = physics_state.data.qpos.shape[0]
+        if done is None:
+            done = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        rc = self.lib.zb_terminations_f32(self._stream(), ctypes.c_void_p(physics_state.data.qpos.data_ptr()),
+                                          ctypes.c_void_p(physics_state.data.flags.data_ptr()), ctypes.c_void_p(done.data_ptr()), n,
+                                          z_lo, z_hi, max_tilt)
+        self._check(rc)
+        return done
 
     def launch_count(self) -> int:
         return int(self.lib.zb_launch_count())

@@ -69,6 +69,10 @@ static int g_stage;
 #define STAGE(s) ((void)0)
 #endif
 
+static int g_variant = 0;                    /* see zbo_set_variant */
+static _Thread_local real g_w[ZBO_NEFC][6];   /* contact-row wrench directions [off x dir; dir] */
+static _Thread_local const ZbModel* g_model;
+
 /* ------------------------------------------------------------------------------------------
  * small math — mujoco/mjx/_src/math.py [R]
  * ---------------------------------------------------------------------------------------- */
@@ -642,6 +646,12 @@ static void make_constraint(const ZbModel* m, const ZbOpts* o, const EnvModel* e
       real sgn = (k & 1) ? (real)-1 : (real)1;
       const real* dt_ = dc[1 + k / 2];
       for (int j = 0; j < NV; j++) d->efc_J[r][j] = dc[0][j] + sgn * dt_[j] * mu;
+      {
+        real dir[3] = {fr[0] + sgn * mu * fr[3 * (1 + k / 2)], fr[1] + sgn * mu * fr[3 * (1 + k / 2) + 1], fr[2] + sgn * mu * fr[3 * (1 + k / 2) + 2]};
+        real tq[3];
+        cross3(tq, off, dir); FL(-9);
+        for (int q_ = 0; q_ < 3; q_++) { g_w[r][q_] = tq[q_]; g_w[r][3 + q_] = dir[q_]; }
+      }
       FL(2 * 12);
       d->efc_type[r] = 3;
       d->efc_pos[r] = dist;
@@ -734,6 +744,25 @@ static void fwd_acceleration(ZboData* d) {
   chol_solve(d->qL, d->qacc_smooth);
 }
 
+/* Experiment switch (tests/diagnostics only): bit 0 = apply the contact rows matrix-free, the way the CUDA kernel does
+ * (J v = w_r . V_box(v), J^T f = cdof . sum_r f_r w_r), instead of through the explicit efc_J rows. */
+static void box_motion(const ZbModel* m, const ZboData* d, int body, const real* v, real* V) {
+  for (int k = 0; k < 6; k++) V[k] = 0;
+  int b = body;
+  while (b > 0 && m->body_dofadr[b] < 0) b = m->body_parent[b];
+  int dof = b > 0 ? m->body_dofadr[b] + (m->body_jnttype[b] == 1 ? 5 : 0) : -1;
+  for (int j = dof; j >= 0; j = m->dof_parent[j])
+    for (int k = 0; k < 6; k++) V[k] += d->cdof[j][k] * v[j];
+}
+static void jv_contacts(const ZboData* d, const real* v, real* jv) {
+  for (int c = 0; c < MAXCON; c++) {
+    if (!d->con_active[c]) continue;
+    real V[6];
+    box_motion(g_model, d, d->con_body[c], v, V);
+    for (int k = 0; k < 4; k++) jv[2 * NV + 4 * c + k] = dot6(g_w[2 * NV + 4 * c + k], V);
+  }
+}
+
 /* ------------------------------------------------------------------------------------------
  * solver.solve — primal CG / Newton with MJX's bracketing line search [R]
  * ---------------------------------------------------------------------------------------- */
@@ -765,8 +794,21 @@ static void update_constraint(const ZboData* d, Ctx* c) {
     }
   }
   for (int j = 0; j < NV; j++) c->qfrc_c[j] = 0;
+  if (g_variant & 1) {
+    for (int g = 0; g < NBOX; g++) {
+      real W[6] = {0, 0, 0, 0, 0, 0};
+      int body = g_model->box_body[g];
+      for (int r = 2 * NV + 16 * g; r < 2 * NV + 16 * g + 16; r++)
+        if (c->force[r] != 0)
+          for (int k = 0; k < 6; k++) W[k] += c->force[r] * g_w[r][k];
+      int b = body;
+      while (b > 0 && g_model->body_dofadr[b] < 0) b = g_model->body_parent[b];
+      int dof = b > 0 ? g_model->body_dofadr[b] + (g_model->body_jnttype[b] == 1 ? 5 : 0) : -1;
+      for (int j = dof; j >= 0; j = g_model->dof_parent[j]) c->qfrc_c[j] += dot6(d->cdof[j], W);
+    }
+  }
   for (int r = 0; r < NEFC; r++)
-    if (c->force[r] != 0) {
+    if (c->force[r] != 0 && !((g_variant & 1) && d->efc_type[r] == 3)) {
       for (int j = 0; j < NV; j++) c->qfrc_c[j] += d->efc_J[r][j] * c->force[r];
       FL(d->efc_type[r] == 3 ? 24 : 2);
     }
@@ -785,6 +827,12 @@ static void ctx_create(const ZboData* d, Ctx* c, const real* qacc) {
       for (int j = 0; j < NV; j++) s += d->efc_J[r][j] * qacc[j];
     c->Jaref[r] = s - d->efc_aref[r];
     if (d->efc_type[r]) FL(d->efc_type[r] == 3 ? 25 : 3);
+  }
+  if (g_variant & 1) {
+    real jv[NEFC];
+    jv_contacts(d, qacc, jv);
+    for (int r = 2 * NV; r < NEFC; r++)
+      if (d->efc_type[r] == 3) c->Jaref[r] = jv[r] - d->efc_aref[r];
   }
   mul_m(d, c->Ma, qacc);
   memset(c->grad, 0, sizeof(c->grad));
@@ -821,6 +869,8 @@ static void update_gradient(const ZbOpts* o, const ZboData* d, Ctx* c) {
 
 typedef struct { real alpha, cost, deriv_0, deriv_1; } LSPoint;
 
+static _Thread_local real* g_lstrace; /* where ls_point logs (alpha, d0, d1) during the first line search, else NULL */
+static _Thread_local int g_lscount;
 static LSPoint ls_point(const ZboData* d, const Ctx* c, real alpha, const real* jv, const real* quad_gauss) {
   real q0 = quad_gauss[0], q1 = quad_gauss[1], q2 = quad_gauss[2];
   for (int r = 0; r < NEFC; r++) {
@@ -843,6 +893,10 @@ static LSPoint ls_point(const ZboData* d, const Ctx* c, real alpha, const real* 
   p.deriv_0 = 2 * alpha * q2 + q1;
   p.deriv_1 = 2 * q2 + (q2 == 0 ? MJ_MINVAL : (real)0);
   FL(10);
+  if (g_lstrace && 32 + 3 * g_lscount + 2 < ZB_NTRACE) {
+    g_lstrace[32 + 3 * g_lscount] = alpha; g_lstrace[32 + 3 * g_lscount + 1] = p.deriv_0; g_lstrace[32 + 3 * g_lscount + 2] = p.deriv_1;
+    g_lscount++;
+  }
   return p;
 }
 static inline int in_bracket(real x, real y) { return (x < y && y < 0) || (x > y && y > 0); }
@@ -862,6 +916,7 @@ static void linesearch(const ZbModel* m, const ZbOpts* o, ZboData* d, Ctx* c) {
     }
     jv[r] = s;
   }
+  if (g_variant & 1) jv_contacts(d, c->search, jv);
   real qg[3] = {c->gauss, 0, 0};
   for (int j = 0; j < NV; j++) {
     qg[1] += c->search[j] * c->Ma[j] - c->search[j] * d->qfrc_smooth[j];
@@ -869,6 +924,8 @@ static void linesearch(const ZbModel* m, const ZbOpts* o, ZboData* d, Ctx* c) {
   }
   qg[2] *= (real)0.5;
   FL(8 * NV);
+  g_lstrace = c->niter == 0 ? d->trace : NULL;
+  g_lscount = 0;
   LSPoint p0 = ls_point(d, c, 0, jv, qg);
   LSPoint lo = ls_point(d, c, p0.alpha - p0.deriv_0 / p0.deriv_1, jv, qg), hi;
   d->ls_evals += 2;
@@ -900,8 +957,14 @@ static void linesearch(const ZbModel* m, const ZbOpts* o, ZboData* d, Ctx* c) {
     it++;
   }
   d->ls_iters += it;
+  g_lstrace = NULL;
   int improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
   real alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+  if (4 * c->niter + 3 < ZB_NTRACE) {
+    d->trace[4 * c->niter] = improved ? alpha : 0;
+    d->trace[4 * c->niter + 2] = (real)it;
+    d->trace[4 * c->niter + 3] = R_SQRT(nrm);
+  }
   if (improved) {
     for (int j = 0; j < NV; j++) { c->qacc[j] += c->search[j] * alpha; c->Ma[j] += mv[j] * alpha; }
     for (int r = 0; r < NEFC; r++) c->Jaref[r] += jv[r] * alpha;
@@ -911,6 +974,7 @@ static void linesearch(const ZbModel* m, const ZbOpts* o, ZboData* d, Ctx* c) {
 
 static void solve(const ZbModel* m, const ZbOpts* o, ZboData* d) {
   STAGE(ZBO_ST_SOLVER);
+  g_model = m;
   static _Thread_local Ctx c, c2;
   const real* start = d->qacc_smooth;
   if (o->warmstart) {
@@ -939,6 +1003,7 @@ static void solve(const ZbModel* m, const ZbOpts* o, ZboData* d) {
     memcpy(pg, c.grad, sizeof(pg));
     memcpy(pMg, c.Mgrad, sizeof(pMg));
     update_constraint(d, &c);
+    if (4 * c.niter + 3 < ZB_NTRACE) d->trace[4 * c.niter + 1] = c.cost;
     update_gradient(o, d, &c);
     if (o->solver == ZB_SOLVER_NEWTON) {
       for (int j = 0; j < NV; j++) c.search[j] = -c.Mgrad[j];
@@ -1168,6 +1233,7 @@ static void write_out(const ZboOut* out, const ZboData* d, int i) {
   CP(contact_dist, d->con_dist, MAXCON);
   CP(contact_pos, d->con_pos, MAXCON * 3);
   CP(efc_force, d->efc_force, NEFC);
+  CP(solver_trace, d->trace, ZB_NTRACE);
 #undef CP
   if (out->contact_mask) {
     int mask = 0;
@@ -1309,6 +1375,8 @@ int SUF(zbo_reset)(const ZbModel* m, const ZbOpts* o, const ZboParams* p, const 
 }
 
 int SUF(zbo_sizeof_data)(void) { return (int)sizeof(ZboData); }
+
+void SUF(zbo_set_variant)(int v) { g_variant = v; }
 
 #if !ZBO_F64
 /* flop counters (meaningful only in the -DZBO_COUNT build, single-threaded) */

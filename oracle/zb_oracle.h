@@ -38,6 +38,7 @@ typedef struct ZboOut {
   real *xpos, *xquat, *cinert, *cvel, *qacc, *qfrc_constraint, *actuator_force, *ctrl, *sensordata, *site_xpos,
       *site_xmat, *contact_dist, *contact_pos, *efc_force;
   int32_t *contact_mask, *solver_niter, *flags;
+  real* solver_trace;
 } ZboOut;
 
 /* everything mjx.forward leaves in mjx.Data for one environment (plus a few debugging extras) */
@@ -58,6 +59,7 @@ typedef struct ZboData {
   real cacc[ZB_NBODY][6], cfrc_int[ZB_NBODY][6], cfrc_ext[ZB_NBODY][6];
   real sensordata[ZB_NSENSORDATA];
   real solver_cost;
+  real trace[ZB_NTRACE];
   int32_t con_body[ZB_MAXCON], con_vert[ZB_MAXCON], con_active[ZB_MAXCON];
   int32_t efc_type[ZBO_NEFC]; /* 0 inert, 1 friction-loss, 2 limit, 3 contact */
   int32_t solver_niter, ls_evals, ls_iters, flags;

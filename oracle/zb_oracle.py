@@ -43,7 +43,7 @@ _REAL_FIELDS = [
     ("qfrc_constraint", (NV,)), ("qacc", (NV,)),
     ("cacc", (NBODY, 6)), ("cfrc_int", (NBODY, 6)), ("cfrc_ext", (NBODY, 6)),
     ("sensordata", (NSENSORDATA,)),
-    ("solver_cost", ()),
+    ("solver_cost", ()), ("trace", (128,)),
 ]
 _INT_FIELDS = [
     ("con_body", (MAXCON,)), ("con_vert", (MAXCON,)), ("con_active", (MAXCON,)), ("efc_type", (NEFC,)),
@@ -103,7 +103,7 @@ def _ptr_struct(names):
 
 _ZboParams = _ptr_struct(_PARAM_FIELDS)
 _ZboState = _ptr_struct(_STATE_FIELDS)
-_ZboOut = _ptr_struct(_OUT_REAL + _OUT_INT)
+_ZboOut = _ptr_struct(_OUT_REAL + _OUT_INT + ["solver_trace"])
 
 
 def build(force: bool = False) -> None:
@@ -161,6 +161,7 @@ class Oracle:
     def new_out(self, n):
         out = {k: np.zeros((n,) + OUT_SHAPES[k], dtype=self.dtype) for k in _OUT_REAL}
         out.update({k: np.zeros((n,), dtype=np.int32) for k in _OUT_INT})
+        out["solver_trace"] = np.zeros((n, 128), dtype=self.dtype)
         return out
 
     def _state(self, st):
@@ -174,7 +175,7 @@ class Oracle:
     def _out(self, out):
         s = _ZboOut()
         if out is not None:
-            for k in _OUT_REAL + _OUT_INT:
+            for k in _OUT_REAL + _OUT_INT + ["solver_trace"]:
                 if out.get(k) is not None:
                     setattr(s, k, out[k].ctypes.data)
         return s
@@ -233,6 +234,10 @@ class Oracle:
                 ctypes.byref(self._out(out)), n, self.threads)
         assert rc == 0, rc
         return out
+
+    def set_variant(self, v: int) -> None:
+        """bit 0: contact rows applied matrix-free like the CUDA kernel (diagnostics)."""
+        getattr(self.lib, "zbo_set_variant" + self.suf)(int(v))
 
     # ---- flop counters (count build only) ------------------------------------------------
     def flops_reset(self):
