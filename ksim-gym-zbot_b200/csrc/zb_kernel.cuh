@@ -28,7 +28,12 @@
 #define NB ZB_NBODY
 #define BL0 (32 - 6) /* first base-dof lane */
 #define CHD 6        /* dof positions per chain group (legs: 6, arms: 4) */
-#define ZB_WPB 4     /* warps (environments) per CTA */
+#ifndef ZB_WPB
+#define ZB_WPB 4 /* warps (environments) per CTA */
+#endif
+#ifndef ZB_MINB
+#define ZB_MINB 4 /* min resident CTAs per SM the register allocation must allow */
+#endif
 #define ZB_SCR 8     /* scratch floats per lane */
 
 static_assert(ZB_NBODY + 6 == 32, "lane mapping assumes 26 bodies + 6 free-joint dofs == one warp");
@@ -38,6 +43,11 @@ static_assert(ZB_NBODY + 6 == 32, "lane mapping assumes 26 bodies + 6 free-joint
 #define MJ_MAXIMP 0.9999f
 
 enum { ZB_MODE_STEP = 0, ZB_MODE_FORWARD = 1, ZB_MODE_RESET = 2 };
+
+// constraint._kbi constants of one (solref, solimp) pair, precomputed on the host (depend on opt.timestep via refsafe)
+struct ZbSolPrm {
+  float k, b, dmin, dmax, width, mid, power, c1, c2;  // c1 = 1/mid^(power-1), c2 = 1/(1-mid)^(power-1)
+};
 
 // Host-derived tables (zb_engine_create) living in device global memory next to the model.
 struct ZbDev {
@@ -55,6 +65,12 @@ struct ZbDev {
   float frame[9];       // make_frame(floor_normal): rows n, t1, t2
   int box_site[ZB_NBOX];
   int any_damping;
+  float fr_R[32], fr_b[32];        // friction-loss rows by lane: R (0 = no row) and b of the dof's solref/solimp
+  ZbSolPrm lim[32];                // joint-limit rows by lane
+  ZbSolPrm con[ZB_NBOX];           // contact rows by box (after geom-priority mixing)
+  float con_includemargin[ZB_NBOX];
+  float con_invweight[ZB_NBOX];    // body_invweight0[world] + body_invweight0[box body]
+  int con_mu_mode[ZB_NBOX];        // 0: floor friction (per-env), 1: box friction, 2: max of both
 };
 
 struct Factor {
@@ -76,7 +92,7 @@ struct WarpEnv {
   int cs, ce, gs, gp, gn, dof, act, lbox, boxlane;
   bool isbody, hinge, bdof, hasdof, chainbody;
   // per-environment model (randomizers, train.py:1439-1455)
-  float mass, inertia[3], arm, damp, floss, q0, mu, mass_tot;
+  float mass, inertia[3], arm, damp, floss, q0, mu, mass_tot, inv_mass_tot;
   float spos[3], squat[4];
   // state
   float q, qv, warm, bq[7];
@@ -90,12 +106,12 @@ struct WarpEnv {
   Factor F0, F1;
   float qfrc_smooth, qacc_smooth, act_force, qfrc_bias;
   // constraint rows
-  bool fr_on, lm_on, c_on;
+  bool fr_on, lm_on, c_on, any_limit;
   float fr_D, fr_rf, fr_f, fr_aref, lm_sign, lm_D, lm_aref, c_D, c_aref, w[6];
   float cdist, cpos[3];
   // solver
   float qacc, Ma, grad, Mgrad, search, mv, qfrc_c;
-  float fr_ja, lm_ja, c_ja, fr_jv, lm_jv, c_jv, fr_force, lm_force, c_force;
+  float fr_ja, lm_ja, c_ja, fr_force, lm_force, c_force;
   float Wf[6];  // total contact wrench of my half's foot (row lanes)
   float gauss, cost, prev_cost;
   int niter;
@@ -220,7 +236,7 @@ struct WarpEnv {
     {
       float s[3] = {isbody ? mass * xipos[0] : 0.f, isbody ? mass * xipos[1] : 0.f, isbody ? mass * xipos[2] : 0.f};
 #pragma unroll
-      for (int k = 0; k < 3; k++) c0[k] = wsum(s[k]) / mass_tot;
+      for (int k = 0; k < 3; k++) c0[k] = wsum(s[k]) * inv_mass_tot;
     }
     // cinert about c0
     {
@@ -349,8 +365,9 @@ struct WarpEnv {
     for (int k = 0; k < CHD; k++) {
       float d = shf(r[k], gs + k);
       if (!(valid && k < gn)) d = 1.f;
-      const float lkk = sqrtf(d);
-      const float ik = 1.f / lkk;
+      float ik = rsqrtf(d);  // MUFU.RSQ + one Newton step: full fp32 accuracy without the IEEE sqrt/div expansions
+      ik = ik * (1.5f - 0.5f * d * ik * ik);
+      const float lkk = d * ik;
       const bool piv = valid && gp == k;
       r[k] = piv ? lkk : ((valid && gp > k) ? r[k] * ik : r[k]);
       inv = piv ? ik : inv;
@@ -423,7 +440,13 @@ struct WarpEnv {
   }
 
   // smooth.solve_m: x <- (M + diag)^-1 x, x distributed over the dof lanes
-  ZB_DI float solve(const Factor& F, float x) {
+  ZB_DI float solve(bool second, float x) {
+    Factor F;  // select which factorization (M or M + dt D) — cheaper than a second copy of this code
+#pragma unroll
+    for (int k = 0; k < CHD; k++) { F.lc[k] = second ? F1.lc[k] : F0.lc[k]; F.lt[k] = second ? F1.lt[k] : F0.lt[k]; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) F.W[k] = second ? F1.W[k] : F0.W[k];
+    F.inv = second ? F1.inv : F0.inv;
     if (!hasdof) x = 0.f;
     // chains: forward substitution
 #pragma unroll
@@ -720,45 +743,29 @@ struct WarpEnv {
 #undef ZB_SUPPORT
   }
 
-  // constraint._kbi + row finish (A.8)
-  ZB_DI void kbi(const float* solref, const float* solimp, float pos, float& k, float& b, float& imp) const {
-    float timeconst = fmaxf(solref[0], 2.f * D->o.dt);
-    const float dampratio = solref[1];
-    const float dmin = clampf(solimp[0], MJ_MINIMP, MJ_MAXIMP), dmax = clampf(solimp[1], MJ_MINIMP, MJ_MAXIMP);
-    const float width = fmaxf(MJ_MINVAL, solimp[2]);
-    const float mid = clampf(solimp[3], MJ_MINIMP, MJ_MAXIMP);
-    const float power = fmaxf(1.f, solimp[4]);
-    k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
-    b = 2.f / (dmax * timeconst);
-    if (solref[0] <= 0.f) { k = -solref[0] / (dmax * dmax); b = -solref[1] / dmax; }
-    const float x = fabsf(pos) / width;
-    float y;
-    if (power == 2.f) {
-      y = x < mid ? (1.f / mid) * (x * x) : 1.f - (1.f / (1.f - mid)) * ((1.f - x) * (1.f - x));
-    } else {
-      y = x < mid ? (1.f / powf(mid, power - 1.f)) * powf(x, power) : 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
-    }
-    imp = dmin + y * (dmax - dmin);
-    imp = clampf(imp, dmin, dmax);
-    if (x > 1.f) imp = dmax;
+  // constraint._kbi impedance with host-precomputed constants (A.8)
+  ZB_DI float impedance(const ZbSolPrm& s, float pos) const {
+    const float x = fabsf(pos) / s.width;
+    const float z = x < s.mid ? x : 1.f - x;
+    const float pw = s.power == 2.f ? z * z : zb_pow(z, s.power);
+    const float y = x < s.mid ? s.c1 * pw : 1.f - s.c2 * pw;
+    float imp = s.dmin + y * (s.dmax - s.dmin);
+    imp = clampf(imp, s.dmin, s.dmax);
+    return x > 1.f ? s.dmax : imp;
   }
 
   ZB_DI void make_constraint() {
     const ZbModel& m = D->m;
     const int d = hasdof ? dof : 0;
-    // friction-loss row of my dof
-    fr_on = hasdof && m.dof_frictionloss[d] > 0.f;
+    // friction-loss row of my dof: pos == 0 -> impedance, R, D and b are model constants (host-precomputed)
+    fr_on = hasdof && D->fr_R[L] > 0.f;
     fr_D = 0.f; fr_rf = 0.f; fr_f = 0.f; fr_aref = 0.f;
     if (fr_on) {
-      const float sr[2] = {m.dof_solref[d][0], m.dof_solref[d][1]};
-      const float si[5] = {m.dof_solimp[d][0], m.dof_solimp[d][1], m.dof_solimp[d][2], m.dof_solimp[d][3], m.dof_solimp[d][4]};
-      float k, b, imp;
-      kbi(sr, si, 0.f, k, b, imp);
-      const float R = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, MJ_MINVAL);
+      const float R = D->fr_R[L];
       fr_D = 1.f / R;
       fr_f = floss;
       fr_rf = R * floss;
-      fr_aref = -b * qv;
+      fr_aref = -D->fr_b[L] * qv;
     }
     // joint-limit row of my hinge
     lm_on = false; lm_D = 0.f; lm_aref = 0.f; lm_sign = 1.f;
@@ -766,27 +773,22 @@ struct WarpEnv {
       const float dmin = q - m.jnt_range[d][0], dmax = m.jnt_range[d][1] - q;
       const float pos = fminf(dmin, dmax) - m.jnt_margin[d];
       if (pos < 0.f) {
-        const float sr[2] = {m.jnt_solref[d][0], m.jnt_solref[d][1]};
-        const float si[5] = {m.jnt_solimp[d][0], m.jnt_solimp[d][1], m.jnt_solimp[d][2], m.jnt_solimp[d][3], m.jnt_solimp[d][4]};
-        float k, b, imp;
-        kbi(sr, si, pos, k, b, imp);
+        const ZbSolPrm& sp = D->lim[L];
+        const float imp = impedance(sp, pos);
         lm_on = true;
         lm_sign = dmin < dmax ? 1.f : -1.f;
         const float R = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, MJ_MINVAL);
         lm_D = 1.f / R;
-        lm_aref = -b * (lm_sign * qv) - k * imp * pos;
+        lm_aref = -sp.b * (lm_sign * qv) - sp.k * imp * pos;
       }
     }
+    any_limit = __any_sync(ZB_FULL, lm_on);
     // contact row r = L: pyramid edge (L & 3) of slot (L >> 2)
     {
       const int g = L >> 4;
-      const float margin = fmaxf(m.floor_margin, m.box_margin[g]), gap = fmaxf(m.floor_gap, m.box_gap[g]);
-      const bool floor_wins = m.floor_priority >= m.box_priority[g];
-      float cmu = floor_wins ? mu : m.box_friction[g][0];
-      if (m.floor_priority == m.box_priority[g]) cmu = fmaxf(mu, m.box_friction[g][0]);
-      const float* srp = m.floor_priority >= m.box_priority[g] ? m.floor_solref : m.box_solref[g];
-      const float* sip = m.floor_priority >= m.box_priority[g] ? m.floor_solimp : m.box_solimp[g];
-      const float dist = cdist - (margin - gap);
+      const ZbSolPrm& sp = D->con[g];
+      const float cmu = D->con_mu_mode[g] == 0 ? mu : (D->con_mu_mode[g] == 1 ? m.box_friction[g][0] : fmaxf(mu, m.box_friction[g][0]));
+      const float dist = cdist - D->con_includemargin[g];
       c_on = dist < 0.f;
       const int e = L & 3;
       const float sgn = (e & 1) ? -1.f : 1.f;
@@ -803,23 +805,25 @@ struct WarpEnv {
       for (int k = 0; k < 6; k++) vf[k] = shf(cvel[k], boxlane);
       c_D = 0.f; c_aref = 0.f;
       if (c_on) {
-        const float sr[2] = {srp[0], srp[1]};
-        const float si[5] = {sip[0], sip[1], sip[2], sip[3], sip[4]};
-        float k, b, imp;
-        kbi(sr, si, dist, k, b, imp);
-        const float t = m.body_invweight0[0][0] + m.body_invweight0[m.box_body[g]][0];
+        const float imp = impedance(sp, dist);
+        const float t = D->con_invweight[g];
         const float invweight = (t + cmu * cmu * t) * 2.f * cmu * cmu / D->o.impratio;
         const float R = fmaxf(invweight * (1.f - imp) / imp, MJ_MINVAL);
         c_D = 1.f / R;
-        c_aref = -b * dot6(w, vf) - k * imp * dist;
+        c_aref = -sp.b * dot6(w, vf) - sp.k * imp * dist;
       }
     }
   }
 
   // ------------------------------------------------------------------------------------------
-  // solver.solve, CG (A.9)
+  // solver.solve, CG (A.9) — ONE loop, every heavy primitive instantiated once (I-cache):
+  //   phase -1 : qacc_smooth = M^-1 qfrc_smooth
+  //   phase 0/1: cost of the two warm-start candidates (qacc_smooth, qacc_warmstart)
+  //   phase 2  : Context.create at the chosen start + first gradient/search direction
+  //   phase 3  : one solver iteration (line search, constraint update, gradient, Polak-Ribiere)
+  //   phase 99 : implicit integration solve (M + dt D)^-1 (qfrc_smooth + qfrc_constraint)
   // ------------------------------------------------------------------------------------------
-  // row costs/forces at the current Jaref; returns this lane's partial constraint cost
+  // forces and cost of the rows at the current Jaref; returns this lane's partial constraint cost
   ZB_DI float row_update() {
     float cst = 0.f;
     fr_force = 0.f; lm_force = 0.f; c_force = 0.f;
@@ -833,109 +837,105 @@ struct WarpEnv {
     if (c_on && c_ja < 0.f) { c_force = -c_D * c_ja; cst += 0.5f * c_D * c_ja * c_ja; }
     return cst;
   }
-  // Context.create without gradient: Jaref, Ma and the cost at qacc = a
-  ZB_DI void ctx_create(float a, float& Ma_, float& frja, float& lmja, float& cja, float& cost_) {
-    float vb[6];
-    Ma_ = mul_m(a, vb);
-    const float cj = contact_jv(a, vb);
-    frja = a - fr_aref;
-    lmja = lm_sign * a - lm_aref;
-    cja = cj - c_aref;
-    const float s1 = fr_ja, s2 = lm_ja, s3 = c_ja;
-    fr_ja = frja; lm_ja = lmja; c_ja = cja;
-    float part = row_update();
-    fr_ja = s1; lm_ja = s2; c_ja = s3;
-    if (hasdof) part += 0.5f * (Ma_ - qfrc_smooth) * (a - qacc_smooth);
-    cost_ = wsum(part);
-  }
-  ZB_DI void update_constraint() {
-    float part = row_update();
-    float g = hasdof ? 0.5f * (Ma - qfrc_smooth) * (qacc - qacc_smooth) : 0.f;
-    // two sums: gauss is needed separately by the line search
-    float p2[2] = {part, g};
-    reduce_scatter<2>(p2, L);
-    const float csum = shf(p2[0], 0), gsum = shf(p2[0], 16);
-    gauss = gsum;
-    prev_cost = cost;
-    cost = gsum + csum;
-    const float jt = contact_jtf(c_force);
-    qfrc_c = hasdof ? jt + (fr_on ? fr_force : 0.f) + (lm_on ? lm_sign * lm_force : 0.f) : 0.f;
-  }
-  ZB_DI void update_gradient() {
-    grad = hasdof ? Ma - qfrc_smooth - qfrc_c : 0.f;
-    Mgrad = solve(F0, grad);
-  }
-  ZB_DI LSPoint ls_point(float alpha, const float (&qg)[3]) {
-    float q0_ = 0.f, q1 = 0.f, q2 = 0.f;
-    if (fr_on) {
-      const float x0 = fr_ja, jv = fr_jv, x = x0 + alpha * jv;
-      if (x <= -fr_rf && fr_f > 0.f) { q0_ += fr_f * (-0.5f * fr_rf - x0); q1 += -fr_f * jv; }
-      else if (x >= fr_rf && fr_f > 0.f) { q0_ += fr_f * (-0.5f * fr_rf + x0); q1 += fr_f * jv; }
-      else { q0_ += 0.5f * fr_D * x0 * x0; q1 += fr_D * x0 * jv; q2 += 0.5f * fr_D * jv * jv; }
-    }
-    if (lm_on && (lm_ja + alpha * lm_jv) < 0.f) { q0_ += 0.5f * lm_D * lm_ja * lm_ja; q1 += lm_D * lm_ja * lm_jv; q2 += 0.5f * lm_D * lm_jv * lm_jv; }
-    if (c_on && (c_ja + alpha * c_jv) < 0.f) { q0_ += 0.5f * c_D * c_ja * c_ja; q1 += c_D * c_ja * c_jv; q2 += 0.5f * c_D * c_jv * c_jv; }
-    float p[4] = {q0_, q1, q2, 0.f};
-    reduce_scatter<4>(p, L);  // lanes 8k..8k+7 hold total k
-    const float t0 = shf(p[0], 0) + qg[0], t1 = shf(p[0], 8) + qg[1], t2 = shf(p[0], 16) + qg[2];
-    LSPoint r;
-    r.alpha = alpha;
-    // NOT fused on purpose (__fmul_rn/__fadd_rn are never contracted into FMA): when the active set did not change, the
-    // Newton point alpha = -t1 / (2 t2) makes 2*alpha*t2 + t1 round to EXACTLY 0 with separately rounded products, and the
-    // reference's bracket logic treats an exact zero as "not in bracket" (the point is rejected).  An FMA would return the
-    // tiny residual instead and flip that decision in ~14 % of the states (tests/gpu_probe3.py).
-    r.cost = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(alpha, alpha), t2), __fmul_rn(alpha, t1)), t0);
-    r.d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, alpha), t2), t1);
-    r.d1 = __fadd_rn(__fmul_rn(2.f, t2), (t2 == 0.f ? MJ_MINVAL : 0.f));
-    if (trace && niter == 0 && L == 0 && 32 + 3 * lscount + 2 < ZB_NTRACE) {
-      trace[32 + 3 * lscount] = alpha; trace[32 + 3 * lscount + 1] = r.d0; trace[32 + 3 * lscount + 2] = r.d1;
-    }
-    lscount++;
-    return r;
-  }
   static ZB_DI bool in_bracket(float x, float y) { return (x < y && y < 0.f) || (x > y && y > 0.f); }
 
-  ZB_DI void linesearch() {
+  // exact line search along `search` (MJX _linesearch): three candidate points per iteration, evaluated together
+  ZB_DI void linesearch(float cjv) {
     const ZbOpts& o = D->o;
-    float vb[6];
-    mv = mul_m(search, vb);
-    c_jv = contact_jv(search, vb);
-    fr_jv = search;
-    lm_jv = lm_sign * search;
+    const float fr_jv = search, lm_jv = lm_sign * search;
     float p[4] = {search * search, search * Ma - search * qfrc_smooth, search * mv, 0.f};
     if (!hasdof) { p[0] = p[1] = p[2] = 0.f; }
     reduce_scatter<4>(p, L);
     const float snorm = shf(p[0], 0);
-    const float qg[3] = {gauss, shf(p[0], 8), 0.5f * shf(p[0], 16)};
-    const float smag = sqrtf(snorm) * D->m.meaninertia * (float)NV;
-    const float gtol = o.tolerance * o.ls_tolerance * smag;
-    lscount = 0;
-    const LSPoint p0 = ls_point(0.f, qg);
-    LSPoint lo = ls_point(p0.alpha - p0.d0 / p0.d1, qg), hi;
-    if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+    const float qg0 = gauss, qg1 = shf(p[0], 8), qg2 = 0.5f * shf(p[0], 16);
+    const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * D->m.meaninertia * (float)NV);
+    // per-row quadratics (MJX: quad = [0.5 D x0^2, D x0 jv, 0.5 D jv^2]; friction rows also have two linear zones)
+    const float fq0 = 0.5f * fr_D * fr_ja * fr_ja, fq1 = fr_D * fr_ja * fr_jv, fq2 = 0.5f * fr_D * fr_jv * fr_jv;
+    const float fn0 = fr_f * (-0.5f * fr_rf - fr_ja), fp0 = fr_f * (-0.5f * fr_rf + fr_ja), fl1 = fr_f * fr_jv;
+    const float lq0 = 0.5f * lm_D * lm_ja * lm_ja, lq1 = lm_D * lm_ja * lm_jv, lq2 = 0.5f * lm_D * lm_jv * lm_jv;
+    const float cq0 = 0.5f * c_D * c_ja * c_ja, cq1 = c_D * c_ja * cjv, cq2 = 0.5f * c_D * cjv * cjv;
+    const bool fr_lin = fr_on && fr_f > 0.f;
+    LSPoint p0, lo, hi;
+    float al[3] = {0.f, 0.f, 0.f};
     bool swap = true;
-    int it = 0;
+    int it = 0, stage = 0;
+#pragma unroll 1
     while (true) {
+      // ---- evaluate the three alphas: 9 partial sums -> one transpose-reduce ----
+      float s[16];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const float a = al[j];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        if (fr_on) {
+          const float x = fr_ja + a * fr_jv;
+          const bool neg = fr_lin && x <= -fr_rf, pos = fr_lin && x >= fr_rf;
+          s0 = neg ? fn0 : (pos ? fp0 : fq0);
+          s1 = neg ? -fl1 : (pos ? fl1 : fq1);
+          s2 = (neg || pos) ? 0.f : fq2;
+        }
+        if (any_limit && lm_on && (lm_ja + a * lm_jv) < 0.f) { s0 += lq0; s1 += lq1; s2 += lq2; }
+        if (c_on && (c_ja + a * cjv) < 0.f) { s0 += cq0; s1 += cq1; s2 += cq2; }
+        s[3 * j] = s0; s[3 * j + 1] = s1; s[3 * j + 2] = s2;
+      }
+#pragma unroll
+      for (int k = 9; k < 16; k++) s[k] = 0.f;
+      reduce_scatter<16>(s, L);  // lanes 2k, 2k+1 hold total k
+      LSPoint pt[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const float t0 = shf(s[0], 6 * j) + qg0, t1 = shf(s[0], 6 * j + 2) + qg1, t2 = shf(s[0], 6 * j + 4) + qg2;
+        const float a = al[j];
+        // NOT fused on purpose (__fmul_rn/__fadd_rn are never contracted into FMA): when the active set did not change, the
+        // Newton point alpha = -t1 / (2 t2) makes 2*alpha*t2 + t1 round to EXACTLY 0 with separately rounded products, and
+        // the reference's bracket logic treats an exact zero as "not in bracket" (the point is rejected).  An FMA would
+        // return the tiny residual instead and flip that decision in ~14 % of the states (tests/gpu_probe3.py).
+        pt[j].alpha = a;
+        pt[j].cost = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(a, a), t2), __fmul_rn(a, t1)), t0);
+        pt[j].d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, a), t2), t1);
+        pt[j].d1 = __fadd_rn(__fmul_rn(2.f, t2), (t2 == 0.f ? MJ_MINVAL : 0.f));
+      }
+      if (trace && niter == 0 && L == 0) {
+        const int np = stage < 2 ? 1 : 3;
+        for (int j = 0; j < np; j++)
+          if (32 + 3 * lscount + 2 < ZB_NTRACE) {
+            trace[32 + 3 * lscount] = pt[j].alpha; trace[32 + 3 * lscount + 1] = pt[j].d0; trace[32 + 3 * lscount + 2] = pt[j].d1;
+            lscount++;
+          }
+      }
+      if (stage == 0) {  // p0 = point(0)
+        p0 = pt[0];
+        const float a1 = p0.alpha - p0.d0 / p0.d1;
+        al[0] = al[1] = al[2] = a1;
+        stage = 1;
+        continue;
+      }
+      if (stage == 1) {  // lo = point(newton(p0)); order the bracket
+        if (pt[0].d0 < p0.d0) { lo = pt[0]; hi = p0; } else { hi = pt[0]; lo = p0; }
+        stage = 2;
+      } else {
+        const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
+        const bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
+        const bool s2 = in_bracket(lo.d0, mid.d0); if (s2) lo = mid;
+        const bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) lo = hi_next;
+        const bool s4 = in_bracket(hi.d0, hi_next.d0); if (s4) hi = hi_next;
+        const bool s5 = in_bracket(hi.d0, mid.d0); if (s5) hi = mid;
+        const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) hi = lo_next;
+        swap = s1 | s2 | s3 | s4 | s5 | s6;
+        it++;
+      }
       bool done = it >= o.ls_iterations;
       done |= !swap;
       done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
       done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
       if (done) break;
-      const LSPoint lo_next = ls_point(lo.alpha - lo.d0 / lo.d1, qg);
-      const LSPoint hi_next = ls_point(hi.alpha - hi.d0 / hi.d1, qg);
-      const LSPoint mid = ls_point(0.5f * (lo.alpha + hi.alpha), qg);
-      const bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
-      const bool s2 = in_bracket(lo.d0, mid.d0); if (s2) lo = mid;
-      const bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) lo = hi_next;
-      const bool s4 = in_bracket(hi.d0, hi_next.d0); if (s4) hi = hi_next;
-      const bool s5 = in_bracket(hi.d0, mid.d0); if (s5) hi = mid;
-      const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) hi = lo_next;
-      swap = s1 | s2 | s3 | s4 | s5 | s6;
-      it++;
+      al[0] = lo.alpha - lo.d0 / lo.d1;
+      al[1] = hi.alpha - hi.d0 / hi.d1;
+      al[2] = 0.5f * (lo.alpha + hi.alpha);
     }
     const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
     const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
-    if (trace && L == 0 && 4 * niter + 3 < ZB_NTRACE) {
+    if (trace && L == 0 && 4 * niter + 3 < 32) {
       trace[4 * niter] = improved ? alpha : 0.f;
       trace[4 * niter + 2] = (float)it;
       trace[4 * niter + 3] = sqrtf(snorm);
@@ -945,47 +945,90 @@ struct WarpEnv {
       Ma += mv * alpha;
       fr_ja += fr_jv * alpha;
       lm_ja += lm_jv * alpha;
-      c_ja += c_jv * alpha;
+      c_ja += cjv * alpha;
     }
   }
 
-  ZB_DI void solve_constraints() {
+  // The whole constrained solve + (optionally) the implicit-integration solve.  Returns the integration acceleration.
+  ZB_DI float solve_all(bool implicit_damp) {
     const ZbOpts& o = D->o;
-    // warm start: the cheaper of qacc_warmstart and qacc_smooth
-    float Ma_s, fj_s, lj_s, cj_s, cost_s;
-    ctx_create(qacc_smooth, Ma_s, fj_s, lj_s, cj_s, cost_s);
-    qacc = qacc_smooth; Ma = Ma_s; fr_ja = fj_s; lm_ja = lj_s; c_ja = cj_s;
-    if (o.warmstart) {
-      float Ma_w, fj_w, lj_w, cj_w, cost_w;
-      ctx_create(warm, Ma_w, fj_w, lj_w, cj_w, cost_w);
-      if (cost_w < cost_s) { qacc = hasdof ? warm : 0.f; Ma = Ma_w; fr_ja = fj_w; lm_ja = lj_w; c_ja = cj_w; }
-    }
-    cost = INFINITY; prev_cost = 0.f; niter = 0;
-    update_constraint();
-    update_gradient();
-    search = -Mgrad;
     const float scale = 1.f / (D->m.meaninertia * (float)NV);
+    int phase = -1;
+    float v = 0.f, cost_s = 0.f, qa_int = 0.f, pg = 0.f, pMg = 0.f;
+    cost = 0.f; prev_cost = 0.f; niter = 0; lscount = 0;
+    qacc = 0.f; Ma = 0.f; fr_ja = lm_ja = c_ja = 0.f; qfrc_c = 0.f; grad = 0.f; Mgrad = 0.f; search = 0.f; mv = 0.f; gauss = 0.f;
+    fr_force = lm_force = c_force = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) Wf[k] = 0.f;
+#pragma unroll 1
     while (true) {
+      if (phase >= 0 && phase < 99) {
+        // ---- operator application: mv = M v, contact rows J v ----
+        float vb[6];
+        mv = mul_m(v, vb);
+        const float cjv = contact_jv(v, vb);
+        if (phase >= 3) {
+          linesearch(cjv);
+        } else {  // Context.create at qacc = v
+          qacc = hasdof ? v : 0.f;
+          Ma = mv;
+          fr_ja = v - fr_aref;
+          lm_ja = lm_sign * v - lm_aref;
+          c_ja = cjv - c_aref;
+        }
+        // ---- _update_constraint: forces, cost ----
+        const float part = row_update();
+        float p2[2] = {part, hasdof ? 0.5f * (Ma - qfrc_smooth) * (qacc - qacc_smooth) : 0.f};
+        reduce_scatter<2>(p2, L);
+        gauss = shf(p2[0], 16);
+        prev_cost = phase == 2 ? INFINITY : cost;
+        cost = gauss + shf(p2[0], 0);
+        if (trace && L == 0 && phase >= 3 && 4 * niter + 3 < 32) trace[4 * niter + 1] = cost;
+      }
+      float x = 0.f;
+      if (phase == -1 || phase >= 2) {
+        if (phase >= 2 && phase < 99) {
+          const float jt = contact_jtf(c_force);
+          qfrc_c = hasdof ? jt + (fr_on ? fr_force : 0.f) + (lm_on ? lm_sign * lm_force : 0.f) : 0.f;
+          pg = grad; pMg = Mgrad;
+          grad = hasdof ? Ma - qfrc_smooth - qfrc_c : 0.f;
+        }
+        const float rhs = phase == -1 ? qfrc_smooth : (phase == 99 ? qfrc_smooth + qfrc_c : grad);
+        x = solve(phase == 99, rhs);
+      }
+      // ---- transitions ----
+      if (phase == -1) { qacc_smooth = x; v = x; phase = o.warmstart ? 0 : 2; continue; }
+      if (phase == 0) { cost_s = cost; v = warm; phase = 1; continue; }
+      if (phase == 1) { v = cost < cost_s ? warm : qacc_smooth; phase = 2; continue; }
+      if (phase == 99) { qa_int = x; break; }
+      Mgrad = x;
+      if (phase == 2) {
+        search = -Mgrad;
+      } else {
+        float p2[2] = {grad * (Mgrad - pMg), pg * pMg};
+        reduce_scatter<2>(p2, L);
+        const float num = shf(p2[0], 0), den = shf(p2[0], 16);
+        const float beta = fmaxf(0.f, num / fmaxf(MJ_MINVAL, den));
+        search = -Mgrad + beta * search;
+        niter++;
+      }
       const float improvement = scale * (prev_cost - cost);
       const float gradient = scale * sqrtf(wsum(grad * grad));
       bool done = niter >= o.iterations;
       done |= improvement < o.tolerance;
       done |= gradient < o.tolerance;
-      if (done) break;
-      linesearch();
-      const float pg = grad, pMg = Mgrad;
-      update_constraint();
-      if (trace && L == 0 && 4 * niter + 3 < ZB_NTRACE) trace[4 * niter + 1] = cost;
-      update_gradient();
-      float p2[2] = {grad * (Mgrad - pMg), pg * pMg};
-      reduce_scatter<2>(p2, L);
-      const float num = shf(p2[0], 0), den = shf(p2[0], 16);
-      const float beta = fmaxf(0.f, num / fmaxf(MJ_MINVAL, den));
-      search = -Mgrad + beta * search;
-      niter++;
+      if (done) {
+        if (!implicit_damp) { qa_int = qacc; break; }
+        phase = 99;
+        continue;
+      }
+      phase = 3;
+      v = search;
     }
+    return qa_int;
   }
 
+  // ------------------------------------------------------------------------------------------
   // ------------------------------------------------------------------------------------------
   // sensors + rne_postconstraint (A.11); only evaluated when outputs are written
   // ------------------------------------------------------------------------------------------

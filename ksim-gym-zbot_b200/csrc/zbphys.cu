@@ -34,7 +34,7 @@ static int fail(int code, const char* fmt, const char* a = "") {
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(ZB_WPB * 32) zb_kernel(const ZbDev* __restrict__ D, ZbEnvParams P, ZbState S,
+__global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* __restrict__ D, ZbEnvParams P, ZbState S,
                                                        const float* __restrict__ action, const float* __restrict__ push_rand,
                                                        int push_per_substep, ZbOut O, int n_envs, int n_substeps,
                                                        const uint8_t* __restrict__ done, const float* __restrict__ rq,
@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zb_kernel(const ZbDev* __restrict
   E.q0 = E.hinge ? (P.qpos0 ? P.qpos0[(size_t)env * NQ + d + 1] : m.qpos0[d + 1]) : 0.f;
   E.mu = P.floor_friction ? P.floor_friction[env] : m.floor_friction[0];
   E.mass_tot = wsum(E.mass);
+  E.inv_mass_tot = 1.f / E.mass_tot;
   {
     const int s = E.isbody ? D->body_site[L] : -1;
     const int ss = s >= 0 ? s : 0;
@@ -123,8 +124,15 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zb_kernel(const ZbDev* __restrict
     // ---- mjx.forward ----
     E.kinematics();
     E.mass_matrix();
-    E.factor(E.F0, 0.f);
-    if (implicit_damp && MODE == ZB_MODE_STEP) E.factor(E.F1, dt * E.damp);
+    {  // factor M and (for the implicit integrators) M + dt*diag(damping): one copy of the factorization code
+      const int nfac = (implicit_damp && MODE == ZB_MODE_STEP) ? 2 : 1;
+#pragma unroll 1
+      for (int p = 0; p < nfac; p++) {
+        Factor F;
+        E.factor(F, p ? dt * E.damp : 0.f);
+        if (p == 0) E.F0 = F; else E.F1 = F;
+      }
+    }
     E.collision();
     float qfrc_passive;
     E.velocity(qfrc_passive);
@@ -132,13 +140,10 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zb_kernel(const ZbDev* __restrict
     E.bias_forces();
     const float qfrc_act = E.actuation();
     E.qfrc_smooth = E.hasdof ? qfrc_passive - E.qfrc_bias + qfrc_act : 0.f;
-    E.qacc_smooth = E.solve(E.F0, E.qfrc_smooth);
-    E.solve_constraints();
+    const float qa = E.solve_all(implicit_damp && MODE == ZB_MODE_STEP);
     if (last) E.sensors(sd);
     if (MODE == ZB_MODE_STEP) {
       // ---- euler / implicitfast + _advance ----
-      float qa = E.qacc;
-      if (implicit_damp) qa = E.solve(E.F1, E.qfrc_smooth + E.qfrc_c);
       if (E.hasdof) E.qv += dt * qa;
       if (E.hinge) E.q += dt * E.qv;
       float vb[6];
@@ -277,6 +282,46 @@ static void h_quat_to_mat(float* m, const float* q) {
   m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
 }
 
+// constraint._kbi constants (refsafe uses opt.timestep -> recomputed by zb_engine_set_opts)
+static ZbSolPrm h_solprm(const ZbOpts& o, const float* solref, const float* solimp) {
+  ZbSolPrm s;
+  const float timeconst = fmaxf(solref[0], 2.f * o.dt), dampratio = solref[1];
+  s.dmin = fminf(fmaxf(solimp[0], MJ_MINIMP), MJ_MAXIMP);
+  s.dmax = fminf(fmaxf(solimp[1], MJ_MINIMP), MJ_MAXIMP);
+  s.width = fmaxf(MJ_MINVAL, solimp[2]);
+  s.mid = fminf(fmaxf(solimp[3], MJ_MINIMP), MJ_MAXIMP);
+  s.power = fmaxf(1.f, solimp[4]);
+  s.k = 1.f / (s.dmax * s.dmax * timeconst * timeconst * dampratio * dampratio);
+  s.b = 2.f / (s.dmax * timeconst);
+  if (solref[0] <= 0.f) { s.k = -solref[0] / (s.dmax * s.dmax); s.b = -solref[1] / s.dmax; }
+  s.c1 = 1.f / powf(s.mid, s.power - 1.f);
+  s.c2 = 1.f / powf(1.f - s.mid, s.power - 1.f);
+  return s;
+}
+static void derive_solprm(ZbDev* D) {
+  const ZbModel& m = D->m;
+  for (int L = 0; L < 32; L++) {
+    D->fr_R[L] = 0.f; D->fr_b[L] = 0.f;
+    memset(&D->lim[L], 0, sizeof(ZbSolPrm));
+    const int d = D->lane_dof[L];
+    if (d < 0) continue;
+    if (m.dof_frictionloss[d] > 0.f) {  // pos = 0 -> imp = dmin
+      const ZbSolPrm s = h_solprm(D->o, m.dof_solref[d], m.dof_solimp[d]);
+      const float imp = s.dmin;
+      D->fr_R[L] = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, MJ_MINVAL);
+      D->fr_b[L] = s.b;
+    }
+    D->lim[L] = h_solprm(D->o, m.jnt_solref[d], m.jnt_solimp[d]);
+  }
+  for (int g = 0; g < ZB_NBOX; g++) {
+    const bool floor_wins = m.floor_priority >= m.box_priority[g];
+    D->con[g] = h_solprm(D->o, floor_wins ? m.floor_solref : m.box_solref[g], floor_wins ? m.floor_solimp : m.box_solimp[g]);
+    D->con_mu_mode[g] = m.floor_priority > m.box_priority[g] ? 0 : (m.floor_priority < m.box_priority[g] ? 1 : 2);
+    D->con_includemargin[g] = fmaxf(m.floor_margin, m.box_margin[g]) - fmaxf(m.floor_gap, m.box_gap[g]);
+    D->con_invweight[g] = m.body_invweight0[0][0] + m.body_invweight0[m.box_body[g]][0];
+  }
+}
+
 static int derive(ZbDev* D) {
   const ZbModel& m = D->m;
   if (m.body_jnttype[0] != 0 || m.body_jnttype[1] != 1 || m.body_parent[1] != 0 || m.body_dofadr[1] != 0)
@@ -358,6 +403,7 @@ static int derive(ZbDev* D) {
   }
   D->any_damping = 0;
   for (int i = 0; i < NV; i++) D->any_damping |= m.dof_damping[i] > 0;
+  derive_solprm(D);
   return ZB_OK;
 }
 
@@ -427,10 +473,11 @@ int zb_engine_set_opts(ZbEngine* e, const ZbOpts* opts) {
   int rc = check_opts(opts);
   if (rc) return rc;
   e->host.o = *opts;
+  derive_solprm(&e->host);
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(e->device);
-  cudaError_t ce = cudaMemcpy(&e->dev->o, &e->host.o, sizeof(ZbOpts), cudaMemcpyHostToDevice);
+  cudaError_t ce = cudaMemcpy(e->dev, &e->host, sizeof(ZbDev), cudaMemcpyHostToDevice);
   cudaSetDevice(prev);
   if (ce != cudaSuccess) return fail(ZB_ECUDA, "zb_engine_set_opts: %s", cudaGetErrorString(ce));
   return ZB_OK;

@@ -74,7 +74,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("ZBPHYS_LIB") or LIB_PATH  # ZBPHYS_LIB: tuning variants of the same library
     if not os.path.exists(p):
         raise RuntimeError(f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
                            "There is no CPU fallback for the physics step.")
