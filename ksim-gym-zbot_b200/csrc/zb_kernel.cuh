@@ -86,6 +86,8 @@ struct LSPoint {
 
 struct WarpEnv {
   const ZbDev* D;
+  ZbOpts o;           // by value from the kernel parameters: uniform-datapath registers, provably warp-uniform control flow
+  float meaninertia;
   float* scr;  // per-warp scratch, 32 * ZB_SCR floats
   int L;
   // topology of this lane
@@ -119,8 +121,8 @@ struct WarpEnv {
   int lscount;
 
   // ------------------------------------------------------------------------------------------
-  ZB_DI void init_topology(const ZbDev* D_, float* scr_, int lane) {
-    D = D_; scr = scr_; L = lane;
+  ZB_DI void init_topology(const ZbDev* D_, const ZbOpts& o_, float meaninertia_, float* scr_, int lane) {
+    D = D_; o = o_; meaninertia = meaninertia_; scr = scr_; L = lane;
     isbody = L < NB;
     const int jt = isbody ? D->m.body_jnttype[L] : 0;
     hinge = jt == 2;
@@ -582,9 +584,9 @@ struct WarpEnv {
       const float vl[3] = {vb[0], vb[1], vb[2]};
       float c[3];
       cross3(c, vl, cvel_base);
-      cacc_base_lin[0] = -D->o.gravity[0] + c[0];
-      cacc_base_lin[1] = -D->o.gravity[1] + c[1];
-      cacc_base_lin[2] = -D->o.gravity[2] + c[2];
+      cacc_base_lin[0] = -o.gravity[0] + c[0];
+      cacc_base_lin[1] = -o.gravity[1] + c[1];
+      cacc_base_lin[2] = -o.gravity[2] + c[2];
     }
     qfrc_passive = hasdof ? -damp * qv : 0.f;
   }
@@ -596,7 +598,7 @@ struct WarpEnv {
     chain_prefix<6>(pre);
 #pragma unroll
     for (int k = 0; k < 6; k++) cacc[k] = chainbody ? pre[k] : 0.f;
-    if (L == 0) { cacc[3] = -D->o.gravity[0]; cacc[4] = -D->o.gravity[1]; cacc[5] = -D->o.gravity[2]; }
+    if (L == 0) { cacc[3] = -o.gravity[0]; cacc[4] = -o.gravity[1]; cacc[5] = -o.gravity[2]; }
     else if (isbody) { cacc[3] += cacc_base_lin[0]; cacc[4] += cacc_base_lin[1]; cacc[5] += cacc_base_lin[2]; }
     float cfrc[6], t[6], u[6];
     inert_mul(cfrc, cinert, cacc);
@@ -807,7 +809,7 @@ struct WarpEnv {
       if (c_on) {
         const float imp = impedance(sp, dist);
         const float t = D->con_invweight[g];
-        const float invweight = (t + cmu * cmu * t) * 2.f * cmu * cmu / D->o.impratio;
+        const float invweight = (t + cmu * cmu * t) * 2.f * cmu * cmu / o.impratio;
         const float R = fmaxf(invweight * (1.f - imp) / imp, MJ_MINVAL);
         c_D = 1.f / R;
         c_aref = -sp.b * dot6(w, vf) - sp.k * imp * dist;
@@ -841,14 +843,13 @@ struct WarpEnv {
 
   // exact line search along `search` (MJX _linesearch): three candidate points per iteration, evaluated together
   ZB_DI void linesearch(float cjv) {
-    const ZbOpts& o = D->o;
     const float fr_jv = search, lm_jv = lm_sign * search;
     float p[4] = {search * search, search * Ma - search * qfrc_smooth, search * mv, 0.f};
     if (!hasdof) { p[0] = p[1] = p[2] = 0.f; }
     reduce_scatter<4>(p, L);
     const float snorm = shf(p[0], 0);
     const float qg0 = gauss, qg1 = shf(p[0], 8), qg2 = 0.5f * shf(p[0], 16);
-    const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * D->m.meaninertia * (float)NV);
+    const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * meaninertia * (float)NV);
     // per-row quadratics (MJX: quad = [0.5 D x0^2, D x0 jv, 0.5 D jv^2]; friction rows also have two linear zones)
     const float fq0 = 0.5f * fr_D * fr_ja * fr_ja, fq1 = fr_D * fr_ja * fr_jv, fq2 = 0.5f * fr_D * fr_jv * fr_jv;
     const float fn0 = fr_f * (-0.5f * fr_rf - fr_ja), fp0 = fr_f * (-0.5f * fr_rf + fr_ja), fl1 = fr_f * fr_jv;
@@ -928,7 +929,9 @@ struct WarpEnv {
       done |= !swap;
       done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
       done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
-      if (done) break;
+      // (every lane holds the same values; the vote only makes the exit PROVABLY warp-uniform, otherwise ptxas wraps each
+      //  shuffle of the loop in WARPSYNC/ENDCOLLECTIVE)
+      if (__all_sync(ZB_FULL, done)) break;
       al[0] = lo.alpha - lo.d0 / lo.d1;
       al[1] = hi.alpha - hi.d0 / hi.d1;
       al[2] = 0.5f * (lo.alpha + hi.alpha);
@@ -951,8 +954,7 @@ struct WarpEnv {
 
   // The whole constrained solve + (optionally) the implicit-integration solve.  Returns the integration acceleration.
   ZB_DI float solve_all(bool implicit_damp) {
-    const ZbOpts& o = D->o;
-    const float scale = 1.f / (D->m.meaninertia * (float)NV);
+    const float scale = 1.f / (meaninertia * (float)NV);
     int phase = -1;
     float v = 0.f, cost_s = 0.f, qa_int = 0.f, pg = 0.f, pMg = 0.f;
     cost = 0.f; prev_cost = 0.f; niter = 0; lscount = 0;
@@ -999,7 +1001,7 @@ struct WarpEnv {
       // ---- transitions ----
       if (phase == -1) { qacc_smooth = x; v = x; phase = o.warmstart ? 0 : 2; continue; }
       if (phase == 0) { cost_s = cost; v = warm; phase = 1; continue; }
-      if (phase == 1) { v = cost < cost_s ? warm : qacc_smooth; phase = 2; continue; }
+      if (phase == 1) { v = __all_sync(ZB_FULL, cost < cost_s) ? warm : qacc_smooth; phase = 2; continue; }
       if (phase == 99) { qa_int = x; break; }
       Mgrad = x;
       if (phase == 2) {
@@ -1017,7 +1019,7 @@ struct WarpEnv {
       bool done = niter >= o.iterations;
       done |= improvement < o.tolerance;
       done |= gradient < o.tolerance;
-      if (done) {
+      if (__all_sync(ZB_FULL, done)) {
         if (!implicit_damp) { qa_int = qacc; break; }
         phase = 99;
         continue;
@@ -1049,7 +1051,7 @@ struct WarpEnv {
 #pragma unroll
     for (int k = 0; k < 6; k++) cacc[k] = (chainbody ? pre[k] : 0.f) + Ab[k];
     cacc[3] += cacc_base_lin[0]; cacc[4] += cacc_base_lin[1]; cacc[5] += cacc_base_lin[2];
-    if (L == 0) { cacc[0] = cacc[1] = cacc[2] = 0.f; cacc[3] = -D->o.gravity[0]; cacc[4] = -D->o.gravity[1]; cacc[5] = -D->o.gravity[2]; }
+    if (L == 0) { cacc[0] = cacc[1] = cacc[2] = 0.f; cacc[3] = -o.gravity[0]; cacc[4] = -o.gravity[1]; cacc[5] = -o.gravity[2]; }
     // cfrc_int = local - cfrc_ext, accumulated leaf -> root along the chains
     float cf[6], t[6], u[6];
     inert_mul(cf, cinert, cacc);

@@ -34,7 +34,7 @@ static int fail(int code, const char* fmt, const char* a = "") {
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* __restrict__ D, ZbEnvParams P, ZbState S,
+__global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* __restrict__ D, ZbOpts o, float meaninertia, ZbEnvParams P, ZbState S,
                                                        const float* __restrict__ action, const float* __restrict__ push_rand,
                                                        int push_per_substep, ZbOut O, int n_envs, int n_substeps,
                                                        const uint8_t* __restrict__ done, const float* __restrict__ rq,
@@ -45,9 +45,8 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
   if (env >= n_envs) return;
   if (MODE == ZB_MODE_RESET && done && !done[env]) return;
   const ZbModel& m = D->m;
-  const ZbOpts& o = D->o;
   WarpEnv E;
-  E.init_topology(D, scratch[wib], L);
+  E.init_topology(D, o, meaninertia, scratch[wib], L);
   const int b = E.isbody ? L : 0;
   const int d = E.hasdof ? E.dof : 0;
   // ---- per-environment model (randomizers, train.py:1439-1455) ----
@@ -504,7 +503,7 @@ int zb_step_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbSt
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  zb_kernel<ZB_MODE_STEP><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, P, *state, action, push_rand, push_per_substep, O,
+  zb_kernel<ZB_MODE_STEP><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
                                                                          n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr);
   return after_launch("zb_step_f32 launch: %s");
 }
@@ -518,7 +517,7 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  zb_kernel<ZB_MODE_FORWARD><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+  zb_kernel<ZB_MODE_FORWARD><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
                                                                             nullptr, nullptr, nullptr, nullptr);
   return after_launch("zb_forward_f32 launch: %s");
 }
@@ -533,7 +532,7 @@ int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbS
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  zb_kernel<ZB_MODE_RESET><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
+  zb_kernel<ZB_MODE_RESET><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
                                                                           reset_qpos, reset_qvel, reset_t_rem);
   return after_launch("zb_reset_f32 launch: %s");
 }

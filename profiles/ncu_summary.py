@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (ncu --set full) into the few numbers DESIGN.md / profiles/*.md quote.
+usage: python profiles/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-substring]"""
+import csv, subprocess, sys, io
+rep = sys.argv[1]; want = sys.argv[2] if len(sys.argv) > 2 else "zb_kernel<0>"
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, data = rows[0], rows[1], rows[2:]
+ki = hdr.index("Kernel Name")
+sel = [r for r in data if want.replace("<", "<").split("<")[0] in r[ki] and (("<" + want.split("<")[1]) in r[ki].replace("(int)", "") if "<" in want else True)]
+keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+        "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__warps_eligible.avg.per_cycle_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_shfl.sum", "local_load_requests", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
+for r in sel:
+    print("kernel:", r[ki][:60])
+    for k in keys:
+        if k in hdr:
+            print(f"  {k:75s} {r[hdr.index(k)]:>16s} {units[hdr.index(k)]}")
+    for i, h in enumerate(hdr):
+        if "average_warps_issue_stalled" in h and h.endswith("per_issue_active.ratio"):
+            try:
+                v = float(r[i])
+            except ValueError:
+                continue
+            if v >= 0.15:
+                print(f"  stall {h.split('stalled_')[1].split('_per_issue')[0]:30s} {v:8.2f} warps per issue-active cycle")
