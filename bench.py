@@ -187,14 +187,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from ksim_gym_zbot_b200.engine import EnvParams, PushEventConfig, ZbotCudaEngine
+    from ksim_gym_zbot_b200.sharding import aggregate_throughput, rank_seed
 
     push_cfg = PushEventConfig() if randomized else None
-    eng = ZbotCudaEngine(model, n_env, device=local, opts=opts, ctrl_dt=a.ctrl_dt, push=push_cfg, seed=a.seed + rank)
+    eng = ZbotCudaEngine(model, n_env, device=local, opts=opts, ctrl_dt=a.ctrl_dt, push=push_cfg, seed=rank_seed(a.seed, rank))
     params_np = M.randomize_env_params(model, n_env, a.seed + 100 + rank) if randomized else None
     ep = EnvParams(n_env, dev, **params_np) if randomized else None
     K, W = a.steps, a.warmup
     g = torch.Generator(device=dev)
-    g.manual_seed(a.seed + rank)
+    g.manual_seed(rank_seed(a.seed, rank) + 17)
     bias = torch.tensor(M.BIAS_POSE, dtype=torch.float32, device=dev)
     actions = bias + 0.3 * (torch.rand((K + W, n_env, M.NU), generator=g, device=dev) * 2 - 1)
     pushes = torch.stack([eng.sample_push(n_env) for _ in range(K + W)]) if randomized else None
@@ -248,11 +249,7 @@ def main():
     launches = eng.launch_count() - launches0
     step_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
     total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
-    value = world * n_env * S * K / (total_ms_max * 1e-3)
+    value, total_ms_max = aggregate_throughput(n_env * S * K, total_ms, dev)  # sum of units / max over ranks of device time
     niter_mean = float(ps.data.solver_niter.float().mean().item())
     ncon_mean = float(sum(((ps.data.contact_mask >> c) & 1).float().mean().item() for c in range(8)))
     resets_per_step = float(n_done.item()) / K
@@ -281,10 +278,7 @@ def main():
         torch.cuda.current_stream().synchronize()  # the caller reads the result of step i before issuing step i+1
     e1.record()
     torch.cuda.synchronize()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_env * S * K / (float(e2e_ms.item()) * 1e-3)
+    e2e_value, _ = aggregate_throughput(n_env * S * K, e0.elapsed_time(e1), dev)
     clk = clocks.stop() if rank == 0 else None
 
     # ---------------- FP32 peak probe (roofline denominator; not in MEASURED_PEAKS.json) ----------------

@@ -841,61 +841,87 @@ struct WarpEnv {
   }
   static ZB_DI bool in_bracket(float x, float y) { return (x < y && y < 0.f) || (x > y && y > 0.f); }
 
-  // exact line search along `search` (MJX _linesearch): three candidate points per iteration, evaluated together
+  // Per-row quadratic data of one line search (MJX: quad = [0.5 D x0^2, D x0 jv, 0.5 D jv^2]; friction rows add two
+  // linear zones).  Kept as (D*x0, D*jv) per row: the three coefficients are one multiply away.
+  struct LSRows {
+    float fr_jv, lm_jv, c_jv;
+    float f1, f2, fl, c1, c2, l1, l2;  // D*x0*jv, 0.5*D*jv^2 (and f*jv) of the friction / contact / limit row of this lane
+    float qg0, qg1, qg2;
+  };
+
+  // Evaluate the 1-D cost model at three step sizes.  COST=false: derivatives only (6 sums); COST=true: also the cost.
+  template <bool COST>
+  ZB_DI void ls_eval(const LSRows& r, const float (&al)[3], LSPoint (&pt)[3]) {
+    constexpr int NS = COST ? 16 : 8, PER = COST ? 3 : 2;
+    float s[NS];
+    const bool fr_lin = fr_on && fr_f > 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float a = al[j];
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      if (fr_on) {
+        const float x = fr_ja + a * r.fr_jv;
+        const bool neg = fr_lin && x <= -fr_rf, pos = fr_lin && x >= fr_rf, quad = !(neg || pos);
+        s1 = quad ? r.f1 : (neg ? -r.fl : r.fl);
+        s2 = quad ? r.f2 : 0.f;
+        if (COST) s0 = quad ? 0.5f * fr_D * fr_ja * fr_ja : fr_f * (-0.5f * fr_rf + (neg ? -fr_ja : fr_ja));
+      }
+      if (any_limit && lm_on && (lm_ja + a * r.lm_jv) < 0.f) {
+        s1 += r.l1; s2 += r.l2;
+        if (COST) s0 += 0.5f * lm_D * lm_ja * lm_ja;
+      }
+      if (c_on && (c_ja + a * r.c_jv) < 0.f) {
+        s1 += r.c1; s2 += r.c2;
+        if (COST) s0 += 0.5f * c_D * c_ja * c_ja;
+      }
+      if (COST) { s[3 * j] = s0; s[3 * j + 1] = s1; s[3 * j + 2] = s2; }
+      else { s[2 * j] = s1; s[2 * j + 1] = s2; }
+    }
+#pragma unroll
+    for (int k = 3 * PER; k < NS; k++) s[k] = 0.f;
+    reduce_scatter<NS>(s, L);  // value k lives in lanes k*(32/NS) ..
+    constexpr int STR = 32 / NS;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float a = al[j];
+      const float t1 = shf(s[0], STR * (PER * j + (COST ? 1 : 0))) + r.qg1;
+      const float t2 = shf(s[0], STR * (PER * j + (COST ? 2 : 1))) + r.qg2;
+      // NOT fused on purpose (__fmul_rn/__fadd_rn are never contracted into FMA): when the active set did not change, the
+      // Newton point alpha = -t1 / (2 t2) makes 2*alpha*t2 + t1 round to EXACTLY 0 with separately rounded products, and
+      // the reference's bracket logic treats an exact zero as "not in bracket" (the point is rejected).  An FMA would
+      // return the tiny residual instead and flip that decision in ~14 % of the states (tests/gpu_probe3.py).
+      pt[j].alpha = a;
+      pt[j].d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, a), t2), t1);
+      pt[j].d1 = __fadd_rn(__fmul_rn(2.f, t2), (t2 == 0.f ? MJ_MINVAL : 0.f));
+      pt[j].cost = 0.f;
+      if (COST) {
+        const float t0 = shf(s[0], STR * (PER * j)) + r.qg0;
+        pt[j].cost = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(a, a), t2), __fmul_rn(a, t1)), t0);
+      }
+    }
+  }
+
+  // exact line search along `search` (MJX _linesearch): three candidate points per iteration, evaluated together.
+  // Only the derivatives steer the bracket; the costs of p0 / lo / hi are needed once, for the final pick.
   ZB_DI void linesearch(float cjv) {
-    const float fr_jv = search, lm_jv = lm_sign * search;
+    LSRows r;
+    r.fr_jv = search; r.lm_jv = lm_sign * search; r.c_jv = cjv;
     float p[4] = {search * search, search * Ma - search * qfrc_smooth, search * mv, 0.f};
     if (!hasdof) { p[0] = p[1] = p[2] = 0.f; }
     reduce_scatter<4>(p, L);
     const float snorm = shf(p[0], 0);
-    const float qg0 = gauss, qg1 = shf(p[0], 8), qg2 = 0.5f * shf(p[0], 16);
+    r.qg0 = gauss; r.qg1 = shf(p[0], 8); r.qg2 = 0.5f * shf(p[0], 16);
     const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * meaninertia * (float)NV);
-    // per-row quadratics (MJX: quad = [0.5 D x0^2, D x0 jv, 0.5 D jv^2]; friction rows also have two linear zones)
-    const float fq0 = 0.5f * fr_D * fr_ja * fr_ja, fq1 = fr_D * fr_ja * fr_jv, fq2 = 0.5f * fr_D * fr_jv * fr_jv;
-    const float fn0 = fr_f * (-0.5f * fr_rf - fr_ja), fp0 = fr_f * (-0.5f * fr_rf + fr_ja), fl1 = fr_f * fr_jv;
-    const float lq0 = 0.5f * lm_D * lm_ja * lm_ja, lq1 = lm_D * lm_ja * lm_jv, lq2 = 0.5f * lm_D * lm_jv * lm_jv;
-    const float cq0 = 0.5f * c_D * c_ja * c_ja, cq1 = c_D * c_ja * cjv, cq2 = 0.5f * c_D * cjv * cjv;
-    const bool fr_lin = fr_on && fr_f > 0.f;
-    LSPoint p0, lo, hi;
+    r.f1 = fr_D * fr_ja * r.fr_jv; r.f2 = 0.5f * fr_D * r.fr_jv * r.fr_jv; r.fl = fr_f * r.fr_jv;
+    r.l1 = lm_D * lm_ja * r.lm_jv; r.l2 = 0.5f * lm_D * r.lm_jv * r.lm_jv;
+    r.c1 = c_D * c_ja * r.c_jv; r.c2 = 0.5f * c_D * r.c_jv * r.c_jv;
+    LSPoint p0, lo, hi, pt[3];
     float al[3] = {0.f, 0.f, 0.f};
     bool swap = true;
     int it = 0, stage = 0;
 #pragma unroll 1
     while (true) {
-      // ---- evaluate the three alphas: 9 partial sums -> one transpose-reduce ----
-      float s[16];
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const float a = al[j];
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        if (fr_on) {
-          const float x = fr_ja + a * fr_jv;
-          const bool neg = fr_lin && x <= -fr_rf, pos = fr_lin && x >= fr_rf;
-          s0 = neg ? fn0 : (pos ? fp0 : fq0);
-          s1 = neg ? -fl1 : (pos ? fl1 : fq1);
-          s2 = (neg || pos) ? 0.f : fq2;
-        }
-        if (any_limit && lm_on && (lm_ja + a * lm_jv) < 0.f) { s0 += lq0; s1 += lq1; s2 += lq2; }
-        if (c_on && (c_ja + a * cjv) < 0.f) { s0 += cq0; s1 += cq1; s2 += cq2; }
-        s[3 * j] = s0; s[3 * j + 1] = s1; s[3 * j + 2] = s2;
-      }
-#pragma unroll
-      for (int k = 9; k < 16; k++) s[k] = 0.f;
-      reduce_scatter<16>(s, L);  // lanes 2k, 2k+1 hold total k
-      LSPoint pt[3];
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const float t0 = shf(s[0], 6 * j) + qg0, t1 = shf(s[0], 6 * j + 2) + qg1, t2 = shf(s[0], 6 * j + 4) + qg2;
-        const float a = al[j];
-        // NOT fused on purpose (__fmul_rn/__fadd_rn are never contracted into FMA): when the active set did not change, the
-        // Newton point alpha = -t1 / (2 t2) makes 2*alpha*t2 + t1 round to EXACTLY 0 with separately rounded products, and
-        // the reference's bracket logic treats an exact zero as "not in bracket" (the point is rejected).  An FMA would
-        // return the tiny residual instead and flip that decision in ~14 % of the states (tests/gpu_probe3.py).
-        pt[j].alpha = a;
-        pt[j].cost = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(a, a), t2), __fmul_rn(a, t1)), t0);
-        pt[j].d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, a), t2), t1);
-        pt[j].d1 = __fadd_rn(__fmul_rn(2.f, t2), (t2 == 0.f ? MJ_MINVAL : 0.f));
-      }
+      ls_eval<false>(r, al, pt);
       if (trace && niter == 0 && L == 0) {
         const int np = stage < 2 ? 1 : 3;
         for (int j = 0; j < np; j++)
@@ -936,8 +962,11 @@ struct WarpEnv {
       al[1] = hi.alpha - hi.d0 / hi.d1;
       al[2] = 0.5f * (lo.alpha + hi.alpha);
     }
-    const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
-    const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+    // costs of p0, lo, hi (same model, evaluated once)
+    al[0] = 0.f; al[1] = lo.alpha; al[2] = hi.alpha;
+    ls_eval<true>(r, al, pt);
+    const bool improved = (pt[1].cost < pt[0].cost) || (pt[2].cost < pt[0].cost);
+    const float alpha = pt[1].cost < pt[2].cost ? lo.alpha : hi.alpha;
     if (trace && L == 0 && 4 * niter + 3 < 32) {
       trace[4 * niter] = improved ? alpha : 0.f;
       trace[4 * niter + 2] = (float)it;
@@ -946,9 +975,9 @@ struct WarpEnv {
     if (improved) {
       qacc += search * alpha;
       Ma += mv * alpha;
-      fr_ja += fr_jv * alpha;
-      lm_ja += lm_jv * alpha;
-      c_ja += cjv * alpha;
+      fr_ja += r.fr_jv * alpha;
+      lm_ja += r.lm_jv * alpha;
+      c_ja += r.c_jv * alpha;
     }
   }
 
