@@ -255,14 +255,29 @@ def main():
     resets_per_step = float(n_done.item()) / K
 
     # ---------------- timed region 2: end to end through the public API with HOST buffers ----------------
-    h_act = actions[W:W + K].cpu().pin_memory()
+    # Every step: H2D of that step's actions from pinned memory -> engine.step / terminations / reset -> D2H of everything the
+    # reference's observations, rewards and trajectory read back (train.py:452-461, 476, 681, 854, 882, 1307) + the done mask.
+    # The output arrays are views into ONE device buffer so the read-back is a single copy.
     out_fields = ("qpos", "qvel", "xpos", "xquat", "cinert", "cvel", "qacc", "actuator_force", "sensordata")
-    h_out = {k: torch.empty_like(getattr(ps.data, k), device="cpu").pin_memory() for k in out_fields}
-    h_out["act_torque"] = torch.empty_like(ps.actuator_state.last_computed_torque, device="cpu").pin_memory()
+    sizes = {k: getattr(ps.data, k).numel() for k in out_fields}
+    sizes["act_torque"] = ps.actuator_state.last_computed_torque.numel()
+    flat = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
+    off = 0
+    for k, nel in sizes.items():
+        cur = ps.actuator_state.last_computed_torque if k == "act_torque" else getattr(ps.data, k)
+        view = flat[off:off + nel].view(cur.shape)
+        view.copy_(cur)
+        if k == "act_torque":
+            ps.actuator_state.last_computed_torque = view
+        else:
+            setattr(ps.data, k, view)
+        off += nel
+    h_act = actions[W:W + K].cpu().pin_memory()
+    h_flat = torch.empty_like(flat, device="cpu").pin_memory()
     h_done = torch.empty_like(done, device="cpu").pin_memory()
     d_act = torch.empty((n_env, M.NU), dtype=torch.float32, device=dev)
     h2d = h_act[0].numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in h_out.values()) + h_done.numel()
+    d2h = h_flat.numel() * 4 + h_done.numel()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -271,9 +286,7 @@ def main():
     for i in range(K):
         d_act.copy_(h_act[i], non_blocking=True)
         ctrl_step(W + i, d_act)
-        for k in out_fields:
-            h_out[k].copy_(getattr(ps.data, k), non_blocking=True)
-        h_out["act_torque"].copy_(ps.actuator_state.last_computed_torque, non_blocking=True)
+        h_flat.copy_(flat, non_blocking=True)
         h_done.copy_(done, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the result of step i before issuing step i+1
     e1.record()

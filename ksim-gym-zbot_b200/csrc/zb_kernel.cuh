@@ -84,6 +84,8 @@ struct LSPoint {
   float alpha, cost, d0, d1;
 };
 
+// TRACE: compile the solver-trace diagnostics in (tests/gpu_probe*.py); the production instantiation carries none of it.
+template <bool TRACE>
 struct WarpEnv {
   const ZbDev* D;
   ZbOpts o;           // by value from the kernel parameters: uniform-datapath registers, provably warp-uniform control flow
@@ -922,7 +924,7 @@ struct WarpEnv {
 #pragma unroll 1
     while (true) {
       ls_eval<false>(r, al, pt);
-      if (trace && niter == 0 && L == 0) {
+      if (TRACE && trace && niter == 0 && L == 0) {
         const int np = stage < 2 ? 1 : 3;
         for (int j = 0; j < np; j++)
           if (32 + 3 * lscount + 2 < ZB_NTRACE) {
@@ -967,7 +969,7 @@ struct WarpEnv {
     ls_eval<true>(r, al, pt);
     const bool improved = (pt[1].cost < pt[0].cost) || (pt[2].cost < pt[0].cost);
     const float alpha = pt[1].cost < pt[2].cost ? lo.alpha : hi.alpha;
-    if (trace && L == 0 && 4 * niter + 3 < 32) {
+    if (TRACE && trace && L == 0 && 4 * niter + 3 < 32) {
       trace[4 * niter] = improved ? alpha : 0.f;
       trace[4 * niter + 2] = (float)it;
       trace[4 * niter + 3] = sqrtf(snorm);
@@ -1014,7 +1016,7 @@ struct WarpEnv {
         gauss = shf(p2[0], 16);
         prev_cost = phase == 2 ? INFINITY : cost;
         cost = gauss + shf(p2[0], 0);
-        if (trace && L == 0 && phase >= 3 && 4 * niter + 3 < 32) trace[4 * niter + 1] = cost;
+        if (TRACE && trace && L == 0 && phase >= 3 && 4 * niter + 3 < 32) trace[4 * niter + 1] = cost;
       }
       float x = 0.f;
       if (phase == -1 || phase >= 2) {

@@ -33,7 +33,7 @@ static int fail(int code, const char* fmt, const char* a = "") {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* __restrict__ D, ZbOpts o, float meaninertia, ZbEnvParams P, ZbState S,
                                                        const float* __restrict__ action, const float* __restrict__ push_rand,
                                                        int push_per_substep, ZbOut O, int n_envs, int n_substeps,
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
   if (env >= n_envs) return;
   if (MODE == ZB_MODE_RESET && done && !done[env]) return;
   const ZbModel& m = D->m;
-  WarpEnv E;
+  WarpEnv<TRACE> E;
   E.init_topology(D, o, meaninertia, scratch[wib], L);
   const int b = E.isbody ? L : 0;
   const int d = E.hasdof ? E.dof : 0;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
   const bool implicit_damp = o.integrator == ZB_INT_IMPLICITFAST || (o.integrator == ZB_INT_EULER && o.eulerdamp && D->any_damping);
   const int nsub = MODE == ZB_MODE_STEP ? n_substeps : 1;
   float* sd = O.sensordata ? O.sensordata + (size_t)env * ZB_NSENSORDATA : nullptr;
-  E.trace = O.solver_trace ? O.solver_trace + (size_t)env * ZB_NTRACE : nullptr;
+  E.trace = (TRACE && O.solver_trace) ? O.solver_trace + (size_t)env * ZB_NTRACE : nullptr;
 
   for (int s = 0; s < nsub; s++) {
     const bool last = s == nsub - 1;
@@ -503,7 +503,9 @@ int zb_step_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbSt
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  zb_kernel<ZB_MODE_STEP><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
+  if (O.solver_trace) zb_kernel<ZB_MODE_STEP, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
+                                                                         n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr);
+  else zb_kernel<ZB_MODE_STEP, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
                                                                          n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr);
   return after_launch("zb_step_f32 launch: %s");
 }
@@ -517,7 +519,9 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  zb_kernel<ZB_MODE_FORWARD><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+  if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+                                                                            nullptr, nullptr, nullptr, nullptr);
+  else zb_kernel<ZB_MODE_FORWARD, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
                                                                             nullptr, nullptr, nullptr, nullptr);
   return after_launch("zb_forward_f32 launch: %s");
 }
@@ -532,7 +536,9 @@ int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbS
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  zb_kernel<ZB_MODE_RESET><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
+  if (O.solver_trace) zb_kernel<ZB_MODE_RESET, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
+                                                                          reset_qpos, reset_qvel, reset_t_rem);
+  else zb_kernel<ZB_MODE_RESET, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
                                                                           reset_qpos, reset_qvel, reset_t_rem);
   return after_launch("zb_reset_f32 launch: %s");
 }
