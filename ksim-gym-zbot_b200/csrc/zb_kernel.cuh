@@ -103,14 +103,14 @@ struct WarpEnv {
   float apos, avel, atq, tgt, ctrl;
   // kinematics
   float xpos[3], xquat[4], xmat[9], xipos[3], xb[3], Rb[9], c0[3];
-  float cinert[10], cdof[6], cdofd[6], cvel[6], cb3[3][6];
+  float cinert[10], cdof[6], cdofd[6], cvel[6];
   float sxpos[3], sxmat[9];
   // dynamics
   float Bm[6], C[CHD];
   Factor F0, F1;
   float qfrc_smooth, qacc_smooth, act_force, qfrc_bias;
   // constraint rows
-  bool fr_on, lm_on, c_on, any_limit;
+  bool fr_on, lm_on, c_on, any_limit, fr_quad;
   float fr_D, fr_rf, fr_f, fr_aref, lm_sign, lm_D, lm_aref, c_D, c_aref, w[6];
   float cdist, cpos[3];
   // solver
@@ -159,6 +159,19 @@ struct WarpEnv {
         const float u = __shfl_down_sync(ZB_FULL, v[k], d);
         if (take) v[k] += u;
       }
+    }
+  }
+
+  // cdof of the three rotational free-joint dofs (columns of the base rotation about the tree COM), uniform in all lanes
+  ZB_DI void base_rot_cdofs(float (&cb)[3][6]) const {
+    const float r[3] = {c0[0] - xb[0], c0[1] - xb[1], c0[2] - xb[2]};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float col[3] = {Rb[i], Rb[3 + i], Rb[6 + i]};
+      float c[3];
+      cross3(c, col, r);
+      cb[i][0] = col[0]; cb[i][1] = col[1]; cb[i][2] = col[2];
+      cb[i][3] = c[0]; cb[i][4] = c[1]; cb[i][5] = c[2];
     }
   }
 
@@ -263,17 +276,10 @@ struct WarpEnv {
         for (int k = 0; k < 10; k++) cinert[k] = 0.f;
       }
     }
-    // cdof.  The three rotational free-joint dofs are computed by every lane (uniform): cb3
+    // cdof.  The three rotational free-joint dofs are computed by every lane (uniform)
     {
-      const float r[3] = {c0[0] - xb[0], c0[1] - xb[1], c0[2] - xb[2]};
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const float col[3] = {Rb[i], Rb[3 + i], Rb[6 + i]};
-        float c[3];
-        cross3(c, col, r);
-        cb3[i][0] = col[0]; cb3[i][1] = col[1]; cb3[i][2] = col[2];
-        cb3[i][3] = c[0]; cb3[i][4] = c[1]; cb3[i][5] = c[2];
-      }
+      float cb3[3][6];
+      base_rot_cdofs(cb3);
 #pragma unroll
       for (int k = 0; k < 6; k++) cdof[k] = 0.f;
       if (hinge) {
@@ -305,6 +311,37 @@ struct WarpEnv {
     }
   }
 
+  // Rows of a tree-structured symmetric matrix  X[i][j] = cdof_j . f_i  (j an ancestor-or-self dof of i), in block form:
+  // hinge lanes get their chain-block row (full, by symmetry) and their coupling to the six base dofs; base lanes get their
+  // 6x6 row.  f = (composite inertia) x cdof gives the mass matrix, f = (sum_r D_r w_r w_r^T) x cdof the Newton J^T D J.
+  ZB_DI void assemble_rows(const float (&f)[6], float (&rb)[6], float (&rc)[CHD]) {
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      float ck[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) ck[j] = shf(cdof[j], gs + k);
+      rc[k] = (hinge && k <= gp) ? dot6(ck, f) : 0.f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHD; k++) scr[L * ZB_SCR + k] = rc[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      const float t = scr[((gs + k) & 31) * ZB_SCR + gp];
+      if (hinge && k > gp && k < gn) rc[k] = t;
+    }
+    __syncwarp();
+    float cb3[3][6];
+    base_rot_cdofs(cb3);
+    rb[0] = f[3]; rb[1] = f[4]; rb[2] = f[5];
+    rb[3] = dot6(cb3[0], f); rb[4] = dot6(cb3[1], f); rb[5] = dot6(cb3[2], f);
+    if (!hasdof) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) rb[k] = 0.f;
+    }
+  }
+
   // ------------------------------------------------------------------------------------------
   // smooth.crb + support.make_m in block form
   // ------------------------------------------------------------------------------------------
@@ -329,31 +366,7 @@ struct WarpEnv {
     }
     float f[6];
     inert_mul(f, crb, cdof);
-    // chain block C: entries k <= gp from cdof of the ancestors, upper part by symmetry (scratch transpose)
-#pragma unroll
-    for (int k = 0; k < CHD; k++) {
-      float ck[6];
-#pragma unroll
-      for (int j = 0; j < 6; j++) ck[j] = shf(cdof[j], gs + k);
-      C[k] = (hinge && k <= gp) ? dot6(ck, f) : 0.f;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < CHD; k++) scr[L * ZB_SCR + k] = C[k];
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < CHD; k++) {
-      const float t = scr[((gs + k) & 31) * ZB_SCR + gp];
-      if (hinge && k > gp && k < gn) C[k] = t;
-    }
-    __syncwarp();
-    // coupling to the base dofs (hinge lanes: B row; base lanes: A row)
-    Bm[0] = f[3]; Bm[1] = f[4]; Bm[2] = f[5];
-    Bm[3] = dot6(cb3[0], f); Bm[4] = dot6(cb3[1], f); Bm[5] = dot6(cb3[2], f);
-    if (!hasdof) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) Bm[k] = 0.f;
-    }
+    assemble_rows(f, Bm, C);
     // armature on the diagonal
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
@@ -384,17 +397,17 @@ struct WarpEnv {
   }
 
   // smooth.factor_m as a block Cholesky of (M + diag(extra))
-  ZB_DI void factor(Factor& F, float extra) {
+  ZB_DI void factor(Factor& F, const float (&Bsrc)[6], const float (&Csrc)[CHD], float extra) {
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
-      F.lc[k] = hinge ? C[k] + (k == gp ? extra : 0.f) : 0.f;
+      F.lc[k] = hinge ? Csrc[k] + (k == gp ? extra : 0.f) : 0.f;
       F.lt[k] = 0.f;
     }
     F.inv = 1.f;
     group_chol(F.lc, F.inv, hinge);
     // W = L_c^-1 B by forward substitution, six right-hand sides
 #pragma unroll
-    for (int a = 0; a < 6; a++) F.W[a] = hinge ? Bm[a] : 0.f;
+    for (int a = 0; a < 6; a++) F.W[a] = hinge ? Bsrc[a] : 0.f;
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
       if (hinge && gp == k) {
@@ -426,7 +439,7 @@ struct WarpEnv {
         const int lo = a < b ? a : b, hi = a < b ? b : a;
         const int idx = lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);
         const float s = shf(p[0], idx);
-        F.lc[b] = bdof ? Bm[b] - s + (b == gp ? extra : 0.f) : F.lc[b];
+        F.lc[b] = bdof ? Bsrc[b] - s + (b == gp ? extra : 0.f) : F.lc[b];
       }
     }
     group_chol(F.lc, F.inv, bdof);
@@ -830,12 +843,12 @@ struct WarpEnv {
   // forces and cost of the rows at the current Jaref; returns this lane's partial constraint cost
   ZB_DI float row_update() {
     float cst = 0.f;
-    fr_force = 0.f; lm_force = 0.f; c_force = 0.f;
+    fr_force = 0.f; lm_force = 0.f; c_force = 0.f; fr_quad = false;
     if (fr_on) {
       const float x = fr_ja;
       if (x <= -fr_rf && fr_f > 0.f) { fr_force = fr_f; cst += fr_f * (-0.5f * fr_rf - x); }
       else if (x >= fr_rf && fr_f > 0.f) { fr_force = -fr_f; cst += fr_f * (-0.5f * fr_rf + x); }
-      else { fr_force = -fr_D * x; cst += 0.5f * fr_D * x * x; }
+      else { fr_force = -fr_D * x; cst += 0.5f * fr_D * x * x; fr_quad = true; }
     }
     if (lm_on && lm_ja < 0.f) { lm_force = -lm_D * lm_ja; cst += 0.5f * lm_D * lm_ja * lm_ja; }
     if (c_on && c_ja < 0.f) { c_force = -c_D * c_ja; cst += 0.5f * c_D * c_ja * c_ja; }
@@ -983,9 +996,87 @@ struct WarpEnv {
     }
   }
 
+  // Newton: H = M + J^T diag(D * active) J (solver._update_gradient), same tree block structure as M.
+  // Contact rows enter through the 6x6 "constraint inertia" of each box, Wm_g = sum_r D_r w_r w_r^T, exactly like the
+  // composite inertia enters the mass matrix; friction-loss / limit rows add D on the diagonal.
+  ZB_DI void newton_hessian(float (&Hb)[6], float (&Hc)[CHD]) {
+    const float a = (c_on && c_ja < 0.f) ? c_D : 0.f;
+    float p16[16], p8[8];
+    {
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+          const float v = a * w[i] * w[j];
+          if (t < 16) p16[t] = v; else p8[t - 16] = v;
+          t++;
+        }
+      p8[5] = p8[6] = p8[7] = 0.f;
+    }
+    // sums over the 16 row lanes of each box: masks 8,4,2,1 only (the two halves stay separate)
+    {
+      int m = 8;
+#pragma unroll
+      for (int half = 8; half >= 1; half >>= 1, m >>= 1) {
+        const bool up = (L & m) != 0;
+#pragma unroll
+        for (int j = 0; j < half; j++) {
+          const float send = up ? p16[j] : p16[j + half], keep = up ? p16[j + half] : p16[j];
+          p16[j] = keep + __shfl_xor_sync(ZB_FULL, send, m);
+        }
+      }
+      m = 8;
+#pragma unroll
+      for (int half = 4; half >= 1; half >>= 1, m >>= 1) {
+        const bool up = (L & m) != 0;
+#pragma unroll
+        for (int j = 0; j < half; j++) {
+          const float send = up ? p8[j] : p8[j + half], keep = up ? p8[j + half] : p8[j];
+          p8[j] = keep + __shfl_xor_sync(ZB_FULL, send, m);
+        }
+      }
+      p8[0] += __shfl_xor_sync(ZB_FULL, p8[0], 1);
+    }
+    // value t < 16 of box g sits in lane 16 g + t, value 16 + u in lanes 16 g + 2u (+1): publish through the scratch
+    __syncwarp();
+    {
+      const int g = L >> 4;
+      scr[g * 24 + (L & 15)] = p16[0];
+      if ((L & 1) == 0 && ((L >> 1) & 7) < 5) scr[g * 24 + 16 + ((L >> 1) & 7)] = p8[0];
+    }
+    __syncwarp();
+    float Wm[21];
+#pragma unroll
+    for (int t = 0; t < 21; t++) {
+      const float w0 = scr[t], w1 = scr[24 + t];
+      Wm[t] = bdof ? w0 + w1 : (hinge && lbox == 0 ? w0 : (hinge && lbox == 1 ? w1 : 0.f));
+    }
+    __syncwarp();
+    float f[6];
+    {
+      float Mx[6][6];
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) { Mx[i][j] = Wm[t]; Mx[j][i] = Wm[t]; t++; }
+#pragma unroll
+      for (int i = 0; i < 6; i++) f[i] = Mx[i][0] * cdof[0] + Mx[i][1] * cdof[1] + Mx[i][2] * cdof[2] + Mx[i][3] * cdof[3] + Mx[i][4] * cdof[4] + Mx[i][5] * cdof[5];
+    }
+    assemble_rows(f, Hb, Hc);
+    const float dg = (fr_on && fr_quad ? fr_D : 0.f) + (lm_on && lm_ja < 0.f ? lm_D : 0.f);
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      Hc[k] = hinge ? Hc[k] + C[k] + (k == gp ? dg : 0.f) : 0.f;
+      Hb[k] = Hb[k] + Bm[k] + ((bdof && k == gp) ? dg : 0.f);
+    }
+  }
+
   // The whole constrained solve + (optionally) the implicit-integration solve.  Returns the integration acceleration.
   ZB_DI float solve_all(bool implicit_damp) {
     const float scale = 1.f / (meaninertia * (float)NV);
+    const bool newton = o.solver == ZB_SOLVER_NEWTON;
     int phase = -1;
     float v = 0.f, cost_s = 0.f, qa_int = 0.f, pg = 0.f, pMg = 0.f;
     cost = 0.f; prev_cost = 0.f; niter = 0; lscount = 0;
@@ -1026,6 +1117,11 @@ struct WarpEnv {
           pg = grad; pMg = Mgrad;
           grad = hasdof ? Ma - qfrc_smooth - qfrc_c : 0.f;
         }
+        if (newton && phase >= 2 && phase < 99) {  // F0 (factor of M) is not needed any more once qacc_smooth exists
+          float Hb[6], Hc[CHD];
+          newton_hessian(Hb, Hc);
+          factor(F0, Hb, Hc, 0.f);
+        }
         const float rhs = phase == -1 ? qfrc_smooth : (phase == 99 ? qfrc_smooth + qfrc_c : grad);
         x = solve(phase == 99, rhs);
       }
@@ -1037,6 +1133,9 @@ struct WarpEnv {
       Mgrad = x;
       if (phase == 2) {
         search = -Mgrad;
+      } else if (newton) {
+        search = -Mgrad;
+        niter++;
       } else {
         float p2[2] = {grad * (Mgrad - pMg), pg * pMg};
         reduce_scatter<2>(p2, L);

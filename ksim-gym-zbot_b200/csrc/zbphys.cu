@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
 #pragma unroll 1
       for (int p = 0; p < nfac; p++) {
         Factor F;
-        E.factor(F, p ? dt * E.damp : 0.f);
+        E.factor(F, E.Bm, E.C, p ? dt * E.damp : 0.f);
         if (p == 0) E.F0 = F; else E.F1 = F;
       }
     }
@@ -408,7 +408,7 @@ static int derive(ZbDev* D) {
 
 static int check_opts(const ZbOpts* o) {
   if (!(o->dt > 0) || o->iterations < 0 || o->ls_iterations < 0 || !(o->impratio > 0)) return fail(ZB_EINVAL, "opts: dt/iterations/impratio invalid%s");
-  if (o->solver != ZB_SOLVER_CG) return fail(ZB_EUNSUP, "opts: only ZB_SOLVER_CG is built into the kernels%s");
+  if (o->solver != ZB_SOLVER_CG && o->solver != ZB_SOLVER_NEWTON) return fail(ZB_EINVAL, "opts: unknown solver%s");
   if (o->integrator != ZB_INT_EULER && o->integrator != ZB_INT_IMPLICITFAST) return fail(ZB_EINVAL, "opts: unknown integrator%s");
   if (o->substep_order != ZB_ORDER_EVENT_ACT_STEP && o->substep_order != ZB_ORDER_ACT_EVENT_STEP) return fail(ZB_EINVAL, "opts: unknown substep_order%s");
   return ZB_OK;

@@ -223,6 +223,27 @@ def test_control_step_parity(zmodel, S, dt):
     _assert_close("time", r, "time", 1e-6)
 
 
+def test_newton_solver(zmodel):
+    """ZB_SOLVER_NEWTON (H = M + J^T D J factored every iteration): forward + one control step against the oracle's Newton."""
+    from ksim_gym_zbot_b200 import model as M
+
+    n = 256
+    r = _run_both(zmodel, n, 4, 81, dt=0.005, params=_params(zmodel, n, 8), opts_kw={"solver": M.SOLVER_NEWTON})
+    c, a, b = r["cuda_reset"], r["f32_reset"], r["f64_reset"]
+    np.testing.assert_array_equal(c["contact_mask"], b["contact_mask"])
+    assert c["solver_niter"].mean() < 6  # Newton needs few iterations
+    for k, tol, floor in [("qacc", 2e-4, 10.0), ("qfrc_constraint", 2e-4, 1.0), ("efc_force", 2e-4, 1.0), ("sensordata", 2e-4, 10.0)]:
+        _assert_close(k, r, k, tol, floor, which="_reset")
+    _assert_close("qpos", r, "qpos", 2e-5)
+    _assert_close("qvel", r, "qvel", 2e-4)
+    # converged Newton == converged CG (both through the kernel)
+    kw = {"iterations": 100, "ls_iterations": 50, "tolerance": 1e-12}
+    rn = _run_both(zmodel, 64, 1, 82, opts_kw={**kw, "solver": M.SOLVER_NEWTON})
+    rc = _run_both(zmodel, 64, 1, 82, opts_kw={**kw, "solver": M.SOLVER_CG})
+    assert rel_err(rn["cuda_reset"]["qacc"], rc["cuda_reset"]["qacc"], 10.0) < 6e-2
+    assert rel_err(rn["cuda_reset"]["qacc"], rn["f64_reset"]["qacc"], 10.0) < 6e-2
+
+
 def test_push_event_and_order(zmodel):
     """PushEvent timer/kick (pre-sampled numbers) in both substep orders, per-step and per-substep random layouts."""
     n, S = 64, 4
