@@ -29,10 +29,13 @@
 #define BL0 (32 - 6) /* first base-dof lane */
 #define CHD 6        /* dof positions per chain group (legs: 6, arms: 4) */
 #ifndef ZB_WPB
-#define ZB_WPB 4 /* warps (environments) per CTA */
+#define ZB_WPB 16 /* warps (environments) per CTA: one 512-thread CTA per SM at 128 registers */
+#endif
+#ifndef ZB_CTA_LOCKSTEP
+#define ZB_CTA_LOCKSTEP 1 /* 1: the warps of a CTA meet at every substep (shared instruction fetch: +30 %); 2: also before every solver pass (measured slower: waits for the slowest line search) */
 #endif
 #ifndef ZB_MINB
-#define ZB_MINB 4 /* min resident CTAs per SM the register allocation must allow */
+#define ZB_MINB 1 /* min resident CTAs per SM the register allocation must allow */
 #endif
 #define ZB_SCR 8     /* scratch floats per lane */
 
@@ -85,7 +88,8 @@ struct LSPoint {
 };
 
 // TRACE: compile the solver-trace diagnostics in (tests/gpu_probe*.py); the production instantiation carries none of it.
-template <bool TRACE>
+// LOCK: CTA-lockstep barriers (see solve_all).
+template <bool TRACE, bool LOCK>
 struct WarpEnv {
   const ZbDev* D;
   ZbOpts o;           // by value from the kernel parameters: uniform-datapath registers, provably warp-uniform control flow
@@ -1084,8 +1088,15 @@ struct WarpEnv {
     fr_force = lm_force = c_force = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; k++) Wf[k] = 0.f;
+    // LOCK: the warps of a CTA meet at a barrier before every pass (solver iteration).  They then stream the same
+    // instructions and share I-cache lines (instruction fetch was the top stall); a warp whose solve has finished keeps
+    // arriving at the barrier until the slowest one is done (it would wait for it at the next substep barrier anyway).
+    bool finished = false;
 #pragma unroll 1
     while (true) {
+      if (LOCK) { if (__syncthreads_and(finished)) break; }
+      else if (finished) break;
+      if (finished) continue;
       if (phase >= 0 && phase < 99) {
         // ---- operator application: mv = M v, contact rows J v ----
         float vb[6];
@@ -1129,7 +1140,7 @@ struct WarpEnv {
       if (phase == -1) { qacc_smooth = x; v = x; phase = o.warmstart ? 0 : 2; continue; }
       if (phase == 0) { cost_s = cost; v = warm; phase = 1; continue; }
       if (phase == 1) { v = __all_sync(ZB_FULL, cost < cost_s) ? warm : qacc_smooth; phase = 2; continue; }
-      if (phase == 99) { qa_int = x; break; }
+      if (phase == 99) { qa_int = x; finished = true; continue; }
       Mgrad = x;
       if (phase == 2) {
         search = -Mgrad;
@@ -1150,7 +1161,7 @@ struct WarpEnv {
       done |= improvement < o.tolerance;
       done |= gradient < o.tolerance;
       if (__all_sync(ZB_FULL, done)) {
-        if (!implicit_damp) { qa_int = qacc; break; }
+        if (!implicit_damp) { qa_int = qacc; finished = true; continue; }
         phase = 99;
         continue;
       }

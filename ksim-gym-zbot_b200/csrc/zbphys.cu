@@ -41,11 +41,19 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
                                                        const float* __restrict__ rv, const float* __restrict__ rt) {
   __shared__ float scratch[ZB_WPB][32 * ZB_SCR];
   const int L = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = blockIdx.x * ZB_WPB + wib;
+  int env = blockIdx.x * ZB_WPB + wib;
+#if ZB_CTA_LOCKSTEP
+  // keep the warps of a CTA in step at substep boundaries so that they stream the same instructions (shared I-cache lines);
+  // a tail warp then has to stay alive: it recomputes the last environment and stores nothing
+  const bool live = env < n_envs;
+  if (!live) { if (MODE != ZB_MODE_STEP) return; env = n_envs - 1; }
+#else
+  const bool live = true;
   if (env >= n_envs) return;
+#endif
   if (MODE == ZB_MODE_RESET && done && !done[env]) return;
   const ZbModel& m = D->m;
-  WarpEnv<TRACE> E;
+  WarpEnv<TRACE, (ZB_CTA_LOCKSTEP >= 2) && MODE == ZB_MODE_STEP> E;
   E.init_topology(D, o, meaninertia, scratch[wib], L);
   const int b = E.isbody ? L : 0;
   const int d = E.hasdof ? E.dof : 0;
@@ -101,6 +109,9 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
 
   for (int s = 0; s < nsub; s++) {
     const bool last = s == nsub - 1;
+#if ZB_CTA_LOCKSTEP
+    if (MODE == ZB_MODE_STEP) __syncthreads();
+#endif
     if (MODE == ZB_MODE_STEP) {
 #pragma unroll
       for (int phase = 0; phase < 2; phase++) {
@@ -165,6 +176,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
     }
   }
 
+  if (!live) return;
   // ---- state write-back ----
   {  // base pose (MJX writes the normalised free-joint quaternion back into qpos, also in forward())
     float v = E.bq[0];
