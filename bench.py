@@ -5,9 +5,9 @@
     python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host cores (oracle port)
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU, weak scaling
 
-A "step" is ONE CONTROL STEP of the whole batch: S fused physics substeps (PushEvent -> Feetech servo -> mjx.step)
-in one kernel launch, followed by the termination check and the partial reset of finished environments — the body of
-ksim's rollout scan around the engine.  One env-step = one physics substep of one environment.
+A "step" is ONE CONTROL STEP of the whole batch: S fused physics substeps (PushEvent -> Feetech servo -> mjx.step), the
+termination check and the partial reset of finished environments — the body of ksim's rollout scan around the engine
+ — in ONE kernel launch (zb_step_autoreset_f32).  One env-step = one physics substep of one environment.
 Default workload = BASELINE.json configs[1]: 4096 envs, random actions, ctrl_dt = 0.02 s with 4 substeps.
 """
 from __future__ import annotations
@@ -206,9 +206,8 @@ def main():
     n_done = torch.zeros((), dtype=torch.int64, device=dev)
 
     def ctrl_step(t, act):
-        eng.step(act, ep, ps, push_rand=None if pushes is None else pushes[t])
-        eng.terminations(ps, done)
-        eng.reset(ep, physics_state=ps, done=done, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
+        # ONE launch: S fused substeps + termination check + partial reset (zb_step_autoreset_f32)
+        eng.step(act, ep, ps, push_rand=None if pushes is None else pushes[t], auto_reset=(rq, rv, rt), done_out=done)
 
     for t in range(W):
         ctrl_step(t, actions[t])
@@ -237,10 +236,8 @@ def main():
         t = W + i
         flush.zero_()  # L2 flush, outside the event pair
         ev[i][0].record()
-        eng.step(actions[t], ep, ps, push_rand=None if pushes is None else pushes[t])
+        ctrl_step(t, actions[t])
         ev[i][1].record()
-        eng.terminations(ps, done)
-        eng.reset(ep, physics_state=ps, done=done, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
         ev[i][2].record()
         n_done += done.sum()
     torch.cuda.synchronize()

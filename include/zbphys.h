@@ -225,6 +225,18 @@ int zb_step_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, 
                 const float* action, const float* push_rand, int push_per_substep, const ZbOut* out,
                 int n_envs, int n_substeps);
 
+/* zb_step_f32 followed, inside the same launch, by the rollout's termination check and partial reset
+ * (ksim RLTask._single_unroll: `done -> engine.reset`, BadZTermination / NotUprightTermination of
+ * /root/reference/train.py:1588-1593): for every environment whose integrated state terminates
+ * (z outside [z_lo, z_hi], base tilt above max_tilt_rad, or non-finite), the state is replaced by
+ * reset_qpos/reset_qvel/reset_t_rem (host-sampled per ksim resets, train.py:1471-1476), PlannerState re-initialised
+ * (train.py:1293-1298), time/warm-start cleared and forward() run on it — exactly zb_terminations_f32 +
+ * zb_reset_f32(done).  done_out [N] (may be NULL) receives the termination mask. */
+int zb_step_autoreset_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, const ZbState* state,
+                          const float* action, const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs,
+                          int n_substeps, const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem,
+                          uint8_t* done_out, float z_lo, float z_hi, float max_tilt_rad);
+
 /* mjx.forward on the current state (no integration, state untouched except the free-joint
  * quaternion normalisation MJX writes back) — what MjxEngine.reset runs after the resets. */
 int zb_forward_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, const ZbState* state,

@@ -16,6 +16,14 @@
 
 #define ZB_ABI_VERSION 1
 
+// auto-reset pass of the step kernel (zb_step_autoreset_f32)
+struct ZbAutoReset {
+  int enabled;
+  float z_lo, z_hi, cos_tilt;
+  const float *reset_qpos, *reset_qvel, *reset_t_rem;
+  uint8_t* done_out;
+};
+
 struct ZbEngine {
   ZbDev host;
   ZbDev* dev;
@@ -38,7 +46,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
                                                        const float* __restrict__ action, const float* __restrict__ push_rand,
                                                        int push_per_substep, ZbOut O, int n_envs, int n_substeps,
                                                        const uint8_t* __restrict__ done, const float* __restrict__ rq,
-                                                       const float* __restrict__ rv, const float* __restrict__ rt) {
+                                                       const float* __restrict__ rv, const float* __restrict__ rt, ZbAutoReset AR) {
   __shared__ float scratch[ZB_WPB][32 * ZB_SCR];
   const int L = threadIdx.x & 31, wib = threadIdx.x >> 5;
   int env = blockIdx.x * ZB_WPB + wib;
@@ -107,12 +115,33 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
   float* sd = O.sensordata ? O.sensordata + (size_t)env * ZB_NSENSORDATA : nullptr;
   E.trace = (TRACE && O.solver_trace) ? O.solver_trace + (size_t)env * ZB_NTRACE : nullptr;
 
-  for (int s = 0; s < nsub; s++) {
+  // s == nsub is the optional auto-reset pass (zb_step_autoreset_f32): terminate -> reset state -> forward(), i.e.
+  // zb_terminations_f32 + zb_reset_f32(done) folded into the step launch (first half).
+  for (int s = 0; s <= nsub; s++) {
     const bool last = s == nsub - 1;
+    const bool extra = s == nsub;
 #if ZB_CTA_LOCKSTEP
     if (MODE == ZB_MODE_STEP) __syncthreads();
 #endif
-    if (MODE == ZB_MODE_STEP) {
+    if (extra) {
+      if (!(MODE == ZB_MODE_STEP && AR.enabled)) break;
+      const float up = E.bq[3] * E.bq[3] - E.bq[4] * E.bq[4] - E.bq[5] * E.bq[5] + E.bq[6] * E.bq[6];
+      const bool nonfinite = !(isfinite(E.q) && isfinite(E.qv) && isfinite(E.bq[0]) && isfinite(E.bq[1]) && isfinite(E.bq[2]) && isfinite(E.bq[3]));
+      bool bad = (E.bq[2] < AR.z_lo) || (E.bq[2] > AR.z_hi) || (up < AR.cos_tilt) || !isfinite(E.bq[2]) || !isfinite(up);
+      bad = __any_sync(ZB_FULL, bad || nonfinite);
+      if (L == 0 && AR.done_out && live) AR.done_out[env] = bad ? 1 : 0;
+      if (!bad) break;
+#pragma unroll
+      for (int k = 0; k < 7; k++) E.bq[k] = AR.reset_qpos[(size_t)env * NQ + k];
+      E.q = E.hinge ? AR.reset_qpos[(size_t)env * NQ + d + 1] : 0.f;
+      E.qv = E.hasdof ? AR.reset_qvel[(size_t)env * NV + d] : 0.f;
+      E.warm = 0.f;
+      E.apos = E.act >= 0 ? E.q : 0.f; E.avel = E.act >= 0 ? E.qv : 0.f; E.atq = 0.f; E.ctrl = 0.f;
+      trem = AR.reset_t_rem ? AR.reset_t_rem[env] : 0.f;
+      tm = 0.f;
+    }
+    const bool stepping = MODE == ZB_MODE_STEP && !extra;
+    if (stepping) {
 #pragma unroll
       for (int phase = 0; phase < 2; phase++) {
         const bool do_event = (o.substep_order == ZB_ORDER_EVENT_ACT_STEP) ? phase == 0 : phase == 1;
@@ -135,7 +164,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
     E.kinematics();
     E.mass_matrix();
     {  // factor M and (for the implicit integrators) M + dt*diag(damping): one copy of the factorization code
-      const int nfac = (implicit_damp && MODE == ZB_MODE_STEP) ? 2 : 1;
+      const int nfac = (implicit_damp && stepping) ? 2 : 1;
 #pragma unroll 1
       for (int p = 0; p < nfac; p++) {
         Factor F;
@@ -150,9 +179,10 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
     E.bias_forces();
     const float qfrc_act = E.actuation();
     E.qfrc_smooth = E.hasdof ? qfrc_passive - E.qfrc_bias + qfrc_act : 0.f;
-    const float qa = E.solve_all(implicit_damp && MODE == ZB_MODE_STEP);
-    if (last) E.sensors(sd);
-    if (MODE == ZB_MODE_STEP) {
+    const float qa = E.solve_all(implicit_damp && stepping);
+    if (last || extra) E.sensors(sd);
+    if (extra) E.warm = 0.f;
+    if (stepping) {
       // ---- euler / implicitfast + _advance ----
       if (E.hasdof) E.qv += dt * qa;
       if (E.hinge) E.q += dt * E.qv;
@@ -505,8 +535,8 @@ static int after_launch(const char* what) {
   return ZB_OK;
 }
 
-int zb_step_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
-                const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps) {
+static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
+                     const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps, ZbAutoReset AR) {
   if (!e || !action) return fail(ZB_EINVAL, "zb_step_f32: null engine/action%s");
   if (n_envs < 0 || n_substeps < 1) return fail(ZB_EINVAL, "zb_step_f32: n_envs >= 0 and n_substeps >= 1 required%s");
   int rc = check_state(state);
@@ -516,10 +546,28 @@ int zb_step_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbSt
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
   if (O.solver_trace) zb_kernel<ZB_MODE_STEP, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
-                                                                         n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr);
+                                                                         n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR);
   else zb_kernel<ZB_MODE_STEP, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
-                                                                         n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr);
+                                                                         n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR);
   return after_launch("zb_step_f32 launch: %s");
+}
+
+int zb_step_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
+                const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps) {
+  ZbAutoReset AR;
+  memset(&AR, 0, sizeof(AR));
+  return step_impl(e, stream, params, state, action, push_rand, push_per_substep, out, n_envs, n_substeps, AR);
+}
+
+int zb_step_autoreset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
+                          const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps,
+                          const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem, uint8_t* done_out,
+                          float z_lo, float z_hi, float max_tilt_rad) {
+  if (!reset_qpos || !reset_qvel) return fail(ZB_EINVAL, "zb_step_autoreset_f32: null reset_qpos/reset_qvel%s");
+  ZbAutoReset AR;
+  AR.enabled = 1; AR.z_lo = z_lo; AR.z_hi = z_hi; AR.cos_tilt = cosf(max_tilt_rad);
+  AR.reset_qpos = reset_qpos; AR.reset_qvel = reset_qvel; AR.reset_t_rem = reset_t_rem; AR.done_out = done_out;
+  return step_impl(e, stream, params, state, action, push_rand, push_per_substep, out, n_envs, n_substeps, AR);
 }
 
 int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const ZbOut* out, int n_envs) {
@@ -532,9 +580,9 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
   if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
-                                                                            nullptr, nullptr, nullptr, nullptr);
+                                                                            nullptr, nullptr, nullptr, nullptr, ZbAutoReset{});
   else zb_kernel<ZB_MODE_FORWARD, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
-                                                                            nullptr, nullptr, nullptr, nullptr);
+                                                                            nullptr, nullptr, nullptr, nullptr, ZbAutoReset{});
   return after_launch("zb_forward_f32 launch: %s");
 }
 
@@ -549,9 +597,9 @@ int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbS
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
   if (O.solver_trace) zb_kernel<ZB_MODE_RESET, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
-                                                                          reset_qpos, reset_qvel, reset_t_rem);
+                                                                          reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{});
   else zb_kernel<ZB_MODE_RESET, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
-                                                                          reset_qpos, reset_qvel, reset_t_rem);
+                                                                          reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{});
   return after_launch("zb_reset_f32 launch: %s");
 }
 

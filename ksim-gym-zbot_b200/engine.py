@@ -57,7 +57,7 @@ ZbOut = _ptr_struct("ZbOut", _OUT_F32 + _OUT_I32 + ["solver_trace"])
 
 ZB_OK, ZB_EINVAL, ZB_ENODEV, ZB_ECUDA, ZB_EUNSUP = 0, -1, -2, -3, -4
 EXPORTS = ["zb_engine_create", "zb_engine_destroy", "zb_engine_set_opts", "zb_step_f32", "zb_forward_f32", "zb_reset_f32",
-           "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count", "zb_bench_ffma", "zb_terminations_f32"]
+           "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count", "zb_bench_ffma", "zb_terminations_f32", "zb_step_autoreset_f32"]
 
 
 class ZbError(RuntimeError):
@@ -86,6 +86,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.zb_engine_set_opts.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     lib.zb_step_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.zb_step_autoreset_f32.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + \
+        [ctypes.c_void_p] * 4 + [ctypes.c_float] * 3
     lib.zb_forward_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     lib.zb_reset_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -350,8 +352,12 @@ class ZbotCudaEngine:
 
     def step(self, action: torch.Tensor, physics_model: EnvParams | None, physics_state: PhysicsState,
              curriculum_level: float = 1.0, rng=None, push_rand: torch.Tensor | None = None,
-             n_substeps: int | None = None) -> PhysicsState:
-        """MjxEngine.step: one control step = ``phys_steps_per_ctrl_steps`` fused physics substeps (in place)."""
+             n_substeps: int | None = None, auto_reset: tuple | None = None, done_out: torch.Tensor | None = None,
+             z_lo: float = 0.05, z_hi: float = 0.5, max_tilt: float = math.radians(60)) -> PhysicsState:
+        """MjxEngine.step: one control step = ``phys_steps_per_ctrl_steps`` fused physics substeps (in place).
+
+        ``auto_reset=(reset_qpos, reset_qvel, reset_t_rem)`` folds the rollout's termination check + partial reset
+        (train.py:1588-1593, 1471-1476) into the same launch; ``done_out`` (uint8 [N]) receives the mask."""
         ps = physics_state
         n = ps.data.qpos.shape[0]
         if not (action.is_cuda and action.dtype == torch.float32 and action.is_contiguous()):
@@ -366,10 +372,19 @@ class ZbotCudaEngine:
             per_substep = 1 if push_rand.dim() == 3 else 0
         S = self.phys_steps_per_ctrl_steps if n_substeps is None else int(n_substeps)
         st, out = self._c_state(ps), self._c_out(ps)
-        rc = self.lib.zb_step_f32(self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st),
-                                  ctypes.c_void_p(action.data_ptr()),
-                                  None if push_rand is None else ctypes.c_void_p(push_rand.data_ptr()), per_substep,
-                                  ctypes.byref(out), n, S)
+        pr = None if push_rand is None else ctypes.c_void_p(push_rand.data_ptr())
+        if auto_reset is None:
+            rc = self.lib.zb_step_f32(self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st),
+                                      ctypes.c_void_p(action.data_ptr()), pr, per_substep, ctypes.byref(out), n, S)
+        else:
+            rq, rv, rt = auto_reset
+            for t in (rq, rv) + ((rt,) if rt is not None else ()):
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+            rc = self.lib.zb_step_autoreset_f32(
+                self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st), ctypes.c_void_p(action.data_ptr()), pr,
+                per_substep, ctypes.byref(out), n, S, ctypes.c_void_p(rq.data_ptr()), ctypes.c_void_p(rv.data_ptr()),
+                None if rt is None else ctypes.c_void_p(rt.data_ptr()),
+                None if done_out is None else ctypes.c_void_p(done_out.data_ptr()), z_lo, z_hi, max_tilt)
         self._check(rc)
         ps.most_recent_action = action
         return ps

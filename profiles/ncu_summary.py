@@ -7,7 +7,7 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 ki = hdr.index("Kernel Name")
-sel = [r for r in data if want.replace("<", "<").split("<")[0] in r[ki] and (("<" + want.split("<")[1]) in r[ki].replace("(int)", "") if "<" in want else True)]
+sel = [r for r in data if want.split("<")[0] in r[ki] and ("<" not in want or ("<" + want.split("<")[1].rstrip(">")) in r[ki].replace("(int)", "").replace("(bool)", ""))]
 keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
         "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__warps_eligible.avg.per_cycle_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",

