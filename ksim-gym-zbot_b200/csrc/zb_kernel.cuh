@@ -976,8 +976,13 @@ struct WarpEnv {
       // (every lane holds the same values; the vote only makes the exit PROVABLY warp-uniform, otherwise ptxas wraps each
       //  shuffle of the loop in WARPSYNC/ENDCOLLECTIVE)
       if (__all_sync(ZB_FULL, done)) break;
-      al[0] = lo.alpha - lo.d0 / lo.d1;
-      al[1] = hi.alpha - hi.d0 / hi.d1;
+      // Newton steps from both ends.  A bracket end often sits on an EXACTLY zero derivative (see ls_make_point); 0 / d1
+      // sends the IEEE division into its out-of-line special-case path, so skip it (warp-uniform branch, same result).
+      float q_lo = 0.f, q_hi = 0.f;
+      if (lo.d0 != 0.f) q_lo = lo.d0 / lo.d1;
+      if (hi.d0 != 0.f) q_hi = hi.d0 / hi.d1;
+      al[0] = lo.alpha - q_lo;
+      al[1] = hi.alpha - q_hi;
       al[2] = 0.5f * (lo.alpha + hi.alpha);
       zz[0] = zone_at(r, al[0]); zz[1] = zone_at(r, al[1]); zz[2] = zone_at(r, al[2]);
       const bool f0 = __any_sync(ZB_FULL, zz[0] != Slo.z), f1 = __any_sync(ZB_FULL, zz[1] != Shi.z);
