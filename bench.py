@@ -326,6 +326,13 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None  # DRAM bytes per launch of the step kernel from the committed ncu capture of THIS workload, if there is one
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(a.workload)
+        if tr and tr["envs"] == n_env and tr["substeps"] == S:
+            traffic = tr["bytes_per_launch"]
+    except Exception:
+        pass
     bytes_ctrl = algorithmic_bytes_per_ctrl_step(randomized, randomized)
     step_s = step_ms * 1e-3 / K  # average duration of the dominant kernel (zb_kernel<STEP>)
     roof = {
@@ -333,7 +340,8 @@ def main():
         "achieved": None if flops_per is None else flops_per * n_env * S / step_s / 1e12,
         "peak": fp32_peak, "peak_source": "measured in this run (FFMA probe zb_bench_ffma; MEASURED_PEAKS.json has no FP32 figure)",
         "frac": None if flops_per is None else flops_per * n_env * S / step_s / 1e12 / fp32_peak,
-        "traffic": None, "flops_per_env_step": flops_per, "flops_source": "oracle op counters (fp32, 64-env sample of this workload)",
+        "traffic": traffic, "traffic_note": "ncu dram bytes per launch (profiles/r1_traffic.json); algorithmic bytes per launch = %d" % (bytes_ctrl * n_env),
+        "flops_per_env_step": flops_per, "flops_source": "oracle op counters (fp32, 64-env sample of this workload)",
         "kernel_ms_per_launch": step_ms / K, "kernel_share_of_step": step_ms / total_ms,
         "hbm": {"bound": "hbm", "unit": "GB/s", "achieved": bytes_ctrl * n_env / step_s / 1e9, "peak": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "frac": bytes_ctrl * n_env / step_s / 1e9 / hbm_peak,
