@@ -304,6 +304,64 @@ def test_partial_reset(zmodel):
     eng.close()
 
 
+def test_joint_limit_rows(zmodel):
+    """States with several joints beyond their range: limit rows active in the kernel exactly where the oracle has them."""
+    from ksim_gym_zbot_b200 import model as M
+
+    n = 128
+    q, v = random_states(zmodel, n, 101)
+    rng = np.random.default_rng(102)
+    lo, hi = zmodel.field("jnt_range")[6:, 0], zmodel.field("jnt_range")[6:, 1]
+    for i in range(n):
+        js = rng.choice(20, size=3, replace=False)
+        for j in js:
+            q[i, 7 + j] = (lo[j] - rng.uniform(0.01, 0.1)) if rng.random() < 0.5 else (hi[j] + rng.uniform(0.01, 0.1))
+    opts = M.make_opts(dt=0.002)
+    eng = _engine(zmodel, n, opts=opts, ctrl_dt=0.002)
+    ps = eng.reset(reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(v), reset_t_rem=torch.full((n,), 1e9))
+    c = _to_np(ps)
+    o = _oracle(zmodel, opts, np.float64)
+    st, out = o.new_state(n), o.new_out(n)
+    o.reset(st, q, v, np.full(n, 1e9), out=out)
+    lim_c, lim_o = c["efc_force"][:, 26:52] != 0, out["efc_force"][:, 26:52] != 0
+    assert lim_o.sum() >= 2 * n  # the case set really has active limits
+    assert (lim_c == lim_o).mean() > 0.995
+    assert (c["efc_force"][:, 26:52] >= 0).all()
+    e = np.abs(c["qacc"] - out["qacc"]) / np.maximum(10, np.abs(out["qacc"]))
+    assert np.median(e.max(axis=1)) < 5e-3
+    eng.close()
+
+
+def test_tail_warps_nan_flag_and_independence(zmodel):
+    """n not a multiple of the 16 environments per CTA; a NaN environment is flagged, does not disturb its neighbours
+    (environments are independent) and is recovered by the auto-reset pass."""
+    n = 37
+    q, v = random_states(zmodel, n, 111)
+    act = torch.tensor(random_actions(n, 112), device="cuda")
+    res = []
+    for poison in (False, True):
+        eng = _engine(zmodel, n, dt=0.005, ctrl_dt=0.02)
+        vv = v.copy()
+        if poison:
+            vv[3, 8] = np.nan
+        ps = eng.reset(reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(vv), reset_t_rem=torch.full((n,), 1e9))
+        eng.step(act, None, ps)
+        res.append(_to_np(ps))
+        if poison:
+            assert res[-1]["flags"][3] == 1 and res[-1]["flags"].sum() == 1
+            rq, rv = random_states(zmodel, n, 113, tilt=0.01)
+            done = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            eng.step(act, None, ps, auto_reset=(torch.tensor(rq, device="cuda"), torch.tensor(rv, device="cuda"), None), done_out=done)
+            after = _to_np(ps)
+            assert done[3] == 1 and np.isfinite(after["qpos"]).all() and np.isfinite(after["xpos"]).all()
+            assert after["flags"].sum() == 0 and after["time"][3] == 0
+        eng.close()
+    clean, bad = res
+    keep = np.arange(n) != 3
+    for k in ("qpos", "qvel", "xpos", "sensordata", "act_torque"):
+        np.testing.assert_array_equal(clean[k][keep], bad[k][keep], err_msg=k)
+
+
 def test_autoreset_equals_three_calls(zmodel):
     """zb_step_autoreset_f32 == zb_step_f32 + zb_terminations_f32 + zb_reset_f32(done), bit for bit."""
     n, S = 300, 4
