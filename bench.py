@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)  # rollout length of the reference: 4.0 s / 0.02 s (train.py:1775)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="BASELINE.json configs[1] / configs[2]")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"], help="BASELINE.json configs[1] / configs[2] / configs[4] (contact-heavy)")
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="0 = 4096 (c2) / 16384 (c3)")
     ap.add_argument("--substeps", type=int, default=4, help="physics substeps per control step (BASELINE config: 4; train.py:1777: 20)")
     ap.add_argument("--ctrl-dt", type=float, default=0.02)
@@ -160,10 +160,12 @@ def main():
 
     model = M.build_zbot_syn()
     opts = M.make_opts(dt=a.ctrl_dt / S, iterations=a.solver_iterations, ls_iterations=a.ls_iterations)
-    randomized = a.workload == "c3"
+    randomized = a.workload in ("c3", "c5")
     config = {
-        "workload": ("BASELINE.json configs[1]: Z-Bot 4096 envs random-action rollout, ctrl_dt=0.02, 4 substeps" if a.workload == "c2"
-                     else "BASELINE.json configs[2]: Z-Bot 16384 envs, push + friction/mass randomization + resets"),
+        "workload": {"c2": "BASELINE.json configs[1]: Z-Bot 4096 envs random-action rollout, ctrl_dt=0.02, 4 substeps",
+                     "c3": "BASELINE.json configs[2]: Z-Bot 16384 envs, push + friction/mass randomization + resets",
+                     "c5": "BASELINE.json configs[4]: contact-heavy (falls and pushes): resets tilted up to 40 deg and dropped from +8 cm, "
+                           "pushes every 0.2-0.4 s at 10x magnitude, randomization + resets"}[a.workload],
         "model": "zbot_syn v1 (synthetic Z-Bot topology; the real MJCF is not shipped with the reference)",
         "envs_per_gpu": n_env, "substeps": S, "dt": a.ctrl_dt / S, "ctrl_dt": a.ctrl_dt, "solver": "cg",
         "iterations": a.solver_iterations, "ls_iterations": a.ls_iterations, "integrator": "implicitfast",
@@ -190,6 +192,8 @@ def main():
     from ksim_gym_zbot_b200.sharding import aggregate_throughput, rank_seed
 
     push_cfg = PushEventConfig() if randomized else None
+    if a.workload == "c5":
+        push_cfg = PushEventConfig(x_linvel=1.0, y_linvel=1.0, z_linvel=0.5, interval_range=(0.2, 0.4))
     eng = ZbotCudaEngine(model, n_env, device=local, opts=opts, ctrl_dt=a.ctrl_dt, push=push_cfg, seed=rank_seed(a.seed, rank))
     params_np = M.randomize_env_params(model, n_env, a.seed + 100 + rank) if randomized else None
     ep = EnvParams(n_env, dev, **params_np) if randomized else None
@@ -200,6 +204,13 @@ def main():
     actions = bias + 0.3 * (torch.rand((K + W, n_env, M.NU), generator=g, device=dev) * 2 - 1)
     pushes = torch.stack([eng.sample_push(n_env) for _ in range(K + W)]) if randomized else None
     rq, rv, rt = eng.sample_reset(n_env)
+    if a.workload == "c5":  # tilted + dropped reset states
+        ax = torch.randn((n_env, 3), generator=g, device=dev)
+        ax = ax / ax.norm(dim=1, keepdim=True)
+        ang = (torch.rand((n_env,), generator=g, device=dev) * 2 - 1) * math.radians(40)
+        rq[:, 3] = torch.cos(ang / 2)
+        rq[:, 4:7] = ax * torch.sin(ang / 2)[:, None]
+        rq[:, 2] += 0.08
     ps = eng.reset(ep, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
     done = torch.zeros((n_env,), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -376,8 +387,24 @@ def run_reference(a, model, opts, S, n_env, randomized, config, world):
     v = np.zeros((n, M.NV), np.float32)
     v[:, 6:] = rng.uniform(-0.01, 0.01, (n, M.NU))
     params = {k: x for k, x in M.randomize_env_params(model, n, a.seed + 100).items()} if randomized else None
-    o.reset(st, q, v, np.full(n, 1e9, np.float32), params=params)
+    if a.workload == "c5":  # tilted + dropped reset states, as in the CUDA arm
+        ax = rng.normal(size=(n, 3))
+        ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+        ang = rng.uniform(-1, 1, n) * math.radians(40)
+        q[:, 3] = np.cos(ang / 2)
+        q[:, 4:7] = ax * np.sin(ang / 2)[:, None]
+        q[:, 2] += 0.08
+    # PushEvent numbers (same stand-in sampler as engine.sample_push)
+    scale = np.array([0.1, 0.1, 0.05, 0, 0, 0], np.float32) * (10.0 if a.workload == "c5" else 1.0)
+    iv = (0.2, 0.4) if a.workload == "c5" else (2.0, 4.0)
     K, W = a.steps, a.warmup
+    pushes = None
+    t_rem0 = np.full(n, 1e9, np.float32)
+    if randomized:
+        u = rng.uniform(0, 1, (K + W, n, 8)).astype(np.float32)
+        pushes = np.concatenate([(u[..., :6] * 2 - 1) * scale * ((0.05 + 0.10 * u[..., 6:7]) / 0.15), iv[0] + (iv[1] - iv[0]) * u[..., 7:8]], axis=-1).astype(np.float32)
+        t_rem0 = rng.uniform(iv[0], iv[1], n).astype(np.float32)
+    o.reset(st, q, v, t_rem0, params=params)
     acts = (M.BIAS_POSE[None, None] + 0.3 * rng.uniform(-1, 1, (K + W, n, M.NU))).astype(np.float32)
 
     def term(s):
@@ -386,10 +413,10 @@ def run_reference(a, model, opts, S, n_env, randomized, config, world):
         return ((qq[:, 2] < 0.05) | (qq[:, 2] > 0.5) | (up < 0.5) | ~np.isfinite(qq[:, 2])).astype(np.uint8)
 
     def ctrl_step(t):
-        o.step(st, acts[t], S, params=params)
+        o.step(st, acts[t], S, params=params, push_rand=None if pushes is None else pushes[t])
         d = term(st)
         if d.any():
-            o.reset(st, q, v, np.full(n, 1e9, np.float32), done=d, params=params)
+            o.reset(st, q, v, t_rem0, done=d, params=params)
 
     for t in range(W):
         ctrl_step(t)

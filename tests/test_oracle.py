@@ -222,6 +222,31 @@ def test_cg_and_newton_agree_at_convergence(zmodel):
         np.testing.assert_allclose(d.get("efc_J").T @ d.get("efc_force"), d.get("qfrc_constraint"), atol=1e-10)
 
 
+def test_force_law_and_cost_monotone(zmodel):
+    """efc_force == -D (J qacc - aref) on the active rows (Huber-clamped on friction rows) at ANY solver output, and the
+    solver cost never increases from one iteration to the next (trace[4 i + 1])."""
+    q, v = random_states(zmodel, 8, 20)
+    for solver in (M.SOLVER_CG, M.SOLVER_NEWTON):
+        o = zo.Oracle(zmodel, M.make_opts(solver=solver), np.float64)
+        for i in range(8):
+            d = o.forward_one(q[i], v[i], ctrl=np.zeros(20))
+            jar = d.get("efc_J") @ d.get("qacc") - d.get("efc_aref")
+            D, f, t, fl, R = d.get("efc_D"), d.get("efc_force"), d.get("efc_type"), d.get("efc_floss"), d.get("efc_R")
+            for r in range(len(t)):
+                if t[r] == 0:
+                    assert f[r] == 0
+                elif t[r] == 1:
+                    exp = np.clip(-D[r] * jar[r], -fl[r], fl[r])
+                    assert abs(f[r] - exp) < 1e-9 * max(1, abs(exp)), (r, f[r], exp)
+                    assert abs(R[r] * D[r] - 1) < 1e-12
+                else:
+                    exp = -D[r] * jar[r] if jar[r] < 0 else 0.0
+                    assert abs(f[r] - exp) < 1e-9 * max(1, abs(exp)), (r, f[r], exp)
+            costs = d.get("trace")[1:4 * d.solver_niter:4]
+            assert np.all(np.diff(costs) <= 1e-9 * np.abs(costs[:-1]) + 1e-12), costs
+            assert d.solver_niter <= 8
+
+
 def test_constraint_rows(zmodel):
     """Row bookkeeping: friction rows on the 20 hinge dofs, limits only when violated, 4 pyramid rows per active contact."""
     m = zmodel
