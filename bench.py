@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--ls-iterations", type=int, default=8)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-shards", type=int, default=4, help="environment blocks (streams) the end-to-end loop drives the batch in")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -263,40 +264,67 @@ def main():
     resets_per_step = float(n_done.item()) / K
 
     # ---------------- timed region 2: end to end through the public API with HOST buffers ----------------
-    # Every step: H2D of that step's actions from pinned memory -> engine.step / terminations / reset -> D2H of everything the
-    # reference's observations, rewards and trajectory read back (train.py:452-461, 476, 681, 854, 882, 1307) + the done mask.
-    # The output arrays are views into ONE device buffer so the read-back is a single copy.
+    # Every step: H2D of that step's actions from pinned memory -> engine.step (one launch incl. termination + reset) -> D2H of
+    # everything the reference's observations, rewards and trajectory read back (train.py:452-461, 476, 681, 854, 882, 1307)
+    # + the done mask; the host waits for all of it before it issues the next step.  The batch is driven as `--e2e-shards`
+    # environment blocks on separate streams (the C ABI takes any [lo, hi) block), so one block's read-back overlaps the other
+    # block's kernel; each block's outputs are views into ONE device buffer, i.e. one D2H copy per block.
     out_fields = ("qpos", "qvel", "xpos", "xquat", "cinert", "cvel", "qacc", "actuator_force", "sensordata")
-    sizes = {k: getattr(ps.data, k).numel() for k in out_fields}
-    sizes["act_torque"] = ps.actuator_state.last_computed_torque.numel()
-    flat = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
-    off = 0
-    for k, nel in sizes.items():
-        cur = ps.actuator_state.last_computed_torque if k == "act_torque" else getattr(ps.data, k)
-        view = flat[off:off + nel].view(cur.shape)
-        view.copy_(cur)
-        if k == "act_torque":
-            ps.actuator_state.last_computed_torque = view
-        else:
-            setattr(ps.data, k, view)
-        off += nel
+    nsh = max(1, min(a.e2e_shards, n_env // 16))
+    from ksim_gym_zbot_b200.sharding import shard_range
+
+    shards = []
+    for k in range(nsh):
+        lo, hi = shard_range(n_env, nsh, k)
+        sp = eng.new_state(hi - lo)
+        for f in ("qpos", "qvel", "qacc_warmstart", "time"):
+            getattr(sp.data, f).copy_(getattr(ps.data, f)[lo:hi])
+        for f in ("position", "velocity", "last_computed_torque"):
+            getattr(sp.actuator_state, f).copy_(getattr(ps.actuator_state, f)[lo:hi])
+        sp.event_states["push_t_rem"].copy_(ps.event_states["push_t_rem"][lo:hi])
+        sizes = {f: getattr(sp.data, f).numel() for f in out_fields}
+        sizes["act_torque"] = sp.actuator_state.last_computed_torque.numel()
+        flat = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
+        off = 0
+        for f, nel in sizes.items():
+            cur = sp.actuator_state.last_computed_torque if f == "act_torque" else getattr(sp.data, f)
+            view = flat[off:off + nel].view(cur.shape)
+            view.copy_(cur)
+            if f == "act_torque":
+                sp.actuator_state.last_computed_torque = view
+            else:
+                setattr(sp.data, f, view)
+            off += nel
+        shards.append(dict(lo=lo, hi=hi, ps=sp, flat=flat, h_flat=torch.empty_like(flat, device="cpu").pin_memory(),
+                           done=torch.zeros((hi - lo,), dtype=torch.uint8, device=dev),
+                           h_done=torch.empty((hi - lo,), dtype=torch.uint8).pin_memory(),
+                           d_act=torch.empty((hi - lo, M.NU), dtype=torch.float32, device=dev),
+                           ep=None if ep is None else ep.slice(lo, hi), rq=rq[lo:hi].contiguous(), rv=rv[lo:hi].contiguous(),
+                           rt=rt[lo:hi].contiguous(), stream=torch.cuda.Stream(device=dev)))
     h_act = actions[W:W + K].cpu().pin_memory()
-    h_flat = torch.empty_like(flat, device="cpu").pin_memory()
-    h_done = torch.empty_like(done, device="cpu").pin_memory()
-    d_act = torch.empty((n_env, M.NU), dtype=torch.float32, device=dev)
     h2d = h_act[0].numel() * 4
-    d2h = h_flat.numel() * 4 + h_done.numel()
+    d2h = sum(sh["h_flat"].numel() * 4 + sh["h_done"].numel() for sh in shards)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main = torch.cuda.current_stream()
     e0.record()
+    for sh in shards:
+        sh["stream"].wait_stream(main)
     for i in range(K):
-        d_act.copy_(h_act[i], non_blocking=True)
-        ctrl_step(W + i, d_act)
-        h_flat.copy_(flat, non_blocking=True)
-        h_done.copy_(done, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the result of step i before issuing step i+1
+        t = W + i
+        for sh in shards:
+            with torch.cuda.stream(sh["stream"]):
+                sh["d_act"].copy_(h_act[i, sh["lo"]:sh["hi"]], non_blocking=True)
+                eng.step(sh["d_act"], sh["ep"], sh["ps"], push_rand=None if pushes is None else pushes[t, sh["lo"]:sh["hi"]],
+                         auto_reset=(sh["rq"], sh["rv"], sh["rt"]), done_out=sh["done"])
+                sh["h_flat"].copy_(sh["flat"], non_blocking=True)
+                sh["h_done"].copy_(sh["done"], non_blocking=True)
+        for sh in shards:
+            sh["stream"].synchronize()  # the caller reads the result of step i before issuing step i+1
+    for sh in shards:
+        main.wait_stream(sh["stream"])
     e1.record()
     torch.cuda.synchronize()
     e2e_value, _ = aggregate_throughput(n_env * S * K, e0.elapsed_time(e1), dev)
@@ -361,7 +389,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "streams": nsh},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         "stats": {"solver_niter_mean_last_step": niter_mean, "active_contacts_mean_last_step": ncon_mean, "resets_per_step": resets_per_step,
                   "ctrl_steps_per_s": value / S, "solver_niter_mean_cpu_sample": niter_cpu, "flops_per_stage": flops_stage},
