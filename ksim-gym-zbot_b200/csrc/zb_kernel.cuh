@@ -465,13 +465,8 @@ struct WarpEnv {
   }
 
   // smooth.solve_m: x <- (M + diag)^-1 x, x distributed over the dof lanes
-  ZB_DI float solve(bool second, float x) {
-    Factor F;  // select which factorization (M or M + dt D) — cheaper than a second copy of this code
-#pragma unroll
-    for (int k = 0; k < CHD; k++) { F.lc[k] = second ? F1.lc[k] : F0.lc[k]; F.lt[k] = second ? F1.lt[k] : F0.lt[k]; }
-#pragma unroll
-    for (int k = 0; k < 6; k++) F.W[k] = second ? F1.W[k] : F0.W[k];
-    F.inv = second ? F1.inv : F0.inv;
+  ZB_DI float solve(float x) {
+    const Factor& F = F0;  // solve_all moves the (M + dt D) factor into F0 before the integration solve
     if (!hasdof) x = 0.f;
     // chains: forward substitution
 #pragma unroll
@@ -942,21 +937,35 @@ struct WarpEnv {
   ZB_DI void linesearch(float cjv) {
     LSRows r;
     r.fr_jv = search; r.lm_jv = lm_sign * search; r.c_jv = cjv;
-    float p[4] = {search * search, search * Ma - search * qfrc_smooth, search * mv, 0.f};
-    if (!hasdof) { p[0] = p[1] = p[2] = 0.f; }
-    reduce_scatter<4>(p, L);
-    const float snorm = shf(p[0], 0);
-    r.qg0 = gauss; r.qg1 = shf(p[0], 8); r.qg2 = 0.5f * shf(p[0], 16);
-    const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * meaninertia * (float)NV);
     r.f1 = fr_D * fr_ja * r.fr_jv; r.f2 = 0.5f * fr_D * r.fr_jv * r.fr_jv; r.fl = fr_f * r.fr_jv;
     r.l1 = lm_D * lm_ja * r.lm_jv; r.l2 = 0.5f * lm_D * r.lm_jv * r.lm_jv;
     r.c1 = c_D * c_ja * r.c_jv; r.c2 = 0.5f * c_D * r.c_jv * r.c_jv;
     LSPoint p0, lo, hi, pt[3];
     LSSet S0, Slo, Shi, st[3];
     float al[3] = {0.f, 0.f, 0.f};
-    int zz[3] = {zone_at(r, 0.f), 0, 0};
-    ls_eval<1>(r, al, zz, pt, st);  // p0 = point(0)
-    p0 = pt[0]; S0 = st[0];
+    int zz[3] = {0, 0, 0};
+    float snorm;
+    {
+      // |search|^2, the Gauss part of the quadratic and the row sums of p0 = point(0) in ONE transpose-reduce
+      const int z = zone_at(r, 0.f);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      if (fr_on) {
+        const bool neg = (z & 1) != 0, pos = (z & 2) != 0, quad = !(neg || pos);
+        s0 = quad ? 0.5f * fr_D * fr_ja * fr_ja : fr_f * (-0.5f * fr_rf + (neg ? -fr_ja : fr_ja));
+        s1 = quad ? r.f1 : (neg ? -r.fl : r.fl);
+        s2 = quad ? r.f2 : 0.f;
+      }
+      if (z & 4) { s0 += 0.5f * lm_D * lm_ja * lm_ja; s1 += r.l1; s2 += r.l2; }
+      if (z & 8) { s0 += 0.5f * c_D * c_ja * c_ja; s1 += r.c1; s2 += r.c2; }
+      float p[8] = {search * search, search * Ma - search * qfrc_smooth, search * mv, s0, s1, s2, 0.f, 0.f};
+      if (!hasdof) { p[0] = p[1] = p[2] = 0.f; }
+      reduce_scatter<8>(p, L);  // value k in lanes 4k..4k+3
+      snorm = shf(p[0], 0);
+      r.qg0 = gauss; r.qg1 = shf(p[0], 4); r.qg2 = 0.5f * shf(p[0], 8);
+      S0.t0 = shf(p[0], 12) + r.qg0; S0.t1 = shf(p[0], 16) + r.qg1; S0.t2 = shf(p[0], 20) + r.qg2; S0.z = z;
+      p0 = ls_make_point(0.f, S0);
+    }
+    const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * meaninertia * (float)NV);
     al[0] = p0.alpha - p0.d0 / p0.d1;
     zz[0] = zone_at(r, al[0]);
     ls_eval<1>(r, al, zz, pt, st);  // lo = point(newton(p0)); order the bracket
@@ -1176,7 +1185,7 @@ struct WarpEnv {
           factor(F0, Hb, Hc, 0.f);
         }
         const float rhs = phase == -1 ? qfrc_smooth : (phase == 99 ? qfrc_smooth + qfrc_c : grad);
-        x = solve(phase == 99, rhs);
+        x = solve(rhs);
       }
       // ---- transitions ----
       if (phase == -1) { qacc_smooth = x; v = x; phase = o.warmstart ? 0 : 2; continue; }
@@ -1184,26 +1193,28 @@ struct WarpEnv {
       if (phase == 1) { v = __all_sync(ZB_FULL, cost < cost_s) ? warm : qacc_smooth; phase = 2; continue; }
       if (phase == 99) { qa_int = x; finished = true; continue; }
       Mgrad = x;
-      if (phase == 2) {
+      float gnorm2;
+      if (phase == 2 || newton) {
+        gnorm2 = wsum(grad * grad);
         search = -Mgrad;
-      } else if (newton) {
-        search = -Mgrad;
-        niter++;
-      } else {
-        float p2[2] = {grad * (Mgrad - pMg), pg * pMg};
-        reduce_scatter<2>(p2, L);
-        const float num = shf(p2[0], 0), den = shf(p2[0], 16);
+        if (phase != 2) niter++;
+      } else {  // Polak-Ribiere+ and the gradient norm of the convergence test in one transpose-reduce
+        float p4[4] = {grad * (Mgrad - pMg), pg * pMg, grad * grad, 0.f};
+        reduce_scatter<4>(p4, L);
+        const float num = shf(p4[0], 0), den = shf(p4[0], 8);
+        gnorm2 = shf(p4[0], 16);
         const float beta = fmaxf(0.f, num / fmaxf(MJ_MINVAL, den));
         search = -Mgrad + beta * search;
         niter++;
       }
       const float improvement = scale * (prev_cost - cost);
-      const float gradient = scale * sqrtf(wsum(grad * grad));
+      const float gradient = scale * sqrtf(gnorm2);
       bool done = niter >= o.iterations;
       done |= improvement < o.tolerance;
       done |= gradient < o.tolerance;
       if (__all_sync(ZB_FULL, done)) {
         if (!implicit_damp) { qa_int = qacc; finished = true; continue; }
+        F0 = F1;  // the factor of M is dead from here on
         phase = 99;
         continue;
       }
