@@ -171,6 +171,10 @@ typedef struct ZbEnvParams {
   const float* floor_friction;   /* [N]              FloorFrictionRandomizer (sliding mu)   */
   const float* imu_site_pos;     /* [N, 3]           IMUAlignmentRandomizer                 */
   const float* imu_site_quat;    /* [N, 4]                                                  */
+  /* MjxEngine.step action latency (ksim `action_latency_range`, commented out at train.py:1786):
+   * substeps s < latency_steps[i] still track prev_action, later ones the new action.  NULL = no latency. */
+  const float* prev_action;      /* [N, ZB_NU]       PhysicsState.most_recent_action        */
+  const int32_t* latency_steps;  /* [N]              round(action_latency / dt)             */
 } ZbEnvParams;
 
 /* ksim PhysicsState, flattened (data.qpos/qvel/qacc_warmstart/time, actuator_state ==

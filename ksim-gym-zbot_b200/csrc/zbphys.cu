@@ -14,7 +14,7 @@
 #include "../../include/zbphys.h"
 #include "zb_kernel.cuh"
 
-#define ZB_ABI_VERSION 1
+#define ZB_ABI_VERSION 2
 
 // auto-reset pass of the step kernel (zb_step_autoreset_f32)
 struct ZbAutoReset {
@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
   E.warm = (MODE != ZB_MODE_RESET && E.hasdof && S.qacc_warmstart) ? S.qacc_warmstart[(size_t)env * NV + d] : 0.f;
   const int a = E.act >= 0 ? E.act : 0;
   E.apos = E.avel = E.atq = E.tgt = E.ctrl = 0.f;
+  float prev_tgt = 0.f;
+  const int latency = (MODE == ZB_MODE_STEP && P.prev_action && P.latency_steps) ? P.latency_steps[env] : 0;
   if (E.act >= 0) {
     if (MODE == ZB_MODE_RESET) {  // get_initial_state train.py:1293-1298
       E.apos = E.q; E.avel = E.qv; E.atq = 0.f;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
       E.apos = S.act_pos[(size_t)env * NU + a]; E.avel = S.act_vel[(size_t)env * NU + a]; E.atq = S.act_torque[(size_t)env * NU + a];
     }
     if (MODE == ZB_MODE_STEP) E.tgt = action[(size_t)env * NU + a];
+    if (MODE == ZB_MODE_STEP && P.prev_action) prev_tgt = P.prev_action[(size_t)env * NU + a];
     if (MODE == ZB_MODE_FORWARD) E.ctrl = E.atq;
   }
   float trem = 0.f, tm = 0.f;
@@ -156,7 +159,10 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
             trem = t;
           }
         } else {
+          const float new_tgt = E.tgt;
+          if (s < latency) E.tgt = prev_tgt;  // action latency: the servo still tracks the previous action
           E.actuator(dt);
+          E.tgt = new_tgt;
         }
       }
     }

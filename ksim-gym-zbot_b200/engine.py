@@ -28,7 +28,7 @@ _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libzbphys.so")
 
 _PARAM_FIELDS = ["body_mass", "body_inertia", "dof_armature", "dof_damping", "dof_frictionloss", "qpos0",
-                 "floor_friction", "imu_site_pos", "imu_site_quat"]
+                 "floor_friction", "imu_site_pos", "imu_site_quat", "prev_action", "latency_steps"]
 _STATE_FIELDS = ["qpos", "qvel", "qacc_warmstart", "act_pos", "act_vel", "act_torque", "push_t_rem", "time"]
 _OUT_F32 = ["xpos", "xquat", "cinert", "cvel", "qacc", "qfrc_constraint", "actuator_force", "ctrl", "sensordata",
             "site_xpos", "site_xmat", "contact_dist", "contact_pos", "efc_force"]
@@ -44,7 +44,7 @@ OUT_SHAPES = {
 }
 PARAM_SHAPES = {"body_mass": (M.NBODY,), "body_inertia": (M.NBODY, 3), "dof_armature": (M.NV,), "dof_damping": (M.NV,),
                 "dof_frictionloss": (M.NV,), "qpos0": (M.NQ,), "floor_friction": (), "imu_site_pos": (3,),
-                "imu_site_quat": (4,)}
+                "imu_site_quat": (4,), "prev_action": (M.NU,), "latency_steps": ()}
 
 
 def _ptr_struct(name, names):
@@ -182,7 +182,8 @@ class EnvParams:
         for k, v in arrays.items():
             if k not in PARAM_SHAPES:
                 raise KeyError(k)
-            t = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v, dtype=torch.float32).to(device).contiguous()
+            dt_ = torch.int32 if k == "latency_steps" else torch.float32
+            t = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v, dtype=dt_).to(device).contiguous()
             if tuple(t.shape) != (n_envs,) + PARAM_SHAPES[k]:
                 raise ValueError(f"{k}: expected shape {(n_envs,) + PARAM_SHAPES[k]}, got {tuple(t.shape)}")
             self.tensors[k] = t
@@ -211,7 +212,8 @@ class ZbotCudaEngine:
                  ctrl_dt: float = 0.02, iterations: int = 8, ls_iterations: int = 8, solver: int = M.SOLVER_CG,
                  integrator: int = M.INT_IMPLICITFAST, push: PushEventConfig | None = None,
                  resets: ResetConfig | None = None, opts: M.ZbOpts | None = None, seed: int = 0,
-                 outputs: tuple[str, ...] | None = None):
+                 outputs: tuple[str, ...] | None = None, action_latency_range: tuple[float, float] = (0.0, 0.0),
+                 drop_action_prob: float = 0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("ZbotCudaEngine needs a CUDA device: the physics step has no CPU fallback")
         self.lib = load_library()
@@ -225,6 +227,8 @@ class ZbotCudaEngine:
         self.phys_steps_per_ctrl_steps = max(1, int(round(self.ctrl_dt / self.dt)))
         self.push = push
         self.resets = resets or ResetConfig()
+        self.action_latency_range = tuple(action_latency_range)  # seconds, sampled per reset (ksim get_physics_engine)
+        self.drop_action_prob = float(drop_action_prob)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(seed)
         self.outputs = tuple(outputs) if outputs is not None else tuple(_OUT_F32 + _OUT_I32)
@@ -344,10 +348,16 @@ class ZbotCudaEngine:
                                    ctypes.c_void_p(reset_qvel.data_ptr()),
                                    None if reset_t_rem is None else ctypes.c_void_p(reset_t_rem.data_ptr()), ctypes.byref(out), n)
         self._check(rc)
+        lo_, hi_ = self.action_latency_range
+        new_lat = lo_ + (hi_ - lo_) * torch.rand((n,), generator=self.gen, device=self.device) if hi_ > 0 else None
         if done is None:
             ps.most_recent_action.copy_(ps.data.qpos[:, 7:])  # get_default_action train.py:1282-1283
+            if new_lat is not None:
+                ps.action_latency = new_lat
         else:
             ps.most_recent_action[:] = torch.where(dn.bool()[:, None], ps.data.qpos[:, 7:], ps.most_recent_action)
+            if new_lat is not None:
+                ps.action_latency = torch.where(dn.bool(), new_lat, ps.action_latency)
         return ps
 
     def step(self, action: torch.Tensor, physics_model: EnvParams | None, physics_state: PhysicsState,
@@ -364,6 +374,17 @@ class ZbotCudaEngine:
             action = action.to(self.device, torch.float32).contiguous()
         if tuple(action.shape) != (n, M.NU):
             raise ValueError(f"action must be [{n}, {M.NU}]")
+        # MjxEngine.step: drop-action bernoulli and action latency (both off in the reference's config)
+        if self.drop_action_prob > 0:
+            drop = torch.rand((n, 1), generator=self.gen, device=self.device) < self.drop_action_prob
+            action = torch.where(drop, ps.most_recent_action, action).contiguous()
+        if ps.action_latency is not None and self.action_latency_range[1] > 0:
+            lat = EnvParams.__new__(EnvParams)
+            lat.n_envs = n
+            lat.tensors = dict(physics_model.tensors) if physics_model is not None else {}
+            lat.tensors["prev_action"] = ps.most_recent_action.contiguous()
+            lat.tensors["latency_steps"] = torch.round(ps.action_latency / self.dt).to(torch.int32).contiguous()
+            physics_model = lat
         per_substep = 0
         if push_rand is None and self.push is not None:
             push_rand = self.sample_push(n, curriculum_level)

@@ -1313,7 +1313,9 @@ int SUF(zbo_step)(const ZbModel* m, const ZbOpts* o, const ZboParams* p, const Z
             st->push_t_rem[i] = t;
           }
         } else {
-          feetech(m, dt, action + (size_t)i * NU, d->qpos, d->qvel, apos, avel, atq, d->ctrl);
+          const real* tgt = action + (size_t)i * NU; /* action latency: early substeps keep the previous action */
+          if (p && p->prev_action && p->latency_steps && s < p->latency_steps[i]) tgt = p->prev_action + (size_t)i * NU;
+          feetech(m, dt, tgt, d->qpos, d->qvel, apos, avel, atq, d->ctrl);
         }
       }
       forward(m, o, &e, d);

@@ -29,7 +29,8 @@ enum {
 /* host mirrors of ZbEnvParams / ZbState / ZbOut with `real` arrays */
 typedef struct ZboParams {
   const real *body_mass, *body_inertia, *dof_armature, *dof_damping, *dof_frictionloss, *qpos0, *floor_friction,
-      *imu_site_pos, *imu_site_quat;
+      *imu_site_pos, *imu_site_quat, *prev_action;
+  const int32_t* latency_steps;
 } ZboParams;
 typedef struct ZboState {
   real *qpos, *qvel, *qacc_warmstart, *act_pos, *act_vel, *act_torque, *push_t_rem, *time;

@@ -78,7 +78,7 @@ ZboDataF32 = _make_data(ctypes.c_float)
 ZboDataF64 = _make_data(ctypes.c_double)
 
 _PARAM_FIELDS = ["body_mass", "body_inertia", "dof_armature", "dof_damping", "dof_frictionloss", "qpos0",
-                 "floor_friction", "imu_site_pos", "imu_site_quat"]
+                 "floor_friction", "imu_site_pos", "imu_site_quat", "prev_action", "latency_steps"]
 _STATE_FIELDS = ["qpos", "qvel", "qacc_warmstart", "act_pos", "act_vel", "act_torque", "push_t_rem", "time"]
 _OUT_REAL = ["xpos", "xquat", "cinert", "cvel", "qacc", "qfrc_constraint", "actuator_force", "ctrl", "sensordata",
              "site_xpos", "site_xmat", "contact_dist", "contact_pos", "efc_force"]
@@ -149,7 +149,7 @@ class Oracle:
         if params:
             for k in _PARAM_FIELDS:
                 if params.get(k) is not None:
-                    a = self._arr(params[k])
+                    a = np.ascontiguousarray(params[k], dtype=np.int32) if k == "latency_steps" else self._arr(params[k])
                     keep.append(a)
                     setattr(s, k, a.ctypes.data)
         return s, keep

@@ -399,6 +399,32 @@ def test_push_event_and_reset_semantics(zmodel):
     np.testing.assert_array_equal(st["push_t_rem"][[0, 3]], 2.5)
 
 
+def test_action_latency_semantics(zmodel):
+    """MjxEngine.step latency select: substeps s < latency_steps track prev_action, later ones the new one."""
+    n, S = 5, 4
+    q, v = random_states(zmodel, n, 30)
+    a_new, a_old = random_actions(n, 31), random_actions(n, 32)
+    o = zo.Oracle(zmodel, M.make_opts(dt=0.005), np.float64)
+
+    def run(action, params):
+        st = o.new_state(n)
+        o.reset(st, q, v, np.full(n, 1e9))
+        o.step(st, action, S, params=params)
+        return st
+
+    base_new, base_old = run(a_new, None), run(a_old, None)
+    lat0 = run(a_new, {"prev_action": a_old, "latency_steps": np.zeros(n, np.int32)})
+    latS = run(a_new, {"prev_action": a_old, "latency_steps": np.full(n, S, np.int32)})
+    mixed = run(a_new, {"prev_action": a_old, "latency_steps": np.array([0, 1, 2, 3, 9], np.int32)})
+    for k in ("qpos", "qvel", "act_pos", "act_torque"):
+        np.testing.assert_array_equal(lat0[k], base_new[k])
+        np.testing.assert_array_equal(latS[k], base_old[k])
+        np.testing.assert_array_equal(mixed[k][0], base_new[k][0])
+        np.testing.assert_array_equal(mixed[k][4], base_old[k][4])
+    assert np.abs(mixed["act_pos"][2] - base_new["act_pos"][2]).max() > 1e-6
+    assert np.abs(mixed["act_pos"][2] - base_old["act_pos"][2]).max() > 1e-6
+
+
 def test_env_param_overrides(zmodel):
     """Randomizer fields (train.py:1439-1455) reach the dynamics: heavier body -> larger M, floor mu -> contact rows."""
     m = zmodel

@@ -130,7 +130,7 @@ def test_library_exports_and_errors(zmodel):
     lib = load_library()
     for name in EXPORTS:
         assert hasattr(lib, name)
-    assert lib.zb_abi_version() == 1
+    assert lib.zb_abi_version() == 2
     h = ctypes.c_void_p()
     assert lib.zb_engine_create(None, None, 0, ctypes.byref(h)) == ZB_EINVAL
     bad = M.make_opts(dt=-1.0)
@@ -360,6 +360,40 @@ def test_tail_warps_nan_flag_and_independence(zmodel):
     keep = np.arange(n) != 3
     for k in ("qpos", "qvel", "xpos", "sensordata", "act_torque"):
         np.testing.assert_array_equal(clean[k][keep], bad[k][keep], err_msg=k)
+
+
+def test_action_latency_and_drop(zmodel):
+    """Action latency (prev_action / latency_steps) in the kernel == oracle; engine-level latency + drop-action plumbing."""
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import EnvParams
+
+    n, S = 64, 4
+    q, v = random_states(zmodel, n, 121)
+    a_new, a_old = random_actions(n, 122), random_actions(n, 123)
+    lat = np.random.default_rng(124).integers(0, S + 2, n).astype(np.int32)
+    opts = M.make_opts(dt=0.005, iterations=0)  # deterministic tier: exact comparison of the servo path
+    eng = _engine(zmodel, n, opts=opts, ctrl_dt=0.02)
+    ps = eng.reset(reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(v), reset_t_rem=torch.full((n,), 1e9))
+    ep = EnvParams(n, eng.device, prev_action=a_old, latency_steps=lat)
+    eng.step(torch.tensor(a_new, device="cuda"), ep, ps)
+    c = _to_np(ps)
+    o = _oracle(zmodel, opts, np.float32)
+    st = o.new_state(n)
+    o.reset(st, q, v, np.full(n, 1e9))
+    o.step(st, a_new, S, params={"prev_action": a_old, "latency_steps": lat})
+    for k in ("act_pos", "act_vel"):
+        np.testing.assert_allclose(c[k], st[k], rtol=1e-6, atol=1e-6)
+    assert rel_err(c["qpos"], st["qpos"]) < 5e-5  # four fp32 substeps
+    eng.close()
+    # engine plumbing: latency sampled at reset, prev action = most_recent_action, drop-action keeps the previous action
+    eng = _engine(zmodel, n, dt=0.005, ctrl_dt=0.02, action_latency_range=(0.0, 0.02), drop_action_prob=1.0)
+    ps = eng.reset()
+    assert ps.action_latency.min() >= 0 and ps.action_latency.max() <= 0.02 and ps.action_latency.std() > 0
+    before = ps.most_recent_action.clone()
+    eng.step(torch.tensor(a_new, device="cuda"), None, ps)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ps.most_recent_action.cpu().numpy(), before.cpu().numpy())  # every action dropped
+    eng.close()
 
 
 def test_autoreset_equals_three_calls(zmodel):
