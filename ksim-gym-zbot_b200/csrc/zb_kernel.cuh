@@ -76,11 +76,11 @@ struct ZbDev {
   int con_mu_mode[ZB_NBOX];        // 0: floor friction (per-env), 1: box friction, 2: max of both
 };
 
-struct Factor {
-  float lc[CHD];  // row gp of the group's Cholesky factor (entries k <= gp)
-  float lt[CHD];  // column gp (entries k >= gp)
-  float inv;      // 1 / L[gp][gp]
-  float W[6];     // hinge lanes: row of W = L_c^-1 B
+struct Factor {      // block LDL^T of M (or M + dt D); every entry is zero where it does not apply to the lane
+  float lc[CHD];  // Lt[gp][k], k < gp: row of the unit lower factor of the lane's group (chain block or base block)
+  float lt[CHD];  // Lt[k][gp], k > gp: column
+  float inv;      // 1 / D[gp]
+  float W[6];     // hinge lanes: row of G = D_c^-1 Lt_c^-1 B
 };
 
 struct LSPoint {
@@ -384,60 +384,59 @@ struct WarpEnv {
     }
   }
 
-  // in-group right-looking Cholesky on the rows held in r[] (lower part), lanes gs..gs+gn-1
-  ZB_DI void group_chol(float (&r)[CHD], float& inv, bool valid) {
+  // In-group right-looking LDL^T on the rows held in r[] (lower part), lanes gs..gs+gn-1:  A = Lt D Lt^T, Lt unit lower.
+  // Afterwards r[k] (k < gp) = Lt[gp][k], invd = 1 / D[gp].  No square roots; entries above the diagonal are scratch.
+  ZB_DI void group_ldl(float (&r)[CHD], float& invd, bool valid) {
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
       float d = shf(r[k], gs + k);
       if (!(valid && k < gn)) d = 1.f;
-      float ik = rsqrtf(d);  // MUFU.RSQ + one Newton step: full fp32 accuracy without the IEEE sqrt/div expansions
-      ik = ik * (1.5f - 0.5f * d * ik * ik);
-      const float lkk = d * ik;
-      const bool piv = valid && gp == k;
-      r[k] = piv ? lkk : ((valid && gp > k) ? r[k] * ik : r[k]);
-      inv = piv ? ik : inv;
+      const float id = __frcp_rn(d);
+      float ajk[CHD];
 #pragma unroll
-      for (int j = k + 1; j < CHD; j++) {
-        const float ljk = shf(r[k], gs + j);
-        if (valid && gp >= j && j < gn) r[j] -= r[k] * ljk;
-      }
+      for (int j = k + 1; j < CHD; j++) ajk[j] = shf(r[k], gs + j);  // a_jk BEFORE scaling = Lt_jk d_k
+      r[k] = (valid && gp > k) ? r[k] * id : r[k];
+      invd = (valid && gp == k) ? id : invd;
+#pragma unroll
+      for (int j = k + 1; j < CHD; j++) r[j] = fmaf(-r[k], ajk[j], r[j]);  // rows j > gp only collect scratch
     }
   }
 
-  // smooth.factor_m as a block Cholesky of (M + diag(extra))
+  // smooth.factor_m as a block LDL^T of (M + diag(extra)), M = [[A, B^T], [B, C]]:
+  //   chains  C = Lt_c D_c Lt_c^T,  Wt = Lt_c^-1 B,  G = D_c^-1 Wt,  S = A - Wt^T G = Lt_s D_s Lt_s^T.
+  // All stored coefficients are ZERO where they do not apply (other lanes, k >= gp, short chains), so the substitutions in
+  // solve() are bare SHFL + FFMA steps without per-step predicates.
   ZB_DI void factor(Factor& F, const float (&Bsrc)[6], const float (&Csrc)[CHD], float extra) {
+    float r[CHD];
 #pragma unroll
-    for (int k = 0; k < CHD; k++) {
-      F.lc[k] = hinge ? Csrc[k] + (k == gp ? extra : 0.f) : 0.f;
-      F.lt[k] = 0.f;
-    }
-    F.inv = 1.f;
-    group_chol(F.lc, F.inv, hinge);
-    // W = L_c^-1 B by forward substitution, six right-hand sides
+    for (int k = 0; k < CHD; k++) r[k] = hinge ? Csrc[k] + (k == gp ? extra : 0.f) : 0.f;
+    float invd = 0.f;
+    group_ldl(r, invd, hinge);
 #pragma unroll
-    for (int a = 0; a < 6; a++) F.W[a] = hinge ? Bsrc[a] : 0.f;
+    for (int k = 0; k < CHD; k++) F.lc[k] = (hinge && k < gp) ? r[k] : 0.f;
+    // Wt = Lt_c^-1 B by unit forward substitution, six right-hand sides
+    float W[6];
 #pragma unroll
-    for (int k = 0; k < CHD; k++) {
-      if (hinge && gp == k) {
+    for (int a = 0; a < 6; a++) W[a] = hinge ? Bsrc[a] : 0.f;
 #pragma unroll
-        for (int a = 0; a < 6; a++) F.W[a] *= F.inv;
-      }
-      if (k < CHD - 1) {
+    for (int k = 0; k < CHD - 1; k++) {
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
-          const float wk = shf(F.W[a], gs + k);
-          if (hinge && gp > k && k < gn) F.W[a] -= F.lc[k] * wk;
-        }
+      for (int a = 0; a < 6; a++) {
+        const float wk = shf(W[a], gs + k);
+        W[a] = fmaf(-F.lc[k], wk, W[a]);
       }
     }
-    // Schur complement S = A - W^T W: 21 unique sums over the hinge lanes, one result per lane
+#pragma unroll
+    for (int a = 0; a < 6; a++) F.W[a] = W[a] * invd;  // G = D_c^-1 Wt (zero outside the hinge lanes)
+    // Schur complement S = A - Wt^T G: 21 unique sums over the hinge lanes, one result per lane
+    float rb[CHD];
     {
       float p[32];
       int t = 0;
 #pragma unroll
       for (int a = 0; a < 6; a++)
 #pragma unroll
-        for (int b = a; b < 6; b++) p[t++] = F.W[a] * F.W[b];
+        for (int b = a; b < 6; b++) p[t++] = W[a] * F.W[b];
 #pragma unroll
       for (int k = 21; k < 32; k++) p[k] = 0.f;
       reduce_scatter<32>(p, L);  // lane t holds sum_t
@@ -446,12 +445,16 @@ struct WarpEnv {
       for (int b = 0; b < 6; b++) {
         const int lo = a < b ? a : b, hi = a < b ? b : a;
         const int idx = lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);
-        const float s = shf(p[0], idx);
-        F.lc[b] = bdof ? Bsrc[b] - s + (b == gp ? extra : 0.f) : F.lc[b];
+        const float sv = shf(p[0], idx);
+        rb[b] = bdof ? Bsrc[b] - sv + (b == gp ? extra : 0.f) : 0.f;
       }
     }
-    group_chol(F.lc, F.inv, bdof);
-    // column copies for the back substitutions
+    float invb = 0.f;
+    group_ldl(rb, invb, bdof);
+#pragma unroll
+    for (int k = 0; k < CHD; k++) F.lc[k] = (bdof && k < gp) ? rb[k] : F.lc[k];
+    F.inv = hinge ? invd : (bdof ? invb : 0.f);
+    // column copies Lt[k][gp] (k > gp) for the back substitutions
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < CHD; k++) scr[L * ZB_SCR + k] = F.lc[k];
@@ -459,7 +462,7 @@ struct WarpEnv {
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
       const float t = scr[((gs + k) & 31) * ZB_SCR + gp];
-      F.lt[k] = (hasdof && k >= gp && k < gn) ? t : 0.f;
+      F.lt[k] = (hasdof && k > gp && k < gn) ? t : 0.f;
     }
     __syncwarp();
   }
@@ -468,53 +471,43 @@ struct WarpEnv {
   ZB_DI float solve(float x) {
     const Factor& F = F0;  // solve_all moves the (M + dt D) factor into F0 before the integration solve
     if (!hasdof) x = 0.f;
-    // chains: forward substitution
+    // chains: unit forward substitution  y_c = Lt_c^-1 r_c
 #pragma unroll
-    for (int k = 0; k < CHD; k++) {
-      if (hinge && gp == k) x *= F.inv;
-      if (k < CHD - 1) {
-        const float yk = shf(x, gs + k);
-        if (hinge && gp > k && k < gn) x -= F.lc[k] * yk;
-      }
+    for (int k = 0; k < CHD - 1; k++) {
+      const float yk = shf(x, gs + k);
+      if (hinge) x = fmaf(-F.lc[k], yk, x);
     }
-    // base right-hand side: r_a - sum_i W_i[a] y_i
+    // base right-hand side: r_b - sum_i G_i y_i
     {
       float p[8];
 #pragma unroll
-      for (int a = 0; a < 6; a++) p[a] = hinge ? F.W[a] * x : 0.f;
+      for (int a = 0; a < 6; a++) p[a] = F.W[a] * x;  // G is zero outside the hinge lanes
       p[6] = p[7] = 0.f;
       reduce_scatter<8>(p, L);  // lanes 4a..4a+3 hold total a
       const float t = shf(p[0], bdof ? 4 * (L - BL0) : 0);
       if (bdof) x -= t;
     }
-    // base group: forward then backward (the backward pulls also broadcast x_base to every lane)
+    // base group: unit forward, scale by D^-1 (chain lanes too: D_c^-1 y_c), unit backward; the backward pulls also
+    // broadcast x_base to every lane
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-      if (bdof && gp == k) x *= F.inv;
-      if (k < 5) {
-        const float yk = shf(x, BL0 + k);
-        if (bdof && gp > k) x -= F.lc[k] * yk;
-      }
+    for (int k = 0; k < 5; k++) {
+      const float yk = shf(x, BL0 + k);
+      if (bdof) x = fmaf(-F.lc[k], yk, x);
     }
+    x *= F.inv;
     float xbv[6];
 #pragma unroll
     for (int k = 5; k >= 0; k--) {
-      if (bdof && gp == k) x *= F.inv;
       xbv[k] = shf(x, BL0 + k);
-      if (bdof && gp < k) x -= F.lt[k] * xbv[k];
+      if (bdof) x = fmaf(-F.lt[k], xbv[k], x);
     }
-    // chains: remove the base coupling, backward substitution
-    if (hinge) {
+    // chains: Lt_c^T x_c = D_c^-1 y_c - G x_b, unit backward substitution
 #pragma unroll
-      for (int a = 0; a < 6; a++) x -= F.W[a] * xbv[a];
-    }
+    for (int a = 0; a < 6; a++) x = fmaf(-F.W[a], xbv[a], x);
 #pragma unroll
-    for (int k = CHD - 1; k >= 0; k--) {
-      if (hinge && gp == k) x *= F.inv;
-      if (k > 0) {
-        const float xk = shf(x, gs + k);
-        if (hinge && gp < k && k < gn) x -= F.lt[k] * xk;
-      }
+    for (int k = CHD - 1; k >= 1; k--) {
+      const float xk = shf(x, gs + k);
+      if (hinge) x = fmaf(-F.lt[k], xk, x);
     }
     return x;
   }
@@ -530,11 +523,11 @@ struct WarpEnv {
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
       const float vk = shf(v, gs + k);
-      if (hinge && k < gn) y += C[k] * vk;
+      y = fmaf(C[k], vk, y);  // C is zero outside the lane's chain block
     }
     float p[8];
 #pragma unroll
-    for (int a = 0; a < 6; a++) p[a] = hinge ? Bm[a] * v : 0.f;
+    for (int a = 0; a < 6; a++) p[a] = hinge ? Bm[a] * v : 0.f;  // (base lanes hold A in Bm: must stay masked)
     p[6] = p[7] = 0.f;
     reduce_scatter<8>(p, L);
     const float t = shf(p[0], bdof ? 4 * (L - BL0) : 0);
