@@ -88,6 +88,7 @@ struct LSPoint {
 };
 struct LSSet {          // an active set of the line search: its summed quadratic and this lane's zone bits
   float t0, t1, t2;
+  float d1;            // second derivative 2 t2 (+ mjMINVAL if t2 == 0): constant on the set
   int z;
 };
 
@@ -850,7 +851,9 @@ struct WarpEnv {
     if (c_on && c_ja < 0.f) { c_force = -c_D * c_ja; cst += 0.5f * c_D * c_ja * c_ja; }
     return cst;
   }
-  static ZB_DI bool in_bracket(float x, float y) { return (x < y && y < 0.f) || (x > y && y > 0.f); }
+  // MJX: (x < y && y < 0) || (x > y && y > 0)  <=>  y lies strictly between x and 0  <=>  (y - x) * y < 0.
+  // (the sign of a rounded difference/product is exact; a product underflowing to 0 would need |d0| < 1e-19)
+  static ZB_DI bool in_bracket(float x, float y) { return __fmul_rn(y - x, y) < 0.f; }
 
   // Per-row quadratic data of one line search (MJX: quad = [0.5 D x0^2, D x0 jv, 0.5 D jv^2]; friction rows add two
   // linear zones).
@@ -883,9 +886,10 @@ struct WarpEnv {
     // the reference's bracket logic treats an exact zero as "not in bracket" (the point is rejected).  An FMA would
     // return the tiny residual instead and flip that decision in ~14 % of the states (tests/gpu_probe3.py).
     p.d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, a), S.t2), S.t1);
-    p.d1 = __fadd_rn(__fmul_rn(2.f, S.t2), (S.t2 == 0.f ? MJ_MINVAL : 0.f));
+    p.d1 = S.d1;
     return p;
   }
+  static ZB_DI float ls_set_d1(float t2) { return __fadd_rn(__fmul_rn(2.f, t2), (t2 == 0.f ? MJ_MINVAL : 0.f)); }
   static ZB_DI float ls_cost(float a, const LSSet& S) {
     return __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(a, a), S.t2), __fmul_rn(a, S.t1)), S.t0);
   }
@@ -919,6 +923,7 @@ struct WarpEnv {
       st[j].t1 = shf(s[0], STR * (3 * j + 1)) + r.qg1;
       st[j].t2 = shf(s[0], STR * (3 * j + 2)) + r.qg2;
       st[j].z = zz[j];
+      st[j].d1 = ls_set_d1(st[j].t2);
       pt[j] = ls_make_point(al[j], st[j]);
     }
   }
@@ -956,6 +961,7 @@ struct WarpEnv {
       snorm = shf(p[0], 0);
       r.qg0 = gauss; r.qg1 = shf(p[0], 4); r.qg2 = 0.5f * shf(p[0], 8);
       S0.t0 = shf(p[0], 12) + r.qg0; S0.t1 = shf(p[0], 16) + r.qg1; S0.t2 = shf(p[0], 20) + r.qg2; S0.z = z;
+      S0.d1 = ls_set_d1(S0.t2);
       p0 = ls_make_point(0.f, S0);
     }
     const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * meaninertia * (float)NV);
