@@ -408,6 +408,12 @@ class ZbotCudaEngine:
                 None if done_out is None else ctypes.c_void_p(done_out.data_ptr()), z_lo, z_hi, max_tilt)
         self._check(rc)
         ps.most_recent_action = action
+        if auto_reset is not None and done_out is not None and self.action_latency_range[1] > 0:
+            # reset environments restart from the default action (get_default_action, train.py:1282-1283) with a fresh latency
+            dn = done_out.bool()
+            ps.most_recent_action = torch.where(dn[:, None], ps.data.qpos[:, 7:], action).contiguous()
+            lo_, hi_ = self.action_latency_range
+            ps.action_latency = torch.where(dn, lo_ + (hi_ - lo_) * torch.rand((n,), generator=self.gen, device=self.device), ps.action_latency)
         return ps
 
     def forward(self, physics_model: EnvParams | None, physics_state: PhysicsState) -> PhysicsState:
