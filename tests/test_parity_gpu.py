@@ -427,6 +427,61 @@ def test_autoreset_equals_three_calls(zmodel):
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
+def test_full_size_properties(zmodel):
+    """BASELINE.json sizes (16 384 envs, S=4; the oracle is too slow there): size-independent properties.
+    (a) run-to-run bitwise determinism, (b) an environment's result does not depend on the batch it sits in,
+    (c) forward() is idempotent and leaves the state alone, (d) invariants over the whole batch."""
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import EnvParams
+
+    n, sub = 16384, 100
+    q, v = random_states(zmodel, n, 131)
+    act = [random_actions(n, 132 + t) for t in range(3)]
+    prm = _params(zmodel, n, 133)
+
+    def run(lo, hi):
+        eng = _engine(zmodel, hi - lo, dt=0.005, ctrl_dt=0.02)
+        ep = EnvParams(hi - lo, eng.device, **{k: a[lo:hi] for k, a in prm.items()})
+        ps = eng.reset(ep, reset_qpos=torch.tensor(q[lo:hi]), reset_qvel=torch.tensor(v[lo:hi]), reset_t_rem=torch.full((hi - lo,), 1e9))
+        for a in act:
+            eng.step(torch.tensor(a[lo:hi], device="cuda"), ep, ps)
+        out = _to_np(ps)
+        eng.forward(ep, ps)
+        f1 = _to_np(ps)
+        eng.forward(ep, ps)
+        f2 = _to_np(ps)
+        eng.close()
+        return out, f1, f2
+
+    full, f1, f2 = run(0, n)
+    again, _, _ = run(0, n)
+    for k in full:
+        np.testing.assert_array_equal(full[k], again[k], err_msg="determinism: " + k)
+    part, _, _ = run(5000, 5000 + sub)
+    for k in full:
+        np.testing.assert_array_equal(full[k][5000:5000 + sub], part[k], err_msg="batch independence: " + k)
+    # forward(): state untouched except the free-joint quaternion, which MJX re-normalises in place (an already unit
+    # quaternion can move by one ulp, and with it the kinematics at rounding level; the capped solver is not compared)
+    for f in (f1, f2):
+        for k in ("qvel", "act_pos", "act_vel", "act_torque", "time", "push_t_rem", "qacc_warmstart"):
+            np.testing.assert_array_equal(f[k], full[k], err_msg="forward leaves the state alone: " + k)
+        np.testing.assert_array_equal(np.delete(f["qpos"], [3, 4, 5, 6], axis=1), np.delete(full["qpos"], [3, 4, 5, 6], axis=1))
+        np.testing.assert_allclose(f["qpos"][:, 3:7], full["qpos"][:, 3:7], atol=3e-7)
+    for k in ("xpos", "xquat", "cinert", "cvel", "site_xpos", "contact_pos"):
+        np.testing.assert_allclose(f1[k], f2[k], rtol=1e-5, atol=2e-6, err_msg="forward idempotence: " + k)
+    np.testing.assert_array_equal(f1["contact_mask"], f2["contact_mask"])
+    assert np.isfinite(full["qpos"]).all() and np.isfinite(full["qvel"]).all() and not full["flags"].any()
+    np.testing.assert_allclose(np.linalg.norm(full["qpos"][:, 3:7], axis=1), 1.0, atol=2e-6)
+    np.testing.assert_allclose(np.linalg.norm(full["xquat"], axis=2), 1.0, atol=2e-6)
+    assert (full["efc_force"][:, 52:] >= 0).all()  # pyramid edge forces push, never pull
+    fl = np.asarray(prm["dof_frictionloss"])
+    assert (np.abs(full["efc_force"][:, 6:26]) <= fl[:, 6:] * (1 + 1e-6)).all()  # Huber rows saturate at frictionloss
+    off = (full["contact_mask"][:, None] >> np.arange(8)[None] & 1) == 0
+    assert (full["efc_force"][:, 52:].reshape(n, 8, 4)[off] == 0).all()  # no force without an active contact
+    np.testing.assert_allclose(full["time"], 3 * 0.02, rtol=1e-6)
+    np.testing.assert_allclose(full["cinert"][:, :, 9], np.asarray(prm["body_mass"]), rtol=1e-6)  # cinert carries the body masses
+
+
 def test_rollout_50_terminations(zmodel):
     """50 control steps (S=4) with random actions and pushes: terminations equal, trajectories stay close."""
     from ksim_gym_zbot_b200 import model as M
