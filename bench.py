@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="0 = 4096 (c2) / 16384 (c3)")
     ap.add_argument("--substeps", type=int, default=4, help="physics substeps per control step (BASELINE config: 4; train.py:1777: 20)")
     ap.add_argument("--ctrl-dt", type=float, default=0.02)
+    ap.add_argument("--solver", default="cg", choices=["cg", "newton"], help="ZbOpts.solver (ksim default unverified, see PARITY_RISKS.md)")
     ap.add_argument("--solver-iterations", type=int, default=8)
     ap.add_argument("--ls-iterations", type=int, default=8)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
@@ -160,7 +161,8 @@ def main():
     from ksim_gym_zbot_b200 import model as M
 
     model = M.build_zbot_syn()
-    opts = M.make_opts(dt=a.ctrl_dt / S, iterations=a.solver_iterations, ls_iterations=a.ls_iterations)
+    opts = M.make_opts(dt=a.ctrl_dt / S, iterations=a.solver_iterations, ls_iterations=a.ls_iterations,
+                       solver=M.SOLVER_NEWTON if a.solver == "newton" else M.SOLVER_CG)
     randomized = a.workload in ("c3", "c5")
     config = {
         "workload": {"c2": "BASELINE.json configs[1]: Z-Bot 4096 envs random-action rollout, ctrl_dt=0.02, 4 substeps",
@@ -168,7 +170,7 @@ def main():
                      "c5": "BASELINE.json configs[4]: contact-heavy (falls and pushes): resets tilted up to 40 deg and dropped from +8 cm, "
                            "pushes every 0.2-0.4 s at 10x magnitude, randomization + resets"}[a.workload],
         "model": "zbot_syn v1 (synthetic Z-Bot topology; the real MJCF is not shipped with the reference)",
-        "envs_per_gpu": n_env, "substeps": S, "dt": a.ctrl_dt / S, "ctrl_dt": a.ctrl_dt, "solver": "cg",
+        "envs_per_gpu": n_env, "substeps": S, "dt": a.ctrl_dt / S, "ctrl_dt": a.ctrl_dt, "solver": a.solver,
         "iterations": a.solver_iterations, "ls_iterations": a.ls_iterations, "integrator": "implicitfast",
         "actions": "bias + 0.3*U(-1,1), torch Philox seed %d" % a.seed, "terminations": "z in [0.05,0.5], tilt<60deg -> in-place reset",
         "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "parallelism": f"dp{world} (envs sharded, no collective in the physics step)",
