@@ -11,8 +11,10 @@
 //   lane r  in [0, 32)  : contact row r = pyramid edge (r & 3) of contact slot (r >> 2); box = r >> 4
 // Tree structure exploited: floating base + serial chains hanging off it (validated on the host).
 //   chain scans  : Hillis-Steele over contiguous body lanes with shfl_up / shfl_down
-//   mass matrix  : M = [[A, B^T], [B, C]], C block-diagonal per chain -> block Cholesky
-//                  (chain factors in parallel, Schur complement S = A - W^T W on the base lanes)
+//   mass matrix  : M = [[A, B^T], [B, C]], C block-diagonal per chain -> block LDL^T
+//                  (chain factors in parallel, Schur complement S = A - Wt^T D^-1 Wt on the base lanes)
+//   execution    : 16 environments per 512-thread CTA, the warps meet at a barrier at every substep so that they stream the
+//                  same instructions (instruction fetch was the top stall of the first version, see profiles/README.md)
 //   constraints  : friction-loss / limit rows are single-entry rows owned by the dof lane; contact rows
 //                  are applied matrix-free: J[r, :] = w_r . cdof[:] (w_r = contact wrench direction), so
 //                  J v = w_r . V_foot(v) and J^T f = cdof . sum_r f_r w_r.
