@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -28,14 +29,20 @@ struct ZbEngine {
   ZbDev host;
   ZbDev* dev;
   int device;
+  int num_sms;
+  int force_wpb;  // ZBPHYS_WPB environment override (experiments), 0 = automatic
 };
 
-static thread_local char g_err[512] = "";
-static std::atomic<long long> g_launches{0};
-
-static int fail(int code, const char* fmt, const char* a = "") {
-  snprintf(g_err, sizeof(g_err), fmt, a);
-  return code;
+// Warps (environments) per CTA of a launch.  One 16-warp CTA is resident per SM.  A batch that does not fill one wave
+// (n < 16 * SMs) is spread over all SMs with smaller CTAs (1024 envs: 147 CTAs of 7 warps, 0.35 ms instead of 64 CTAs of 16,
+// 0.43 ms); larger batches keep 16: two waves of 14 warps measured no faster than 148 + 108 CTAs of 16 (the warps are
+// latency-bound, a CTA of 14 takes as long as one of 16 — profiles/README.md).
+static int pick_wpb(const ZbEngine* e, int n_envs) {
+  if (e->force_wpb > 0) return e->force_wpb;
+  const int sms = e->num_sms > 0 ? e->num_sms : 148;
+  if (n_envs >= ZB_WPB * sms) return ZB_WPB;
+  const int w = (n_envs + sms - 1) / sms;
+  return w < 1 ? 1 : w;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -49,16 +56,18 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
                                                        const float* __restrict__ rv, const float* __restrict__ rt, ZbAutoReset AR) {
   __shared__ float scratch[ZB_WPB][32 * ZB_SCR];
   const int L = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  int env = blockIdx.x * ZB_WPB + wib;
+  const int env = blockIdx.x * (blockDim.x >> 5) + wib;  // warps per CTA is a launch-time choice (<= ZB_WPB, see pick_wpb)
+  // (vote: makes the flag provably warp-uniform for ptxas; a divergent-looking exit around barriers would wrap every
+  //  later shuffle in WARPSYNC)
+  const bool live = __all_sync(ZB_FULL, env < n_envs);
+  if (!live) {
 #if ZB_CTA_LOCKSTEP
-  // keep the warps of a CTA in step at substep boundaries so that they stream the same instructions (shared I-cache lines);
-  // a tail warp then has to stay alive: it recomputes the last environment and stores nothing
-  const bool live = env < n_envs;
-  if (!live) { if (MODE != ZB_MODE_STEP) return; env = n_envs - 1; }
-#else
-  const bool live = true;
-  if (env >= n_envs) return;
+    // a spare warp of the last CTA only keeps the barrier count: one per substep + one for the auto-reset pass
+    if (MODE == ZB_MODE_STEP)
+      for (int s = 0; s <= n_substeps; s++) __syncthreads();
 #endif
+    return;
+  }
   if (MODE == ZB_MODE_RESET && done && !done[env]) return;
   const ZbModel& m = D->m;
   WarpEnv<TRACE, (ZB_CTA_LOCKSTEP >= 2) && MODE == ZB_MODE_STEP> E;
@@ -132,7 +141,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
       const bool nonfinite = !(isfinite(E.q) && isfinite(E.qv) && isfinite(E.bq[0]) && isfinite(E.bq[1]) && isfinite(E.bq[2]) && isfinite(E.bq[3]));
       bool bad = (E.bq[2] < AR.z_lo) || (E.bq[2] > AR.z_hi) || (up < AR.cos_tilt) || !isfinite(E.bq[2]) || !isfinite(up);
       bad = __any_sync(ZB_FULL, bad || nonfinite);
-      if (L == 0 && AR.done_out && live) AR.done_out[env] = bad ? 1 : 0;
+      if (L == 0 && AR.done_out) AR.done_out[env] = bad ? 1 : 0;
       if (!bad) break;
 #pragma unroll
       for (int k = 0; k < 7; k++) E.bq[k] = AR.reset_qpos[(size_t)env * NQ + k];
@@ -212,7 +221,6 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
     }
   }
 
-  if (!live) return;
   // ---- state write-back ----
   {  // base pose (MJX writes the normalised free-joint quaternion back into qpos, also in forward())
     float v = E.bq[0];
@@ -491,6 +499,12 @@ int zb_engine_create(const ZbModel* model, const ZbOpts* opts, int device, ZbEng
   e->host.o = *opts;
   e->device = device;
   e->dev = nullptr;
+  e->num_sms = prop.multiProcessorCount;
+  e->force_wpb = 0;
+  if (const char* w = getenv("ZBPHYS_WPB")) {
+    const int v = atoi(w);
+    if (v >= 1 && v <= ZB_WPB) e->force_wpb = v;
+  }
   rc = derive(&e->host);
   if (rc) { delete e; return rc; }
   int prev = 0;
@@ -550,10 +564,10 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   if (n_envs == 0) return ZB_OK;
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
-  const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  if (O.solver_trace) zb_kernel<ZB_MODE_STEP, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
+  const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
+  if (O.solver_trace) zb_kernel<ZB_MODE_STEP, true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
                                                                          n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR);
-  else zb_kernel<ZB_MODE_STEP, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
+  else zb_kernel<ZB_MODE_STEP, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
                                                                          n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR);
   return after_launch("zb_step_f32 launch: %s");
 }
@@ -584,10 +598,10 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   if (n_envs == 0) return ZB_OK;
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
-  const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+  const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
+  if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
                                                                             nullptr, nullptr, nullptr, nullptr, ZbAutoReset{});
-  else zb_kernel<ZB_MODE_FORWARD, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+  else zb_kernel<ZB_MODE_FORWARD, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
                                                                             nullptr, nullptr, nullptr, nullptr, ZbAutoReset{});
   return after_launch("zb_forward_f32 launch: %s");
 }
@@ -601,10 +615,10 @@ int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbS
   if (n_envs == 0) return ZB_OK;
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
-  const int grid = (n_envs + ZB_WPB - 1) / ZB_WPB;
-  if (O.solver_trace) zb_kernel<ZB_MODE_RESET, true><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
+  const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
+  if (O.solver_trace) zb_kernel<ZB_MODE_RESET, true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
                                                                           reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{});
-  else zb_kernel<ZB_MODE_RESET, false><<<grid, ZB_WPB * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
+  else zb_kernel<ZB_MODE_RESET, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
                                                                           reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{});
   return after_launch("zb_reset_f32 launch: %s");
 }
