@@ -45,6 +45,14 @@ static int pick_wpb(const ZbEngine* e, int n_envs) {
   return w < 1 ? 1 : w;
 }
 
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
