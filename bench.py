@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-shards", type=int, default=4, help="environment blocks (streams) the end-to-end loop drives the batch in")
+    ap.add_argument("--obs", action="store_true", help="observation epilogue: the launch also writes the actor [50] / critic [484] input vectors "
+                    "(train.py:1624-1681); only those + the reward inputs are written / read back instead of every mjx.Data array")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -143,10 +145,13 @@ def oracle_flops_per_env_step(model, opts, state_np, actions_np, S, params):
 
 
 # bytes per control step per env that MUST cross HBM: state in/out + action + per-env model + outputs
-def algorithmic_bytes_per_ctrl_step(randomized: bool, push: bool) -> int:
+def algorithmic_bytes_per_ctrl_step(randomized: bool, push: bool, obs: bool = False) -> int:
     state = 27 + 26 + 26 + 60 + 2  # qpos qvel warmstart planner(3x20) t_rem time
     rd = state + 20 + (7 if push else 0) + (165 if randomized else 0)
     wr = state + (78 + 104 + 260 + 156 + 26 + 26 + 20 + 20 + 18 + 9 + 27 + 8 + 24 + 84 + 3)  # every ZbOut array
+    if obs:  # carry (x, lag) in/out + both network vectors + the reward inputs (xpos qacc actuator_force sensordata site_xpos, 3 ints)
+        rd += 5
+        wr = state + 5 + 50 + 484 + (78 + 26 + 20 + 18 + 9 + 3)
     return 4 * (rd + wr)
 
 
@@ -197,7 +202,12 @@ def main():
     push_cfg = PushEventConfig() if randomized else None
     if a.workload == "c5":
         push_cfg = PushEventConfig(x_linvel=1.0, y_linvel=1.0, z_linvel=0.5, interval_range=(0.2, 0.4))
-    eng = ZbotCudaEngine(model, n_env, device=local, opts=opts, ctrl_dt=a.ctrl_dt, push=push_cfg, seed=rank_seed(a.seed, rank))
+    # --obs: the network inputs come from the epilogue; the remaining mjx.Data outputs are the ones the rewards / terminations read
+    # (train.py:476, 503-546, 681-733: base / feet positions, touch + force sensors, joint state, contact flags)
+    obs_outputs = ("xpos", "qacc", "actuator_force", "sensordata", "site_xpos", "contact_mask", "solver_niter", "flags")
+    eng = ZbotCudaEngine(model, n_env, device=local, opts=opts, ctrl_dt=a.ctrl_dt, push=push_cfg, seed=rank_seed(a.seed, rank),
+                         outputs=obs_outputs if a.obs else None)
+    config["observation_epilogue"] = bool(a.obs)
     params_np = M.randomize_env_params(model, n_env, a.seed + 100 + rank) if randomized else None
     ep = EnvParams(n_env, dev, **params_np) if randomized else None
     K, W = a.steps, a.warmup
@@ -214,14 +224,17 @@ def main():
         rq[:, 3] = torch.cos(ang / 2)
         rq[:, 4:7] = ax * torch.sin(ang / 2)[:, None]
         rq[:, 2] += 0.08
-    ps = eng.reset(ep, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
+    obs = eng.new_observations(n_env) if a.obs else None
+    obs_lag = eng.sample_imu_lag(n_env, (0.0, 0.1)) if a.obs else None  # lag of re-initialised environments (pre-sampled)
+    ps = eng.reset(ep, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt, obs=obs, reset_imu_lag=obs_lag)
     done = torch.zeros((n_env,), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n_done = torch.zeros((), dtype=torch.int64, device=dev)
 
     def ctrl_step(t, act):
         # ONE launch: S fused substeps + termination check + partial reset (zb_step_autoreset_f32)
-        eng.step(act, ep, ps, push_rand=None if pushes is None else pushes[t], auto_reset=(rq, rv, rt), done_out=done)
+        eng.step(act, ep, ps, push_rand=None if pushes is None else pushes[t], auto_reset=(rq, rv, rt), done_out=done, obs=obs,
+                 reset_imu_lag=obs_lag)
 
     for t in range(W):
         ctrl_step(t, actions[t])
@@ -272,6 +285,8 @@ def main():
     # environment blocks on separate streams (the C ABI takes any [lo, hi) block), so one block's read-back overlaps the other
     # block's kernel; each block's outputs are views into ONE device buffer, i.e. one D2H copy per block.
     out_fields = ("qpos", "qvel", "xpos", "xquat", "cinert", "cvel", "qacc", "actuator_force", "sensordata")
+    if a.obs:
+        out_fields = ("qpos", "qvel", "xpos", "qacc", "actuator_force", "sensordata", "site_xpos")
     nsh = max(1, min(a.e2e_shards, n_env // 16))
     from ksim_gym_zbot_b200.sharding import shard_range
 
@@ -286,14 +301,21 @@ def main():
         sp.event_states["push_t_rem"].copy_(ps.event_states["push_t_rem"][lo:hi])
         sizes = {f: getattr(sp.data, f).numel() for f in out_fields}
         sizes["act_torque"] = sp.actuator_state.last_computed_torque.numel()
+        sob = None
+        if a.obs:
+            sob = eng.new_observations(hi - lo)
+            sob.imu_x.copy_(obs.imu_x[lo:hi]); sob.imu_lag.copy_(obs.imu_lag[lo:hi])
+            sizes["actor_obs"], sizes["critic_obs"] = sob.actor_obs.numel(), sob.critic_obs.numel()
         flat = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
         off = 0
         for f, nel in sizes.items():
-            cur = sp.actuator_state.last_computed_torque if f == "act_torque" else getattr(sp.data, f)
+            cur = sp.actuator_state.last_computed_torque if f == "act_torque" else (getattr(sob, f) if f.endswith("_obs") else getattr(sp.data, f))
             view = flat[off:off + nel].view(cur.shape)
             view.copy_(cur)
             if f == "act_torque":
                 sp.actuator_state.last_computed_torque = view
+            elif f.endswith("_obs"):
+                setattr(sob, f, view)
             else:
                 setattr(sp.data, f, view)
             off += nel
@@ -301,6 +323,7 @@ def main():
                            done=torch.zeros((hi - lo,), dtype=torch.uint8, device=dev),
                            h_done=torch.empty((hi - lo,), dtype=torch.uint8).pin_memory(),
                            d_act=torch.empty((hi - lo, M.NU), dtype=torch.float32, device=dev),
+                           obs=sob, lag=None if obs_lag is None else obs_lag[lo:hi].contiguous(),
                            ep=None if ep is None else ep.slice(lo, hi), rq=rq[lo:hi].contiguous(), rv=rv[lo:hi].contiguous(),
                            rt=rt[lo:hi].contiguous(), stream=torch.cuda.Stream(device=dev)))
     h_act = actions[W:W + K].cpu().pin_memory()
@@ -320,7 +343,7 @@ def main():
             with torch.cuda.stream(sh["stream"]):
                 sh["d_act"].copy_(h_act[i, sh["lo"]:sh["hi"]], non_blocking=True)
                 eng.step(sh["d_act"], sh["ep"], sh["ps"], push_rand=None if pushes is None else pushes[t, sh["lo"]:sh["hi"]],
-                         auto_reset=(sh["rq"], sh["rv"], sh["rt"]), done_out=sh["done"])
+                         auto_reset=(sh["rq"], sh["rv"], sh["rt"]), done_out=sh["done"], obs=sh["obs"], reset_imu_lag=sh["lag"])
                 sh["h_flat"].copy_(sh["flat"], non_blocking=True)
                 sh["h_done"].copy_(sh["done"], non_blocking=True)
         for sh in shards:
@@ -374,7 +397,7 @@ def main():
             traffic = tr["bytes_per_launch"]
     except Exception:
         pass
-    bytes_ctrl = algorithmic_bytes_per_ctrl_step(randomized, randomized)
+    bytes_ctrl = algorithmic_bytes_per_ctrl_step(randomized, randomized, a.obs)
     step_s = step_ms * 1e-3 / K  # average duration of the dominant kernel (zb_kernel<STEP>)
     roof = {
         "bound": "fp32", "unit": "TFLOP/s", "kernel": "zb_kernel<ZB_MODE_STEP>",

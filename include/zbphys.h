@@ -37,6 +37,9 @@ extern "C" {
 #define ZB_NEFC_CON (4 * ZB_MAXCON) /* pyramidal condim-3 rows                */
 #define ZB_NTRACE 128     /* solver_trace floats per environment              */
 #define ZB_NSENSORDATA 18 /* quat4 acc3 gyro3 touchL touchR forceL3 forceR3   */
+#define ZB_NCOMMAND 7     /* commands["zero_command"], train.py:416-427       */
+#define ZB_NACTOR_OBS 50  /* NUM_ACTOR_INPUTS, train.py:31-38, 53             */
+#define ZB_NCRITIC_OBS 484 /* NUM_CRITIC_INPUTS, train.py:40-52, 54           */
 
 enum { ZB_SOLVER_CG = 0, ZB_SOLVER_NEWTON = 1 };
 enum { ZB_INT_EULER = 0, ZB_INT_IMPLICITFAST = 1 };
@@ -214,6 +217,45 @@ typedef struct ZbOut {
   float* solver_trace;    /* [N, ZB_NTRACE] diagnostics: per solver iteration i (alpha, cost, ls_iters, |search|) at 4i; from 32 on the (alpha, d0, d1) of every point the FIRST line search evaluates */
 } ZbOut;
 
+/* Observation epilogue: the two network input vectors of the reference, assembled by the step /
+ * reset kernel from the values it already holds in registers, so that the rollout does not re-read cinert / cvel / ... from
+ * HBM and runs no per-observation fusions.  All pointers may be NULL (that part is skipped).
+ *
+ *   actor_obs  [N, 50]  = run_actor's concatenation, /root/reference/train.py:1624-1648:
+ *       joint_pos(20) | joint_vel(20) | imu_orientation(4) | cmd[0:2] | cmd[3] | cmd[4:7]
+ *   critic_obs [N, 484] = run_critic's concatenation, train.py:1650-1681:
+ *       joint_pos(20) | joint_vel/10 (20) | cinert[1:] (250) | cvel[1:] (150) | imu_acc(3) | imu_gyro(3) |
+ *       imu_orientation(4) | cmd(7) | actuator_force/100 (20) | base_pos(3) | base_quat(4)
+ *   with joint_pos = qpos[7:], joint_vel = qvel[6:], base_pos/quat = qpos[0:3]/[3:7] of the NEW state and the mjx.Data
+ *   fields (cinert, cvel, sensordata, actuator_force) exactly as ZbOut reports them (ksim's *Observation classes, [R]).
+ *
+ *   imu_orientation = ImuOrientationObservation.observe_stateful, train.py:837-866: the framequat sensor, spun back by the
+ *   commanded heading cmd[3] (rotate_quat_by_quat(..., inverse=True), train.py:751-787), flipped to the w >= 0 hemisphere,
+ *   then x <- x*lag + q*(1-lag) with the carry (x, lag) of train.py:846-848.  The carry lives in imu_x / imu_lag (in/out);
+ *   environments re-initialised by the launch (zb_reset_*, the auto-reset pass) restart from x = 0 and
+ *   lag = reset_imu_lag[i] (host-sampled U(lag_range), train.py:1497) before their first observation.
+ *   noise_*: pre-scaled additive observation noise (ksim adds it after observe(); imu_orientation 1 deg and imu_acc 0.5 at
+ *   train.py:1498, 1503-1505 are the only non-zero ones among the network inputs); the carry stays noise-free. */
+typedef struct ZbObs {
+  const float* command;        /* [N, ZB_NCOMMAND]; NULL = zeros (ConstantZeroCommand, train.py:416-427) */
+  float* imu_x;                /* [N, 4]  filter state, in/out (required for imu_orientation)             */
+  float* imu_lag;              /* [N]     EMA factor, in/out                                              */
+  const float* reset_imu_lag;  /* [N]     lag of re-initialised environments; NULL = keep imu_lag         */
+  const float* noise_imu_quat; /* [N, 4]  NULL = none                                                     */
+  const float* noise_imu_acc;  /* [N, 3]  NULL = none                                                     */
+  float* actor_obs;            /* [N, ZB_NACTOR_OBS]                                                      */
+  float* critic_obs;           /* [N, ZB_NCRITIC_OBS]                                                     */
+} ZbObs;
+
+/* Arguments of the auto-reset pass (see zb_step_autoreset_f32). */
+typedef struct ZbAutoResetArgs {
+  const float* reset_qpos;  /* [N, ZB_NQ] */
+  const float* reset_qvel;  /* [N, ZB_NV] */
+  const float* reset_t_rem; /* [N] or NULL */
+  uint8_t* done_out;        /* [N] or NULL */
+  float z_lo, z_hi, max_tilt_rad;
+} ZbAutoResetArgs;
+
 typedef struct ZbEngine ZbEngine; /* opaque: device copy of ZbModel + ZbOpts */
 
 /* Engine construction == mjx.put_model + ksim.get_physics_engine(...) for this path. */
@@ -240,6 +282,17 @@ int zb_step_autoreset_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams
                           const float* action, const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs,
                           int n_substeps, const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem,
                           uint8_t* done_out, float z_lo, float z_hi, float max_tilt_rad);
+
+/* zb_step_f32 / zb_step_autoreset_f32 (autoreset != NULL) with the observation epilogue: ONE launch per control step produces
+ * the next state, the mjx.Data outputs, the termination mask, the partial reset and both network input vectors. */
+int zb_step_obs_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, const ZbState* state, const float* action,
+                    const float* push_rand, int push_per_substep, const ZbOut* out, const ZbObs* obs, int n_envs,
+                    int n_substeps, const ZbAutoResetArgs* autoreset);
+
+/* zb_reset_f32 with the observation epilogue (first observation of an episode; carry re-initialised for the reset envs). */
+int zb_reset_obs_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, const ZbState* state,
+                     const uint8_t* done, const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem,
+                     const ZbOut* out, const ZbObs* obs, int n_envs);
 
 /* mjx.forward on the current state (no integration, state untouched except the free-joint
  * quaternion normalisation MJX writes back) — what MjxEngine.reset runs after the resets. */

@@ -1235,8 +1235,9 @@ struct WarpEnv {
   // ------------------------------------------------------------------------------------------
   // sensors + rne_postconstraint (A.11); only evaluated when outputs are written
   // ------------------------------------------------------------------------------------------
-  ZB_DI void sensors(float* sd /* global [18] or nullptr */) {
-    if (!sd) return;
+  float simu[10];  // imu_site lane: framequat (4), accelerometer (3), gyro (3) of the last sensors() call
+  ZB_DI void sensors(float* sd /* global [18] or nullptr */, bool keep /* the observation epilogue reads simu / act_force */) {
+    if (!sd && !keep) return;
     const ZbModel& m = D->m;
     // cacc with qacc: base part uniform, chain part by prefix scan
     float ab[6];
@@ -1270,10 +1271,10 @@ struct WarpEnv {
       float qq[4];
       quat_mul(qq, xquat, squat);
       normalize4(qq);
-      sd[ZB_SENS_IMU_QUAT + 0] = qq[0]; sd[ZB_SENS_IMU_QUAT + 1] = qq[1]; sd[ZB_SENS_IMU_QUAT + 2] = qq[2]; sd[ZB_SENS_IMU_QUAT + 3] = qq[3];
+      simu[0] = qq[0]; simu[1] = qq[1]; simu[2] = qq[2]; simu[3] = qq[3];
       float gy[3];
       matT_vec(gy, sxmat, cvel);
-      sd[ZB_SENS_IMU_GYRO + 0] = gy[0]; sd[ZB_SENS_IMU_GYRO + 1] = gy[1]; sd[ZB_SENS_IMU_GYRO + 2] = gy[2];
+      simu[7] = gy[0]; simu[8] = gy[1]; simu[9] = gy[2];
       const float diff[3] = {sxpos[0] - c0[0], sxpos[1] - c0[1], sxpos[2] - c0[2]};
       float ang[3], lin[3], acc[3], tt[3], uu[3], corr[3];
       matT_vec(ang, sxmat, cvel);
@@ -1284,8 +1285,15 @@ struct WarpEnv {
       uu[0] = cacc[3] - tt[0]; uu[1] = cacc[4] - tt[1]; uu[2] = cacc[5] - tt[2];
       matT_vec(acc, sxmat, uu);
       cross3(corr, ang, lin);
-      sd[ZB_SENS_IMU_ACC + 0] = acc[0] + corr[0]; sd[ZB_SENS_IMU_ACC + 1] = acc[1] + corr[1]; sd[ZB_SENS_IMU_ACC + 2] = acc[2] + corr[2];
+      simu[4] = acc[0] + corr[0]; simu[5] = acc[1] + corr[1]; simu[6] = acc[2] + corr[2];
+      if (sd) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) sd[ZB_SENS_IMU_QUAT + k] = simu[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { sd[ZB_SENS_IMU_ACC + k] = simu[4 + k]; sd[ZB_SENS_IMU_GYRO + k] = simu[7 + k]; }
+      }
     }
+    if (!sd) return;  // (the warp is converged here: sd and keep are warp-uniform)
     if (s == 1 || s == 2) {  // foot force sensors
       float fo[3];
       matT_vec(fo, sxmat, cf + 3);
@@ -1311,6 +1319,91 @@ struct WarpEnv {
       }
       val += shx(val, 8); val += shx(val, 4); val += shx(val, 2); val += shx(val, 1);
       if ((L & 15) == 0 && ts >= 0) sd[ts == 1 ? ZB_SENS_TOUCH_L : ZB_SENS_TOUCH_R] = val;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Observation epilogue (include/zbphys.h ZbObs): run_actor / run_critic input vectors of train.py:1624-1681,
+  // ImuOrientationObservation.observe_stateful train.py:837-866 with rotate_quat_by_quat train.py:751-787.
+  // reinit: this environment was (re)initialised by the launch -> carry restarts from (0, reset lag) (train.py:846-848).
+  // ------------------------------------------------------------------------------------------
+  ZB_DI void observe(const ZbObs& OB, int env, bool reinit) {
+    const ZbModel& m = D->m;
+    const int il = m.site_body[0];
+    float sq[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) sq[k] = shf(simu[k], il);
+    float cmd[ZB_NCOMMAND];
+#pragma unroll
+    for (int k = 0; k < ZB_NCOMMAND; k++) cmd[k] = OB.command ? OB.command[(size_t)env * ZB_NCOMMAND + k] : 0.f;
+    float ob[4] = {0.f, 0.f, 0.f, 0.f};
+    if (OB.imu_x) {
+      // heading quaternion euler_to_quat([0, 0, yaw]) = (cos(yaw/2), 0, 0, sin(yaw/2)); both operands and the product are
+      // normalised with q / (|q| + 1e-6)
+      float sy, cy;
+      sincosf(0.5f * cmd[3], &sy, &cy);
+      const float nf = sqrtf(sq[0] * sq[0] + sq[1] * sq[1] + sq[2] * sq[2] + sq[3] * sq[3]) + 1e-6f;
+      const float q2[4] = {sq[0] / nf, sq[1] / nf, sq[2] / nf, sq[3] / nf};
+      const float nh = sqrtf(cy * cy + sy * sy) + 1e-6f;
+      const float w1 = cy / nh, z1 = -(sy / nh);  // conjugate: x1 = y1 = -0
+      float r[4] = {w1 * q2[0] - z1 * q2[3], w1 * q2[1] - z1 * q2[2], w1 * q2[2] + z1 * q2[1], w1 * q2[3] + z1 * q2[0]};
+      const float nr = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]) + 1e-6f;
+      const bool flip = r[0] / nr < 0.f;
+      float lag = reinit ? (OB.reset_imu_lag ? OB.reset_imu_lag[env] : (OB.imu_lag ? OB.imu_lag[env] : 0.f)) : (OB.imu_lag ? OB.imu_lag[env] : 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float b = flip ? -(r[k] / nr) : r[k] / nr;
+        const float x0 = reinit ? 0.f : OB.imu_x[(size_t)env * 4 + k];
+        ob[k] = x0 * lag + b * (1.f - lag);
+      }
+      __syncwarp();  // every lane has read the old carry
+      if (L == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) OB.imu_x[(size_t)env * 4 + k] = ob[k];
+      }
+      if (L == 0 && OB.imu_lag && reinit && OB.reset_imu_lag) OB.imu_lag[env] = lag;
+      if (OB.noise_imu_quat) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) ob[k] += OB.noise_imu_quat[(size_t)env * 4 + k];
+      }
+    }
+    float acc[3] = {sq[4], sq[5], sq[6]};
+    if (OB.noise_imu_acc) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) acc[k] += OB.noise_imu_acc[(size_t)env * 3 + k];
+    }
+    if (OB.actor_obs) {
+      float* a = OB.actor_obs + (size_t)env * ZB_NACTOR_OBS;
+      if (hinge) { a[dof - 6] = q; a[NU + dof - 6] = qv; }
+      if (L == 0) {  // imu_orientation(4) | cmd[0:2] | cmd[3] | cmd[4:7]   (plain stores of one lane: a lane-selected
+                     //  register array would be turned into a local-memory array)
+        float* t = a + 2 * NU;
+        t[0] = ob[0]; t[1] = ob[1]; t[2] = ob[2]; t[3] = ob[3];
+        t[4] = cmd[0]; t[5] = cmd[1]; t[6] = cmd[3]; t[7] = cmd[4]; t[8] = cmd[5]; t[9] = cmd[6];
+      }
+    }
+    if (OB.critic_obs) {
+      float* c = OB.critic_obs + (size_t)env * ZB_NCRITIC_OBS;
+      if (hinge) { c[dof - 6] = q; c[NU + dof - 6] = qv / 10.f; }
+      if (isbody && L >= 1) {
+#pragma unroll
+        for (int k = 0; k < 10; k++) c[2 * NU + (L - 1) * 10 + k] = cinert[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) c[2 * NU + 250 + (L - 1) * 6 + k] = cvel[k];
+      }
+      if (L == 0) {  // imu_acc(3) | imu_gyro(3) | imu_orientation(4) | cmd(7)
+        float* t = c + 2 * NU + 400;
+        t[0] = acc[0]; t[1] = acc[1]; t[2] = acc[2]; t[3] = sq[7]; t[4] = sq[8]; t[5] = sq[9];
+        t[6] = ob[0]; t[7] = ob[1]; t[8] = ob[2]; t[9] = ob[3];
+#pragma unroll
+        for (int k = 0; k < ZB_NCOMMAND; k++) t[10 + k] = cmd[k];
+      }
+      if (act >= 0) c[2 * NU + 417 + act] = act_force / 100.f;
+      if (L == 1) {  // base_pos(3) | base_quat(4) = qpos[0:7]
+        float* t = c + 2 * NU + 417 + NU;
+#pragma unroll
+        for (int k = 0; k < 7; k++) t[k] = bq[k];
+      }
     }
   }
 };

@@ -56,12 +56,13 @@ static int fail(int code, const char* fmt, const char* a = "") {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODE, bool TRACE>
+// OBS: the observation epilogue is a separate instantiation so that the plain step keeps its register allocation
+template <int MODE, bool TRACE, bool OBS>
 __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* __restrict__ D, ZbOpts o, float meaninertia, ZbEnvParams P, ZbState S,
                                                        const float* __restrict__ action, const float* __restrict__ push_rand,
                                                        int push_per_substep, ZbOut O, int n_envs, int n_substeps,
                                                        const uint8_t* __restrict__ done, const float* __restrict__ rq,
-                                                       const float* __restrict__ rv, const float* __restrict__ rt, ZbAutoReset AR) {
+                                                       const float* __restrict__ rv, const float* __restrict__ rt, ZbAutoReset AR, ZbObs OB) {
   __shared__ float scratch[ZB_WPB][32 * ZB_SCR];
   const int L = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = blockIdx.x * (blockDim.x >> 5) + wib;  // warps per CTA is a launch-time choice (<= ZB_WPB, see pick_wpb)
@@ -134,6 +135,8 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
   const int nsub = MODE == ZB_MODE_STEP ? n_substeps : 1;
   float* sd = O.sensordata ? O.sensordata + (size_t)env * ZB_NSENSORDATA : nullptr;
   E.trace = (TRACE && O.solver_trace) ? O.solver_trace + (size_t)env * ZB_NTRACE : nullptr;
+  const bool want_obs = OBS && MODE != ZB_MODE_FORWARD && (OB.actor_obs || OB.critic_obs || OB.imu_x);
+  bool reinit = MODE == ZB_MODE_RESET;  // observation carry restarts for environments this launch (re)initialises
 
   // s == nsub is the optional auto-reset pass (zb_step_autoreset_f32): terminate -> reset state -> forward(), i.e.
   // zb_terminations_f32 + zb_reset_f32(done) folded into the step launch (first half).
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
       bad = __any_sync(ZB_FULL, bad || nonfinite);
       if (L == 0 && AR.done_out) AR.done_out[env] = bad ? 1 : 0;
       if (!bad) break;
+      reinit = true;
 #pragma unroll
       for (int k = 0; k < 7; k++) E.bq[k] = AR.reset_qpos[(size_t)env * NQ + k];
       E.q = E.hinge ? AR.reset_qpos[(size_t)env * NQ + d + 1] : 0.f;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
     const float qfrc_act = E.actuation();
     E.qfrc_smooth = E.hasdof ? qfrc_passive - E.qfrc_bias + qfrc_act : 0.f;
     const float qa = E.solve_all(implicit_damp && stepping);
-    if (last || extra) E.sensors(sd);
+    if (last || extra) E.sensors(sd, want_obs);
     if (extra) E.warm = 0.f;
     if (stepping) {
       // ---- euler / implicitfast + _advance ----
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
       if (S.time) S.time[env] = MODE == ZB_MODE_RESET ? 0.f : tm;
     }
   }
+  if (OBS && want_obs) E.observe(OB, env, reinit);
   // ---- outputs: mjx.Data fields as forward() of the last substep left them ----
   if (E.isbody) {
     if (O.xpos) { float* p = O.xpos + ((size_t)env * NB + L) * 3; p[0] = E.xpos[0]; p[1] = E.xpos[1]; p[2] = E.xpos[2]; }
@@ -564,7 +569,8 @@ static int after_launch(const char* what) {
 }
 
 static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
-                     const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps, ZbAutoReset AR) {
+                     const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps, ZbAutoReset AR,
+                     const ZbObs* obs = nullptr) {
   if (!e || !action) return fail(ZB_EINVAL, "zb_step_f32: null engine/action%s");
   if (n_envs < 0 || n_substeps < 1) return fail(ZB_EINVAL, "zb_step_f32: n_envs >= 0 and n_substeps >= 1 required%s");
   int rc = check_state(state);
@@ -572,11 +578,14 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   if (n_envs == 0) return ZB_OK;
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
+  ZbObs OB; memset(&OB, 0, sizeof(OB)); if (obs) OB = *obs;
   const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
-  if (O.solver_trace) zb_kernel<ZB_MODE_STEP, true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
-                                                                         n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR);
-  else zb_kernel<ZB_MODE_STEP, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O,
-                                                                         n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR);
+#define ZB_LAUNCH_STEP(TR, OBSV) zb_kernel<ZB_MODE_STEP, TR, OBSV><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
+    e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR, OB)
+  const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x;
+  if (O.solver_trace) { if (with_obs) ZB_LAUNCH_STEP(true, true); else ZB_LAUNCH_STEP(true, false); }
+  else { if (with_obs) ZB_LAUNCH_STEP(false, true); else ZB_LAUNCH_STEP(false, false); }
+#undef ZB_LAUNCH_STEP
   return after_launch("zb_step_f32 launch: %s");
 }
 
@@ -607,15 +616,22 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
-  if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
-                                                                            nullptr, nullptr, nullptr, nullptr, ZbAutoReset{});
-  else zb_kernel<ZB_MODE_FORWARD, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
-                                                                            nullptr, nullptr, nullptr, nullptr, ZbAutoReset{});
+  if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+                                                                            nullptr, nullptr, nullptr, nullptr, ZbAutoReset{}, ZbObs{});
+  else zb_kernel<ZB_MODE_FORWARD, false, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+                                                                            nullptr, nullptr, nullptr, nullptr, ZbAutoReset{}, ZbObs{});
   return after_launch("zb_forward_f32 launch: %s");
 }
 
-int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const uint8_t* done,
-                 const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem, const ZbOut* out, int n_envs) {
+static int check_obs(const ZbObs* obs) {
+  if (obs && (obs->actor_obs || obs->critic_obs) && !obs->imu_x) return fail(ZB_EINVAL, "obs: imu_x (filter carry) is required when actor_obs / critic_obs are requested%s");
+  if (obs && obs->imu_x && !obs->imu_lag) return fail(ZB_EINVAL, "obs: imu_lag is required with imu_x%s");
+  return ZB_OK;
+}
+
+static int reset_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const uint8_t* done,
+                      const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem, const ZbOut* out, const ZbObs* obs,
+                      int n_envs) {
   if (!e || !reset_qpos || !reset_qvel) return fail(ZB_EINVAL, "zb_reset_f32: null engine/reset_qpos/reset_qvel%s");
   if (n_envs < 0) return fail(ZB_EINVAL, "zb_reset_f32: n_envs < 0%s");
   int rc = check_state(state);
@@ -623,12 +639,43 @@ int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbS
   if (n_envs == 0) return ZB_OK;
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
+  ZbObs OB; memset(&OB, 0, sizeof(OB)); if (obs) OB = *obs;
   const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
-  if (O.solver_trace) zb_kernel<ZB_MODE_RESET, true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
-                                                                          reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{});
-  else zb_kernel<ZB_MODE_RESET, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done,
-                                                                          reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{});
+#define ZB_LAUNCH_RESET(TR, OBSV) zb_kernel<ZB_MODE_RESET, TR, OBSV><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
+    e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done, reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{}, OB)
+  const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x;
+  if (O.solver_trace) { if (with_obs) ZB_LAUNCH_RESET(true, true); else ZB_LAUNCH_RESET(true, false); }
+  else { if (with_obs) ZB_LAUNCH_RESET(false, true); else ZB_LAUNCH_RESET(false, false); }
+#undef ZB_LAUNCH_RESET
   return after_launch("zb_reset_f32 launch: %s");
+}
+
+int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const uint8_t* done,
+                 const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem, const ZbOut* out, int n_envs) {
+  return reset_impl(e, stream, params, state, done, reset_qpos, reset_qvel, reset_t_rem, out, nullptr, n_envs);
+}
+
+int zb_reset_obs_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const uint8_t* done,
+                     const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem, const ZbOut* out, const ZbObs* obs,
+                     int n_envs) {
+  int rc = check_obs(obs);
+  if (rc) return rc;
+  return reset_impl(e, stream, params, state, done, reset_qpos, reset_qvel, reset_t_rem, out, obs, n_envs);
+}
+
+int zb_step_obs_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
+                    const float* push_rand, int push_per_substep, const ZbOut* out, const ZbObs* obs, int n_envs, int n_substeps,
+                    const ZbAutoResetArgs* ar) {
+  int rc = check_obs(obs);
+  if (rc) return rc;
+  ZbAutoReset AR;
+  memset(&AR, 0, sizeof(AR));
+  if (ar) {
+    if (!ar->reset_qpos || !ar->reset_qvel) return fail(ZB_EINVAL, "zb_step_obs_f32: null reset_qpos/reset_qvel%s");
+    AR.enabled = 1; AR.z_lo = ar->z_lo; AR.z_hi = ar->z_hi; AR.cos_tilt = cosf(ar->max_tilt_rad);
+    AR.reset_qpos = ar->reset_qpos; AR.reset_qvel = ar->reset_qvel; AR.reset_t_rem = ar->reset_t_rem; AR.done_out = ar->done_out;
+  }
+  return step_impl(e, stream, params, state, action, push_rand, push_per_substep, out, n_envs, n_substeps, AR, obs);
 }
 
 int zb_terminations_f32(void* stream, const float* qpos, const int32_t* flags, uint8_t* done, int n_envs, float z_lo,

@@ -54,10 +54,20 @@ def _ptr_struct(name, names):
 ZbEnvParams = _ptr_struct("ZbEnvParams", _PARAM_FIELDS)
 ZbState = _ptr_struct("ZbState", _STATE_FIELDS)
 ZbOut = _ptr_struct("ZbOut", _OUT_F32 + _OUT_I32 + ["solver_trace"])
+_OBS_FIELDS = ["command", "imu_x", "imu_lag", "reset_imu_lag", "noise_imu_quat", "noise_imu_acc", "actor_obs", "critic_obs"]
+ZbObs = _ptr_struct("ZbObs", _OBS_FIELDS)
+NUM_ACTOR_INPUTS, NUM_CRITIC_INPUTS, NUM_COMMANDS = 50, 484, 7  # train.py:53-54, 416-427
+
+
+class ZbAutoResetArgs(ctypes.Structure):
+    _fields_ = [("reset_qpos", ctypes.c_void_p), ("reset_qvel", ctypes.c_void_p), ("reset_t_rem", ctypes.c_void_p),
+                ("done_out", ctypes.c_void_p), ("z_lo", ctypes.c_float), ("z_hi", ctypes.c_float), ("max_tilt_rad", ctypes.c_float)]
+
 
 ZB_OK, ZB_EINVAL, ZB_ENODEV, ZB_ECUDA, ZB_EUNSUP = 0, -1, -2, -3, -4
 EXPORTS = ["zb_engine_create", "zb_engine_destroy", "zb_engine_set_opts", "zb_step_f32", "zb_forward_f32", "zb_reset_f32",
-           "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count", "zb_bench_ffma", "zb_terminations_f32", "zb_step_autoreset_f32"]
+           "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count", "zb_bench_ffma", "zb_terminations_f32", "zb_step_autoreset_f32",
+           "zb_step_obs_f32", "zb_reset_obs_f32"]
 
 
 class ZbError(RuntimeError):
@@ -88,6 +98,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     lib.zb_step_autoreset_f32.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + \
         [ctypes.c_void_p] * 4 + [ctypes.c_float] * 3
+    lib.zb_step_obs_f32.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.zb_reset_obs_f32.argtypes = [ctypes.c_void_p] * 10 + [ctypes.c_int]
     lib.zb_forward_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     lib.zb_reset_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -149,6 +161,29 @@ class PhysicsState:
     event_states: dict = field(default_factory=dict)  # {"push_t_rem": [N]}
     actuator_state: PlannerState | None = None
     action_latency: torch.Tensor | None = None
+
+
+@dataclass
+class Observations:
+    """Network inputs of the reference produced by the kernel epilogue (``ZbObs`` in include/zbphys.h):
+    ``actor_obs`` [N, 50] = run_actor's concatenation (train.py:1624-1648), ``critic_obs`` [N, 484] = run_critic's
+    (train.py:1650-1681); ``imu_x`` / ``imu_lag`` are the carry of ImuOrientationObservation (train.py:846-848)."""
+
+    imu_x: torch.Tensor
+    imu_lag: torch.Tensor
+    actor_obs: torch.Tensor
+    critic_obs: torch.Tensor | None
+    lag_range: tuple[float, float] = (0.0, 0.1)  # train.py:1497
+
+    def c_struct(self, command=None, reset_imu_lag=None, noise_imu_quat=None, noise_imu_acc=None) -> ZbObs:
+        s = ZbObs()
+        for k, t in (("command", command), ("imu_x", self.imu_x), ("imu_lag", self.imu_lag), ("reset_imu_lag", reset_imu_lag),
+                     ("noise_imu_quat", noise_imu_quat), ("noise_imu_acc", noise_imu_acc), ("actor_obs", self.actor_obs),
+                     ("critic_obs", self.critic_obs)):
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), k
+                setattr(s, k, t.data_ptr())
+        return s
 
 
 @dataclass
@@ -271,6 +306,17 @@ class ZbotCudaEngine:
             actuator_state=PlannerState(z((M.NU,)), z((M.NU,)), z((M.NU,))), action_latency=z(()),
         )
 
+    def new_observations(self, n: int | None = None, critic: bool = True, lag_range: tuple[float, float] = (0.0, 0.1)) -> Observations:
+        """Buffers + carry of the observation epilogue (ImuOrientationObservation.initial_carry, train.py:846-848)."""
+        n = self.n_envs if n is None else n
+        z = lambda *shape: torch.zeros((n,) + shape, dtype=torch.float32, device=self.device)  # noqa: E731
+        return Observations(imu_x=z(4), imu_lag=self.sample_imu_lag(n, lag_range), actor_obs=z(NUM_ACTOR_INPUTS),
+                            critic_obs=z(NUM_CRITIC_INPUTS) if critic else None, lag_range=tuple(lag_range))
+
+    def sample_imu_lag(self, n: int, lag_range: tuple[float, float]) -> torch.Tensor:
+        lo, hi = lag_range
+        return (lo + (hi - lo) * torch.rand((n,), generator=self.gen, device=self.device)).contiguous()
+
     def _c_state(self, ps: PhysicsState) -> ZbState:
         s = ZbState()
         d, a = ps.data, ps.actuator_state
@@ -327,7 +373,9 @@ class ZbotCudaEngine:
     def reset(self, physics_model: EnvParams | None = None, curriculum_level: float = 1.0, rng=None,
               physics_state: PhysicsState | None = None, done: torch.Tensor | None = None,
               reset_qpos: torch.Tensor | None = None, reset_qvel: torch.Tensor | None = None,
-              reset_t_rem: torch.Tensor | None = None) -> PhysicsState:
+              reset_t_rem: torch.Tensor | None = None, obs: Observations | None = None,
+              command: torch.Tensor | None = None, reset_imu_lag: torch.Tensor | None = None,
+              obs_noise: tuple | None = None) -> PhysicsState:
         """MjxEngine.reset.  With ``physics_state`` and ``done`` given, only the finished environments are reset
         (what ksim's rollout does with ``jnp.where(done, reset_state, state)``)."""
         ps = physics_state if physics_state is not None else self.new_state()
@@ -343,10 +391,18 @@ class ZbotCudaEngine:
         if done is not None:
             dn = done.to(self.device, torch.uint8).contiguous()
         st, out = self._c_state(ps), self._c_out(ps)
-        rc = self.lib.zb_reset_f32(self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st),
-                                   None if dn is None else ctypes.c_void_p(dn.data_ptr()), ctypes.c_void_p(reset_qpos.data_ptr()),
-                                   ctypes.c_void_p(reset_qvel.data_ptr()),
-                                   None if reset_t_rem is None else ctypes.c_void_p(reset_t_rem.data_ptr()), ctypes.byref(out), n)
+        args = (self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st),
+                None if dn is None else ctypes.c_void_p(dn.data_ptr()), ctypes.c_void_p(reset_qpos.data_ptr()),
+                ctypes.c_void_p(reset_qvel.data_ptr()),
+                None if reset_t_rem is None else ctypes.c_void_p(reset_t_rem.data_ptr()), ctypes.byref(out))
+        if obs is None:
+            rc = self.lib.zb_reset_f32(*args, n)
+        else:  # first observation of the episode; the carry of the reset environments restarts (train.py:846-848)
+            if reset_imu_lag is None:
+                reset_imu_lag = self.sample_imu_lag(n, obs.lag_range)
+            nq, na = obs_noise if obs_noise is not None else (None, None)
+            ob = obs.c_struct(command, reset_imu_lag, nq, na)
+            rc = self.lib.zb_reset_obs_f32(*args, ctypes.byref(ob), n)
         self._check(rc)
         lo_, hi_ = self.action_latency_range
         new_lat = lo_ + (hi_ - lo_) * torch.rand((n,), generator=self.gen, device=self.device) if hi_ > 0 else None
@@ -363,11 +419,15 @@ class ZbotCudaEngine:
     def step(self, action: torch.Tensor, physics_model: EnvParams | None, physics_state: PhysicsState,
              curriculum_level: float = 1.0, rng=None, push_rand: torch.Tensor | None = None,
              n_substeps: int | None = None, auto_reset: tuple | None = None, done_out: torch.Tensor | None = None,
-             z_lo: float = 0.05, z_hi: float = 0.5, max_tilt: float = math.radians(60)) -> PhysicsState:
+             z_lo: float = 0.05, z_hi: float = 0.5, max_tilt: float = math.radians(60), obs: Observations | None = None,
+             command: torch.Tensor | None = None, reset_imu_lag: torch.Tensor | None = None,
+             obs_noise: tuple | None = None) -> PhysicsState:
         """MjxEngine.step: one control step = ``phys_steps_per_ctrl_steps`` fused physics substeps (in place).
 
         ``auto_reset=(reset_qpos, reset_qvel, reset_t_rem)`` folds the rollout's termination check + partial reset
-        (train.py:1588-1593, 1471-1476) into the same launch; ``done_out`` (uint8 [N]) receives the mask."""
+        (train.py:1588-1593, 1471-1476) into the same launch; ``done_out`` (uint8 [N]) receives the mask.
+        ``obs`` adds the observation epilogue: the next step's actor / critic input vectors (train.py:1624-1681) are
+        written by the same launch (``command`` [N, 7], ``obs_noise`` = (imu_quat [N, 4], imu_acc [N, 3]) pre-scaled)."""
         ps = physics_state
         n = ps.data.qpos.shape[0]
         if not (action.is_cuda and action.dtype == torch.float32 and action.is_contiguous()):
@@ -394,7 +454,22 @@ class ZbotCudaEngine:
         S = self.phys_steps_per_ctrl_steps if n_substeps is None else int(n_substeps)
         st, out = self._c_state(ps), self._c_out(ps)
         pr = None if push_rand is None else ctypes.c_void_p(push_rand.data_ptr())
-        if auto_reset is None:
+        if obs is not None:
+            ar = None
+            if auto_reset is not None:
+                rq, rv, rt = auto_reset
+                for t in (rq, rv) + ((rt,) if rt is not None else ()):
+                    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                ar = ZbAutoResetArgs(rq.data_ptr(), rv.data_ptr(), None if rt is None else rt.data_ptr(),
+                                     None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt)
+                if reset_imu_lag is None:
+                    reset_imu_lag = self.sample_imu_lag(n, obs.lag_range)
+            nq, na = obs_noise if obs_noise is not None else (None, None)
+            ob = obs.c_struct(command, reset_imu_lag, nq, na)
+            rc = self.lib.zb_step_obs_f32(self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st),
+                                          ctypes.c_void_p(action.data_ptr()), pr, per_substep, ctypes.byref(out), ctypes.byref(ob), n, S,
+                                          None if ar is None else ctypes.byref(ar))
+        elif auto_reset is None:
             rc = self.lib.zb_step_f32(self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st),
                                       ctypes.c_void_p(action.data_ptr()), pr, per_substep, ctypes.byref(out), n, S)
         else:

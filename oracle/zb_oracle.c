@@ -1376,6 +1376,76 @@ int SUF(zbo_reset)(const ZbModel* m, const ZbOpts* o, const ZboParams* p, const 
   return 0;
 }
 
+/* Observation epilogue (include/zbphys.h ZbObs): the network input vectors of the reference, from the arrays zbo_step /
+ * zbo_reset produced.  [V] run_actor train.py:1624-1648, run_critic train.py:1650-1681, ImuOrientationObservation
+ * .observe_stateful train.py:837-866 (carry train.py:846-848), rotate_quat_by_quat train.py:751-787;
+ * [R] ksim's JointPosition/JointVelocity/CenterOfMassInertia/CenterOfMassVelocity/ActuatorForce/BasePosition/
+ * BaseOrientation/SensorObservation = qpos[7:], qvel[6:], cinert[1:], cvel[1:], actuator_force, qpos[0:3], qpos[3:7],
+ * sensordata[range]; xax.euler_to_quat([0, 0, yaw]) = (cos(yaw/2), 0, 0, sin(yaw/2)); additive observation noise.
+ * reinit[i] != 0: carry of environment i restarts from x = 0, lag = reset_lag[i] before this observation. */
+int SUF(zbo_observe)(int n_envs, const real* qpos, const real* qvel, const real* cinert, const real* cvel, const real* sensordata,
+                     const real* actuator_force, const real* command, real* imu_x, real* imu_lag, const uint8_t* reinit,
+                     const real* reset_lag, const real* noise_quat, const real* noise_acc, real* actor_obs, real* critic_obs) {
+  if (n_envs < 0 || !qpos || !qvel || !sensordata || !imu_x || !imu_lag) return ZB_EINVAL;
+  const real eps = (real)1e-6;
+  for (int i = 0; i < n_envs; i++) {
+    const real* q = qpos + (size_t)i * NQ;
+    const real* v = qvel + (size_t)i * NV;
+    const real* sd = sensordata + (size_t)i * ZB_NSENSORDATA;
+    real cmd[ZB_NCOMMAND];
+    for (int k = 0; k < ZB_NCOMMAND; k++) cmd[k] = command ? command[(size_t)i * ZB_NCOMMAND + k] : 0;
+    /* heading quaternion and its conjugate; both operands normalised as q / (|q| + eps) */
+    real fq[4], hq[4] = {R_COS((real)0.5 * cmd[3]), 0, 0, R_SIN((real)0.5 * cmd[3])};
+    const real* sq = sd + ZB_SENS_IMU_QUAT;
+    real nf = R_SQRT(sq[0] * sq[0] + sq[1] * sq[1] + sq[2] * sq[2] + sq[3] * sq[3]) + eps;
+    for (int k = 0; k < 4; k++) fq[k] = sq[k] / nf;
+    real nh = R_SQRT(hq[0] * hq[0] + hq[1] * hq[1] + hq[2] * hq[2] + hq[3] * hq[3]) + eps;
+    for (int k = 0; k < 4; k++) hq[k] = hq[k] / nh;
+    for (int k = 1; k < 4; k++) hq[k] = -hq[k];
+    real r[4];
+    r[0] = hq[0] * fq[0] - hq[1] * fq[1] - hq[2] * fq[2] - hq[3] * fq[3];
+    r[1] = hq[0] * fq[1] + hq[1] * fq[0] + hq[2] * fq[3] - hq[3] * fq[2];
+    r[2] = hq[0] * fq[2] - hq[1] * fq[3] + hq[2] * fq[0] + hq[3] * fq[1];
+    r[3] = hq[0] * fq[3] + hq[1] * fq[2] - hq[2] * fq[1] + hq[3] * fq[0];
+    real nr = R_SQRT(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]) + eps;
+    for (int k = 0; k < 4; k++) r[k] = r[k] / nr;
+    if (r[0] < 0) for (int k = 0; k < 4; k++) r[k] = -r[k];
+    real* x = imu_x + (size_t)i * 4;
+    if (reinit && reinit[i]) {
+      for (int k = 0; k < 4; k++) x[k] = 0;
+      if (reset_lag) imu_lag[i] = reset_lag[i];
+    }
+    const real lag = imu_lag[i];
+    real ob[4], acc[3];
+    for (int k = 0; k < 4; k++) { x[k] = x[k] * lag + r[k] * ((real)1 - lag); ob[k] = x[k] + (noise_quat ? noise_quat[(size_t)i * 4 + k] : 0); }
+    for (int k = 0; k < 3; k++) acc[k] = sd[ZB_SENS_IMU_ACC + k] + (noise_acc ? noise_acc[(size_t)i * 3 + k] : 0);
+    if (actor_obs) {
+      real* a = actor_obs + (size_t)i * ZB_NACTOR_OBS;
+      int t = 0;
+      for (int j = 0; j < NU; j++) a[t++] = q[7 + j];
+      for (int j = 0; j < NU; j++) a[t++] = v[6 + j];
+      for (int k = 0; k < 4; k++) a[t++] = ob[k];
+      a[t++] = cmd[0]; a[t++] = cmd[1]; a[t++] = cmd[3]; a[t++] = cmd[4]; a[t++] = cmd[5]; a[t++] = cmd[6];
+    }
+    if (critic_obs) {
+      if (!cinert || !cvel || !actuator_force) return ZB_EINVAL;
+      real* c = critic_obs + (size_t)i * ZB_NCRITIC_OBS;
+      int t = 0;
+      for (int j = 0; j < NU; j++) c[t++] = q[7 + j];
+      for (int j = 0; j < NU; j++) c[t++] = v[6 + j] / (real)10;
+      for (int k = 0; k < (NB - 1) * 10; k++) c[t++] = cinert[(size_t)i * NB * 10 + 10 + k];
+      for (int k = 0; k < (NB - 1) * 6; k++) c[t++] = cvel[(size_t)i * NB * 6 + 6 + k];
+      for (int k = 0; k < 3; k++) c[t++] = acc[k];
+      for (int k = 0; k < 3; k++) c[t++] = sd[ZB_SENS_IMU_GYRO + k];
+      for (int k = 0; k < 4; k++) c[t++] = ob[k];
+      for (int k = 0; k < ZB_NCOMMAND; k++) c[t++] = cmd[k];
+      for (int j = 0; j < NU; j++) c[t++] = actuator_force[(size_t)i * NU + j] / (real)100;
+      for (int k = 0; k < 7; k++) c[t++] = q[k];
+    }
+  }
+  return 0;
+}
+
 int SUF(zbo_sizeof_data)(void) { return (int)sizeof(ZboData); }
 
 void SUF(zbo_set_variant)(int v) { g_variant = v; }

@@ -235,6 +235,23 @@ class Oracle:
         assert rc == 0, rc
         return out
 
+    def observe(self, state, out, imu_x, imu_lag, command=None, reinit=None, reset_lag=None, noise_quat=None, noise_acc=None,
+                critic=True):
+        """ZbObs epilogue on the arrays a step / reset produced: returns (actor_obs [n,50], critic_obs [n,484] or None);
+        imu_x / imu_lag (arrays of this oracle's dtype) are updated in place."""
+        n = state["qpos"].shape[0]
+        assert imu_x.dtype == self.dtype and imu_lag.dtype == self.dtype and imu_x.flags.c_contiguous
+        actor = np.zeros((n, 50), dtype=self.dtype)
+        crit = np.zeros((n, 484), dtype=self.dtype) if critic else None
+        keep = [self._arr(a) for a in (command, reset_lag, noise_quat, noise_acc)]
+        rn = None if reinit is None else np.ascontiguousarray(reinit, dtype=np.uint8)
+        P = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        fn = getattr(self.lib, "zbo_observe" + self.suf)
+        rc = fn(n, P(state["qpos"]), P(state["qvel"]), P(out["cinert"]), P(out["cvel"]), P(out["sensordata"]), P(out["actuator_force"]),
+                P(keep[0]), P(imu_x), P(imu_lag), P(rn), P(keep[1]), P(keep[2]), P(keep[3]), P(actor), P(crit))
+        assert rc == 0, rc
+        return actor, crit
+
     def set_variant(self, v: int) -> None:
         """bit 0: contact rows applied matrix-free like the CUDA kernel (diagnostics)."""
         getattr(self.lib, "zbo_set_variant" + self.suf)(int(v))

@@ -1,0 +1,200 @@
+"""Observation epilogue (ZbObs): the reference's network input vectors.
+
+CPU part: the oracle's ``zbo_observe`` against an independent numpy transcription of the reference's own code —
+``rotate_quat_by_quat`` (/root/reference/train.py:751-787), ``ImuOrientationObservation.observe_stateful``
+(train.py:837-866, carry :846-848), ``run_actor`` / ``run_critic`` concatenations (train.py:1624-1681).
+GPU part: the kernel epilogue (through the C ABI) against the oracle on the kernel's own state / mjx.Data arrays,
+including the carry restart of auto-reset environments, and the guarantee that the epilogue leaves the physics untouched.
+"""
+
+import numpy as np
+import pytest
+
+from helpers import random_actions, random_states
+
+NU, NB = 20, 26
+
+
+# ---- independent transcription of train.py (numpy, dtype-generic) ---------------------------------------------------
+def rotate_quat_by_quat(quat_to_rotate, rotating_quat, inverse=False, eps=1e-6):
+    dt = quat_to_rotate.dtype
+    eps = dt.type(eps)
+    quat_to_rotate = quat_to_rotate / (np.linalg.norm(quat_to_rotate, axis=-1, keepdims=True).astype(dt) + eps)
+    rotating_quat = rotating_quat / (np.linalg.norm(rotating_quat, axis=-1, keepdims=True).astype(dt) + eps)
+    if inverse:
+        rotating_quat = rotating_quat.copy()
+        rotating_quat[..., 1:] *= -1
+    w1, x1, y1, z1 = np.split(rotating_quat, 4, axis=-1)
+    w2, x2, y2, z2 = np.split(quat_to_rotate, 4, axis=-1)
+    w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2
+    x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2
+    y = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2
+    z = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2
+    result = np.concatenate([w, x, y, z], axis=-1)
+    return result / (np.linalg.norm(result, axis=-1, keepdims=True).astype(dt) + eps)
+
+
+def euler_to_quat(euler):  # xax.euler_to_quat (roll, pitch, yaw) [R]
+    r, p, y = euler[..., 0:1] * 0.5, euler[..., 1:2] * 0.5, euler[..., 2:3] * 0.5
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    return np.concatenate([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy,
+                           cr * cp * sy - sr * sp * cy], axis=-1).astype(euler.dtype)
+
+
+def imu_orientation_observe(sensordata, command, carry):
+    framequat = sensordata[..., 0:4]
+    yaw = command[..., 3:4]
+    hq = euler_to_quat(np.concatenate([np.zeros_like(yaw), np.zeros_like(yaw), yaw], axis=-1))
+    back = rotate_quat_by_quat(framequat, hq, inverse=True)
+    back = np.where(back[..., 0:1] < 0, -back, back)
+    x, lag = carry
+    x = x * lag[..., None] + back * (1 - lag[..., None])
+    return x, (x, lag)
+
+
+def reference_obs(qpos, qvel, cinert, cvel, sensordata, actuator_force, command, carry, noise_quat, noise_acc):
+    imu, carry = imu_orientation_observe(sensordata, command, carry)
+    imu = imu + noise_quat
+    acc = sensordata[..., 4:7] + noise_acc
+    n = qpos.shape[0]
+    actor = np.concatenate([qpos[:, 7:], qvel[:, 6:], imu, command[:, :2], command[:, 3:4], command[:, 4:]], axis=-1)
+    critic = np.concatenate([qpos[:, 7:], qvel[:, 6:] / 10.0, cinert[:, 1:].reshape(n, -1), cvel[:, 1:].reshape(n, -1), acc,
+                             sensordata[:, 7:10], imu, command, actuator_force / 100.0, qpos[:, 0:3], qpos[:, 3:7]], axis=-1)
+    return actor, critic, carry
+
+
+def _random_fields(n, seed, dtype):
+    r = np.random.default_rng(seed)
+    f = dict(qpos=r.normal(size=(n, 27)), qvel=r.normal(size=(n, 26)), cinert=r.normal(size=(n, NB, 10)), cvel=r.normal(size=(n, NB, 6)),
+             sensordata=r.normal(size=(n, 18)), actuator_force=r.normal(size=(n, NU)) * 3, command=r.uniform(-2, 2, (n, 7)))
+    q = r.normal(size=(n, 4))
+    f["sensordata"][:, 0:4] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    return {k: v.astype(dtype) for k, v in f.items()}
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 2e-6)])
+def test_oracle_observe_matches_reference_transcription(zmodel, dtype, tol):
+    import zb_oracle
+    from ksim_gym_zbot_b200 import model as M
+
+    assert (50, 484) == (2 * NU + 4 + 2 + 1 + 3, 2 * NU + 250 + 150 + 3 + 3 + 4 + 7 + NU + 3 + 4)  # train.py:31-54
+    n = 257
+    orc = zb_oracle.Oracle(zmodel, M.make_opts(), dtype)
+    r = np.random.default_rng(5)
+    x_ref, lag_ref = np.zeros((n, 4), dtype), r.uniform(0.0, 0.1, n).astype(dtype)
+    x, lag = x_ref.copy(), lag_ref.copy()
+    for t in range(4):
+        f = _random_fields(n, 100 + t, dtype)
+        if t == 0:
+            f["command"][:] = 0  # ConstantZeroCommand (train.py:416-427): heading 0 -> the backspin is the identity
+        nq, na = (r.normal(size=(n, 4)) * 0.0175).astype(dtype), (r.normal(size=(n, 3)) * 0.5).astype(dtype)
+        reinit = (r.uniform(size=n) < 0.2) if t == 2 else None
+        new_lag = r.uniform(0.0, 0.1, n).astype(dtype)
+        if reinit is not None:  # ksim: carry <- initial_carry = (zeros(4), U(lag_range)) for reset environments
+            x_ref = np.where(reinit[:, None], 0, x_ref).astype(dtype)
+            lag_ref = np.where(reinit, new_lag, lag_ref).astype(dtype)
+        a_ref, c_ref, (x_ref, lag_ref) = reference_obs(f["qpos"], f["qvel"], f["cinert"], f["cvel"], f["sensordata"],
+                                                       f["actuator_force"], f["command"], (x_ref, lag_ref), nq, na)
+        st = {"qpos": f["qpos"], "qvel": f["qvel"]}
+        out = {k: f[k] for k in ("cinert", "cvel", "sensordata", "actuator_force")}
+        a, c = orc.observe(st, out, x, lag, command=f["command"], reinit=reinit, reset_lag=new_lag, noise_quat=nq, noise_acc=na)
+        assert a.shape == (n, 50) and c.shape == (n, 484)
+        np.testing.assert_allclose(a, a_ref, rtol=0, atol=tol)
+        np.testing.assert_allclose(c, c_ref, rtol=0, atol=tol * 10)
+        np.testing.assert_allclose(x, x_ref, rtol=0, atol=tol)
+        np.testing.assert_array_equal(lag, lag_ref)
+        if t == 0:  # zero heading: imu_orientation == (1-lag) * framequat on the w >= 0 hemisphere
+            fq = f["sensordata"][:, 0:4] * np.sign(f["sensordata"][:, 0:1])
+            np.testing.assert_allclose(x, fq * (1 - lag[:, None]), atol=3e-6)
+
+
+# ---- GPU: kernel epilogue vs oracle ---------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_observation_epilogue_matches_oracle(zmodel):
+    import os
+
+    import torch
+    import zb_oracle
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import PushEventConfig, ZbotCudaEngine
+
+    n, S = 300, 4  # 300: the last CTA has spare warps
+    opts = M.make_opts(dt=0.005)
+    eng = ZbotCudaEngine(zmodel, n, device=0, opts=opts, ctrl_dt=0.02, push=PushEventConfig())
+    ref = ZbotCudaEngine(zmodel, n, device=0, opts=opts, ctrl_dt=0.02, push=PushEventConfig())
+    orc = zb_oracle.Oracle(zmodel, opts, np.float32, threads=os.cpu_count() or 1)
+    q, v = random_states(zmodel, n, 11, tilt=0.6)  # large tilts: some environments terminate within a few steps
+    r = np.random.default_rng(3)
+    T = lambda a, dt=torch.float32: torch.tensor(np.ascontiguousarray(a), dtype=dt, device=eng.device)  # noqa: E731
+    trem = T(np.full(n, 0.03, np.float32))
+    obs = eng.new_observations(n)
+    lag0 = r.uniform(0.0, 0.1, n).astype(np.float32)
+    cmd = r.uniform(-1.5, 1.5, (n, 7)).astype(np.float32)
+    ps = eng.reset(reset_qpos=T(q), reset_qvel=T(v), reset_t_rem=trem, obs=obs, command=T(cmd), reset_imu_lag=T(lag0))
+    ps_ref = ref.reset(reset_qpos=T(q), reset_qvel=T(v), reset_t_rem=trem)
+    x, lag = np.zeros((n, 4), np.float32), lag0.copy()
+
+    def check(ps, reinit, new_lag, nq, na, tag):
+        st = {"qpos": ps.data.qpos.cpu().numpy(), "qvel": ps.data.qvel.cpu().numpy()}
+        out = {k: getattr(ps.data, k).cpu().numpy() for k in ("cinert", "cvel", "sensordata", "actuator_force")}
+        a, c = orc.observe(st, out, x, lag, command=cmd, reinit=reinit, reset_lag=new_lag, noise_quat=nq, noise_acc=na)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(obs.actor_obs.cpu().numpy(), a, rtol=0, atol=2e-6, err_msg=tag)
+        # critic: cinert / cvel entries are copies (exact); the scaled / filtered ones are within rounding
+        np.testing.assert_allclose(obs.critic_obs.cpu().numpy(), c, rtol=1e-6, atol=2e-6, err_msg=tag)
+        np.testing.assert_array_equal(obs.critic_obs.cpu().numpy()[:, 40:440], c[:, 40:440])
+        np.testing.assert_allclose(obs.imu_x.cpu().numpy(), x, rtol=0, atol=2e-6, err_msg=tag)
+        np.testing.assert_array_equal(obs.imu_lag.cpu().numpy(), lag)
+
+    check(ps, np.ones(n, bool), lag0, None, None, "reset")
+    rq, rv = random_states(zmodel, n, 12)
+    rq[:, 3:7] /= np.linalg.norm(rq[:, 3:7], axis=1, keepdims=True)
+    done = torch.zeros(n, dtype=torch.uint8, device=eng.device)
+    done_ref = torch.zeros_like(done)
+    n_done = 0
+    for t in range(12):
+        act = T(random_actions(n, 50 + t))
+        pr = eng.sample_push(n)
+        nq, na = (r.normal(size=(n, 4)) * 0.0175).astype(np.float32), (r.normal(size=(n, 3)) * 0.5).astype(np.float32)
+        new_lag = r.uniform(0.0, 0.1, n).astype(np.float32)
+        ar = (T(rq), T(rv), T(np.full(n, 0.05, np.float32)))
+        eng.step(act, None, ps, push_rand=pr, auto_reset=ar, done_out=done, obs=obs, command=T(cmd), reset_imu_lag=T(new_lag),
+                 obs_noise=(T(nq), T(na)))
+        ref.step(act, None, ps_ref, push_rand=pr, auto_reset=ar, done_out=done_ref)
+        dn = done.cpu().numpy().astype(bool)
+        n_done += int(dn.sum())
+        # the epilogue must not change the physics: bitwise the same state / outputs / mask as the plain entry point
+        assert torch.equal(done, done_ref)
+        for k in ("qpos", "qvel", "qacc_warmstart", "cinert", "cvel", "sensordata", "actuator_force", "xpos"):
+            assert torch.equal(getattr(ps.data, k), getattr(ps_ref.data, k)), k
+        check(ps, dn, new_lag, nq, na, f"step {t}")
+    assert n_done > 5, "the scenario is meant to exercise the carry restart of auto-reset environments"
+
+
+@pytest.mark.gpu
+def test_observation_argument_checks(zmodel):
+    import ctypes
+
+    import torch
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import ZB_EINVAL, ZbError, ZbotCudaEngine
+
+    n = 8
+    eng = ZbotCudaEngine(zmodel, n, device=0, opts=M.make_opts(dt=0.005), ctrl_dt=0.02)
+    q, v = random_states(zmodel, n, 1)
+    ps = eng.reset(reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(v))
+    obs = eng.new_observations(n)
+    ob = obs.c_struct()
+    ob.imu_x = None  # actor_obs without the filter carry
+    st, out = eng._c_state(ps), eng._c_out(ps)
+    act = torch.zeros((n, 20), device=eng.device)
+    rc = eng.lib.zb_step_obs_f32(eng._h, eng._stream(), None, ctypes.byref(st), ctypes.c_void_p(act.data_ptr()), None, 0, ctypes.byref(out),
+                                 ctypes.byref(ob), n, 4, None)
+    assert rc == ZB_EINVAL and b"imu_x" in eng.lib.zb_last_error()
+    with pytest.raises(ZbError):
+        eng._check(rc)
+    # actor only (no critic buffer) is fine
+    obs2 = eng.new_observations(n, critic=False)
+    eng.step(act, None, ps, obs=obs2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs2.actor_obs).all() and float(obs2.actor_obs[:, 40:44].norm(dim=1).min()) > 0.5
