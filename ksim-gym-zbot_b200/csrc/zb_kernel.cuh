@@ -1235,8 +1235,9 @@ struct WarpEnv {
   // ------------------------------------------------------------------------------------------
   // sensors + rne_postconstraint (A.11); only evaluated when outputs are written
   // ------------------------------------------------------------------------------------------
-  float simu[10];  // imu_site lane: framequat (4), accelerometer (3), gyro (3) of the last sensors() call
-  ZB_DI void sensors(float* sd /* global [18] or nullptr */, bool keep /* the observation epilogue reads simu / act_force */) {
+  // keep: shared [10] (or nullptr) that receives framequat (4), accelerometer (3), gyro (3) for the observation epilogue —
+  // shared memory, not registers: the values would otherwise stay live across the substep loop and the solver
+  ZB_DI void sensors(float* sd /* global [18] or nullptr */, float* keep) {
     if (!sd && !keep) return;
     const ZbModel& m = D->m;
     // cacc with qacc: base part uniform, chain part by prefix scan
@@ -1271,6 +1272,7 @@ struct WarpEnv {
       float qq[4];
       quat_mul(qq, xquat, squat);
       normalize4(qq);
+      float simu[10];
       simu[0] = qq[0]; simu[1] = qq[1]; simu[2] = qq[2]; simu[3] = qq[3];
       float gy[3];
       matT_vec(gy, sxmat, cvel);
@@ -1286,6 +1288,10 @@ struct WarpEnv {
       matT_vec(acc, sxmat, uu);
       cross3(corr, ang, lin);
       simu[4] = acc[0] + corr[0]; simu[5] = acc[1] + corr[1]; simu[6] = acc[2] + corr[2];
+      if (keep) {
+#pragma unroll
+        for (int k = 0; k < 10; k++) keep[k] = simu[k];
+      }
       if (sd) {
 #pragma unroll
         for (int k = 0; k < 4; k++) sd[ZB_SENS_IMU_QUAT + k] = simu[k];
@@ -1327,12 +1333,11 @@ struct WarpEnv {
   // ImuOrientationObservation.observe_stateful train.py:837-866 with rotate_quat_by_quat train.py:751-787.
   // reinit: this environment was (re)initialised by the launch -> carry restarts from (0, reset lag) (train.py:846-848).
   // ------------------------------------------------------------------------------------------
-  ZB_DI void observe(const ZbObs& OB, int env, bool reinit) {
-    const ZbModel& m = D->m;
-    const int il = m.site_body[0];
+  ZB_DI void observe(const ZbObs& OB, int env, bool reinit, const float* keep /* shared [10] written by sensors() */) {
+    __syncwarp();
     float sq[10];
 #pragma unroll
-    for (int k = 0; k < 10; k++) sq[k] = shf(simu[k], il);
+    for (int k = 0; k < 10; k++) sq[k] = keep[k];
     float cmd[ZB_NCOMMAND];
 #pragma unroll
     for (int k = 0; k < ZB_NCOMMAND; k++) cmd[k] = OB.command ? OB.command[(size_t)env * ZB_NCOMMAND + k] : 0.f;

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
                                                        const uint8_t* __restrict__ done, const float* __restrict__ rq,
                                                        const float* __restrict__ rv, const float* __restrict__ rt, ZbAutoReset AR, ZbObs OB) {
   __shared__ float scratch[ZB_WPB][32 * ZB_SCR];
+  __shared__ float imu_keep[OBS ? ZB_WPB : 1][16];  // sensors() -> observe() hand-over of the IMU sensor values
   const int L = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = blockIdx.x * (blockDim.x >> 5) + wib;  // warps per CTA is a launch-time choice (<= ZB_WPB, see pick_wpb)
   // (vote: makes the flag provably warp-uniform for ptxas; a divergent-looking exit around barriers would wrap every
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
     const float qfrc_act = E.actuation();
     E.qfrc_smooth = E.hasdof ? qfrc_passive - E.qfrc_bias + qfrc_act : 0.f;
     const float qa = E.solve_all(implicit_damp && stepping);
-    if (last || extra) E.sensors(sd, want_obs);
+    if (last || extra) E.sensors(sd, (OBS && want_obs) ? imu_keep[OBS ? wib : 0] : nullptr);
     if (extra) E.warm = 0.f;
     if (stepping) {
       // ---- euler / implicitfast + _advance ----
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* _
       if (S.time) S.time[env] = MODE == ZB_MODE_RESET ? 0.f : tm;
     }
   }
-  if (OBS && want_obs) E.observe(OB, env, reinit);
+  if (OBS && want_obs) E.observe(OB, env, reinit, imu_keep[OBS ? wib : 0]);
   // ---- outputs: mjx.Data fields as forward() of the last substep left them ----
   if (E.isbody) {
     if (O.xpos) { float* p = O.xpos + ((size_t)env * NB + L) * 3; p[0] = E.xpos[0]; p[1] = E.xpos[1]; p[2] = E.xpos[2]; }
