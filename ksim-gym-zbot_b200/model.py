@@ -469,7 +469,14 @@ def build_zbot_syn() -> ZbModel:
         m.field("site_quat")[k] = _QI
         m.field("site_size")[k] = (0.06, 0.035, 0.02)
 
-    # ---- mj_setConst equivalents at qpos0 ----
+    set_const(m)
+    return m
+
+
+def set_const(m: ZbModel) -> None:
+    """MuJoCo's ``mj_setConst`` for the fields this path reads ([R]): ``dof_invweight0`` (diagonal of ``M^-1`` at ``qpos0``,
+    averaged over the translational / rotational triples of the free joint), ``body_invweight0`` (mean translational /
+    rotational diagonal of ``J M^-1 J^T`` at the body COM) and ``meaninertia`` (mean diagonal of ``M``)."""
     qpos0 = m.field("qpos0").astype(np.float64)
     M, jacs = _mass_matrix_np(m, qpos0)
     Minv = np.linalg.inv(M)
@@ -478,11 +485,11 @@ def build_zbot_syn() -> ZbModel:
     inv0[0:3] = diag[0:3].mean()
     inv0[3:6] = diag[3:6].mean()
     inv0[6:] = diag[6:]
+    m.field("body_invweight0")[0] = 0.0
     for b in range(1, NBODY):
         jp_, jr = jacs[b]
         m.field("body_invweight0")[b] = (np.trace(jp_ @ Minv @ jp_.T) / 3.0, np.trace(jr @ Minv @ jr.T) / 3.0)
     m.meaninertia = float(np.diag(M).mean())
-    return m
 
 
 def total_mass(m: ZbModel) -> float:
