@@ -556,3 +556,51 @@ def test_default_pose_trace_golden(zmodel):
     print("   fp32 oracle vs fp64 oracle at the same steps:", e32[0], e32[9], e32[-1])
     assert err[0] < max(1e-5, 5 * e32[0]) and err[-1] < max(2e-4, 5 * e32[-1])  # one env = one sample of a chaotic solve
     eng.close()
+
+
+def test_step_is_cuda_graph_capturable(zmodel):
+    """The ABI promises enqueue-only calls (no allocation, no synchronisation, no host state): a control step captured in a
+    CUDA graph (what XLA's command buffers do with a custom call) replays to bitwise the same states as eager launches."""
+    from ksim_gym_zbot_b200 import model as M
+
+    n, S = 200, 4
+    opts = M.make_opts(dt=0.005)
+    q, v = random_states(zmodel, n, 21)
+    rq, rv = random_states(zmodel, n, 22)
+    res = []
+    for use_graph in (False, True):
+        eng = _engine(zmodel, n, opts=opts, ctrl_dt=0.02)
+        dev = eng.device
+        ps = eng.reset(reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(v), reset_t_rem=torch.full((n,), 1e9))
+        obs = eng.new_observations(n)
+        obs.imu_lag.fill_(0.05)
+        lag = torch.full((n,), 0.07, device=dev)
+        ar = (torch.tensor(rq, device=dev), torch.tensor(rv, device=dev), torch.full((n,), 1e9, device=dev))
+        done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        act = torch.zeros((n, 20), device=dev)
+        acts = [torch.tensor(random_actions(n, 300 + t), device=dev) for t in range(4)]
+        step = lambda: eng.step(act, None, ps, auto_reset=ar, done_out=done, obs=obs, reset_imu_lag=lag)  # noqa: E731
+        if use_graph:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                launches0 = eng.launch_count()
+                with torch.cuda.graph(g, stream=side):
+                    step()
+                assert eng.launch_count() == launches0 + 1  # one kernel per control step went into the graph
+            torch.cuda.current_stream(dev).wait_stream(side)
+            # capture does not execute: state is still the reset state
+            for a in acts:
+                act.copy_(a)
+                g.replay()
+        else:
+            for a in acts:
+                act.copy_(a)
+                step()
+        torch.cuda.synchronize()
+        res.append({k: getattr(ps.data, k).clone() for k in ("qpos", "qvel", "qacc_warmstart", "sensordata", "cinert")} |
+                   {"actor": obs.actor_obs.clone(), "critic": obs.critic_obs.clone(), "x": obs.imu_x.clone()})
+    for k in res[0]:
+        assert torch.equal(res[0][k], res[1][k]), k
