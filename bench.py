@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--ls-iterations", type=int, default=8)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-shards", type=int, default=4, help="environment blocks (streams) the end-to-end loop drives the batch in")
+    ap.add_argument("--e2e-shards", type=int, default=0, help="environment blocks (streams) the end-to-end loop drives the batch in; "
+                    "0 = pick the fastest of 1 / 2 / 4 in a short untimed calibration")
     ap.add_argument("--obs", action="store_true", help="observation epilogue: the launch also writes the actor [50] / critic [484] input vectors "
                     "(train.py:1624-1681); only those + the reward inputs are written / read back instead of every mjx.Data array")
     ap.add_argument("--seed", type=int, default=0)
@@ -287,72 +288,96 @@ def main():
     out_fields = ("qpos", "qvel", "xpos", "xquat", "cinert", "cvel", "qacc", "actuator_force", "sensordata")
     if a.obs:
         out_fields = ("qpos", "qvel", "xpos", "qacc", "actuator_force", "sensordata", "site_xpos")
-    nsh = max(1, min(a.e2e_shards, n_env // 16))
     from ksim_gym_zbot_b200.sharding import shard_range
 
-    shards = []
-    for k in range(nsh):
-        lo, hi = shard_range(n_env, nsh, k)
-        sp = eng.new_state(hi - lo)
-        for f in ("qpos", "qvel", "qacc_warmstart", "time"):
-            getattr(sp.data, f).copy_(getattr(ps.data, f)[lo:hi])
-        for f in ("position", "velocity", "last_computed_torque"):
-            getattr(sp.actuator_state, f).copy_(getattr(ps.actuator_state, f)[lo:hi])
-        sp.event_states["push_t_rem"].copy_(ps.event_states["push_t_rem"][lo:hi])
-        sizes = {f: getattr(sp.data, f).numel() for f in out_fields}
-        sizes["act_torque"] = sp.actuator_state.last_computed_torque.numel()
-        sob = None
-        if a.obs:
-            sob = eng.new_observations(hi - lo)
-            sob.imu_x.copy_(obs.imu_x[lo:hi]); sob.imu_lag.copy_(obs.imu_lag[lo:hi])
-            sizes["actor_obs"], sizes["critic_obs"] = sob.actor_obs.numel(), sob.critic_obs.numel()
-        flat = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
-        off = 0
-        for f, nel in sizes.items():
-            cur = sp.actuator_state.last_computed_torque if f == "act_torque" else (getattr(sob, f) if f.endswith("_obs") else getattr(sp.data, f))
-            view = flat[off:off + nel].view(cur.shape)
-            view.copy_(cur)
-            if f == "act_torque":
-                sp.actuator_state.last_computed_torque = view
-            elif f.endswith("_obs"):
-                setattr(sob, f, view)
-            else:
-                setattr(sp.data, f, view)
-            off += nel
-        shards.append(dict(lo=lo, hi=hi, ps=sp, flat=flat, h_flat=torch.empty_like(flat, device="cpu").pin_memory(),
-                           done=torch.zeros((hi - lo,), dtype=torch.uint8, device=dev),
-                           h_done=torch.empty((hi - lo,), dtype=torch.uint8).pin_memory(),
-                           d_act=torch.empty((hi - lo, M.NU), dtype=torch.float32, device=dev),
-                           obs=sob, lag=None if obs_lag is None else obs_lag[lo:hi].contiguous(),
-                           ep=None if ep is None else ep.slice(lo, hi), rq=rq[lo:hi].contiguous(), rv=rv[lo:hi].contiguous(),
-                           rt=rt[lo:hi].contiguous(), stream=torch.cuda.Stream(device=dev)))
+    def build_shards(nsh):
+        shards = []
+        for k in range(nsh):
+            lo, hi = shard_range(n_env, nsh, k)
+            sp = eng.new_state(hi - lo)
+            for f in ("qpos", "qvel", "qacc_warmstart", "time"):
+                getattr(sp.data, f).copy_(getattr(ps.data, f)[lo:hi])
+            for f in ("position", "velocity", "last_computed_torque"):
+                getattr(sp.actuator_state, f).copy_(getattr(ps.actuator_state, f)[lo:hi])
+            sp.event_states["push_t_rem"].copy_(ps.event_states["push_t_rem"][lo:hi])
+            sizes = {f: getattr(sp.data, f).numel() for f in out_fields}
+            sizes["act_torque"] = sp.actuator_state.last_computed_torque.numel()
+            sob = None
+            if a.obs:
+                sob = eng.new_observations(hi - lo)
+                sob.imu_x.copy_(obs.imu_x[lo:hi]); sob.imu_lag.copy_(obs.imu_lag[lo:hi])
+                sizes["actor_obs"], sizes["critic_obs"] = sob.actor_obs.numel(), sob.critic_obs.numel()
+            flat = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
+            off = 0
+            for f, nel in sizes.items():
+                cur = sp.actuator_state.last_computed_torque if f == "act_torque" else (getattr(sob, f) if f.endswith("_obs") else getattr(sp.data, f))
+                view = flat[off:off + nel].view(cur.shape)
+                view.copy_(cur)
+                if f == "act_torque":
+                    sp.actuator_state.last_computed_torque = view
+                elif f.endswith("_obs"):
+                    setattr(sob, f, view)
+                else:
+                    setattr(sp.data, f, view)
+                off += nel
+            shards.append(dict(lo=lo, hi=hi, ps=sp, flat=flat, h_flat=torch.empty_like(flat, device="cpu").pin_memory(),
+                               done=torch.zeros((hi - lo,), dtype=torch.uint8, device=dev),
+                               h_done=torch.empty((hi - lo,), dtype=torch.uint8).pin_memory(),
+                               d_act=torch.empty((hi - lo, M.NU), dtype=torch.float32, device=dev),
+                               obs=sob, lag=None if obs_lag is None else obs_lag[lo:hi].contiguous(),
+                               ep=None if ep is None else ep.slice(lo, hi), rq=rq[lo:hi].contiguous(), rv=rv[lo:hi].contiguous(),
+                               rt=rt[lo:hi].contiguous(), stream=torch.cuda.Stream(device=dev)))
+        return shards
+
     h_act = actions[W:W + K].cpu().pin_memory()
+
+    def run_e2e(shards, steps):
+        """`steps` closed-loop control steps; returns the device time in ms (events on the main stream around everything)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        main = torch.cuda.current_stream()
+        e0.record()
+        for sh in shards:
+            sh["stream"].wait_stream(main)
+        for i in range(steps):
+            t = W + i
+            for sh in shards:
+                with torch.cuda.stream(sh["stream"]):
+                    sh["d_act"].copy_(h_act[i, sh["lo"]:sh["hi"]], non_blocking=True)
+                    eng.step(sh["d_act"], sh["ep"], sh["ps"], push_rand=None if pushes is None else pushes[t, sh["lo"]:sh["hi"]],
+                             auto_reset=(sh["rq"], sh["rv"], sh["rt"]), done_out=sh["done"], obs=sh["obs"], reset_imu_lag=sh["lag"])
+                    sh["h_flat"].copy_(sh["flat"], non_blocking=True)
+                    sh["h_done"].copy_(sh["done"], non_blocking=True)
+            for sh in shards:
+                sh["stream"].synchronize()  # the caller reads the result of step i before issuing step i+1
+        for sh in shards:
+            main.wait_stream(sh["stream"])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # how many blocks: a launch picks its CTA shape for a GPU of its own, so the best split depends on the batch size
+    cands = [max(1, min(a.e2e_shards, n_env // 16))] if a.e2e_shards > 0 else [c for c in (1, 2, 4) if n_env // c >= 16]
+    calib = {}
+    if len(cands) > 1:
+        for c in cands:
+            sh_ = build_shards(c)
+            run_e2e(sh_, min(3, K))
+            calib[c] = run_e2e(sh_, min(10, K)) / min(10, K)
+            del sh_
+        t_c = torch.tensor([calib[c] for c in cands], device=dev)
+        if world > 1:
+            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)  # every rank must take the same decision
+        nsh = cands[int(torch.argmin(t_c).item())]
+    else:
+        nsh = cands[0]
+    shards = build_shards(nsh)
     h2d = h_act[0].numel() * 4
     d2h = sum(sh["h_flat"].numel() * 4 + sh["h_done"].numel() for sh in shards)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    main = torch.cuda.current_stream()
-    e0.record()
-    for sh in shards:
-        sh["stream"].wait_stream(main)
-    for i in range(K):
-        t = W + i
-        for sh in shards:
-            with torch.cuda.stream(sh["stream"]):
-                sh["d_act"].copy_(h_act[i, sh["lo"]:sh["hi"]], non_blocking=True)
-                eng.step(sh["d_act"], sh["ep"], sh["ps"], push_rand=None if pushes is None else pushes[t, sh["lo"]:sh["hi"]],
-                         auto_reset=(sh["rq"], sh["rv"], sh["rt"]), done_out=sh["done"], obs=sh["obs"], reset_imu_lag=sh["lag"])
-                sh["h_flat"].copy_(sh["flat"], non_blocking=True)
-                sh["h_done"].copy_(sh["done"], non_blocking=True)
-        for sh in shards:
-            sh["stream"].synchronize()  # the caller reads the result of step i before issuing step i+1
-    for sh in shards:
-        main.wait_stream(sh["stream"])
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_value, _ = aggregate_throughput(n_env * S * K, e0.elapsed_time(e1), dev)
+    e2e_ms = run_e2e(shards, K)
+    e2e_value, _ = aggregate_throughput(n_env * S * K, e2e_ms, dev)
     clk = clocks.stop() if rank == 0 else None
 
     # ---------------- FP32 peak probe (roofline denominator; not in MEASURED_PEAKS.json) ----------------
@@ -414,7 +439,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "streams": nsh},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "streams": nsh,
+                "streams_calibration_ms_per_step": calib or None},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         "stats": {"solver_niter_mean_last_step": niter_mean, "active_contacts_mean_last_step": ncon_mean, "resets_per_step": resets_per_step,
                   "ctrl_steps_per_s": value / S, "solver_niter_mean_cpu_sample": niter_cpu, "flops_per_stage": flops_stage},

@@ -13,8 +13,9 @@
 //   chain scans  : Hillis-Steele over contiguous body lanes with shfl_up / shfl_down
 //   mass matrix  : M = [[A, B^T], [B, C]], C block-diagonal per chain -> block LDL^T
 //                  (chain factors in parallel, Schur complement S = A - Wt^T D^-1 Wt on the base lanes)
-//   execution    : 16 environments per 512-thread CTA, the warps meet at a barrier at every substep so that they stream the
-//                  same instructions (instruction fetch was the top stall of the first version, see profiles/README.md)
+//   execution    : 16 (128 registers) or 28 (72 registers) environments per CTA, chosen per launch; the warps meet at a barrier
+//                  at every substep so that they stream the same instructions (instruction fetch was the top stall of the
+//                  first version, see profiles/README.md)
 //   constraints  : friction-loss / limit rows are single-entry rows owned by the dof lane; contact rows
 //                  are applied matrix-free: J[r, :] = w_r . cdof[:] (w_r = contact wrench direction), so
 //                  J v = w_r . V_foot(v) and J^T f = cdof . sum_r f_r w_r.
@@ -31,13 +32,13 @@
 #define BL0 (32 - 6) /* first base-dof lane */
 #define CHD 6        /* dof positions per chain group (legs: 6, arms: 4) */
 #ifndef ZB_WPB
-#define ZB_WPB 16 /* warps (environments) per CTA: one 512-thread CTA per SM at 128 registers */
+#define ZB_WPB 16 /* latency profile: 16 warps (environments) per 512-thread CTA, one CTA per SM at 128 registers */
+#endif
+#ifndef ZB_WPB_WIDE
+#define ZB_WPB_WIDE 28 /* throughput profile: 28 warps per 896-thread CTA at 72 registers (spills, but 4096 envs fit ONE wave of 148 SMs) */
 #endif
 #ifndef ZB_CTA_LOCKSTEP
 #define ZB_CTA_LOCKSTEP 1 /* 1: the warps of a CTA meet at every substep (shared instruction fetch: +30 %); 2: also before every solver pass (measured slower: waits for the slowest line search) */
-#endif
-#ifndef ZB_MINB
-#define ZB_MINB 1 /* min resident CTAs per SM the register allocation must allow */
 #endif
 #define ZB_SCR 8     /* scratch floats per lane */
 

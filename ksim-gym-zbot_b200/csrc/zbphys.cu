@@ -33,16 +33,28 @@ struct ZbEngine {
   int force_wpb;  // ZBPHYS_WPB environment override (experiments), 0 = automatic
 };
 
-// Warps (environments) per CTA of a launch.  One 16-warp CTA is resident per SM.  A batch that does not fill one wave
-// (n < 16 * SMs) is spread over all SMs with smaller CTAs (1024 envs: 147 CTAs of 7 warps, 0.35 ms instead of 64 CTAs of 16,
-// 0.43 ms); larger batches keep 16: two waves of 14 warps measured no faster than 148 + 108 CTAs of 16 (the warps are
-// latency-bound, a CTA of 14 takes as long as one of 16 — profiles/README.md).
-static int pick_wpb(const ZbEngine* e, int n_envs) {
-  if (e->force_wpb > 0) return e->force_wpb;
+// CTA shape of a launch: (profile, warps per CTA).  One CTA is resident per SM and a warp's speed hardly depends on its
+// co-residents (the kernel is latency-bound per warp: 6.4 cycles per instruction even at 7 warps per SM), so the time of a batch
+// is (number of waves) x (time of one CTA) and the shape is chosen to minimise the waves:
+//   * n <= 16 SMs  : latency profile (128 registers), ceil(n / SMs) warps per CTA: every SM gets a small CTA
+//                    (1024 envs: 147 CTAs of 7 warps, 0.35 ms instead of 64 CTAs of 16, 0.43 ms);
+//   * larger       : throughput profile (72 registers, up to 28 warps): spills make one CTA ~1.6x slower (0.60 vs 0.37 ms per
+//                    4 substeps) but it carries 1.75x the environments — 4096 envs run in ONE wave instead of 1.73
+//                    (0.605 vs 0.737 ms), 8192 in two instead of 3.5 (1.18 vs 1.39 ms), 16 384: 2.29 vs 2.48 ms
+//                    (profiles/r1_occupancy_sweep2.txt).  The CTAs are balanced over the waves: ceil(n / (waves SMs)) warps.
+struct CtaShape { bool wide; int wpb; };
+static CtaShape pick_shape(const ZbEngine* e, int n_envs, bool wide_available) {
   const int sms = e->num_sms > 0 ? e->num_sms : 148;
-  if (n_envs >= ZB_WPB * sms) return ZB_WPB;
-  const int w = (n_envs + sms - 1) / sms;
-  return w < 1 ? 1 : w;
+  if (e->force_wpb > 0) return {wide_available && e->force_wpb > ZB_WPB, e->force_wpb > ZB_WPB && !wide_available ? ZB_WPB : e->force_wpb};
+  if (n_envs <= ZB_WPB * sms || !wide_available) {
+    const int w = (n_envs + sms - 1) / sms;
+    return {false, w < 1 ? 1 : (w > ZB_WPB ? ZB_WPB : w)};
+  }
+  const long long per_wave = (long long)ZB_WPB_WIDE * sms;
+  const long long waves = (n_envs + per_wave - 1) / per_wave;
+  int w = (int)((n_envs + waves * sms - 1) / (waves * sms));
+  if (w > ZB_WPB_WIDE) w = ZB_WPB_WIDE;
+  return {true, w};
 }
 
 static thread_local char g_err[512] = "";
@@ -57,14 +69,14 @@ static int fail(int code, const char* fmt, const char* a = "") {
 // the kernel
 // ---------------------------------------------------------------------------------------------
 // OBS: the observation epilogue is a separate instantiation so that the plain step keeps its register allocation
-template <int MODE, bool TRACE, bool OBS>
-__global__ void __launch_bounds__(ZB_WPB * 32, ZB_MINB) zb_kernel(const ZbDev* __restrict__ D, ZbOpts o, float meaninertia, ZbEnvParams P, ZbState S,
+template <int MODE, bool TRACE, bool OBS, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict__ D, ZbOpts o, float meaninertia, ZbEnvParams P, ZbState S,
                                                        const float* __restrict__ action, const float* __restrict__ push_rand,
                                                        int push_per_substep, ZbOut O, int n_envs, int n_substeps,
                                                        const uint8_t* __restrict__ done, const float* __restrict__ rq,
                                                        const float* __restrict__ rv, const float* __restrict__ rt, ZbAutoReset AR, ZbObs OB) {
-  __shared__ float scratch[ZB_WPB][32 * ZB_SCR];
-  __shared__ float imu_keep[OBS ? ZB_WPB : 1][16];  // sensors() -> observe() hand-over of the IMU sensor values
+  __shared__ float scratch[WPB][32 * ZB_SCR];
+  __shared__ float imu_keep[OBS ? WPB : 1][16];  // sensors() -> observe() hand-over of the IMU sensor values
   const int L = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = blockIdx.x * (blockDim.x >> 5) + wib;  // warps per CTA is a launch-time choice (<= ZB_WPB, see pick_wpb)
   // (vote: makes the flag provably warp-uniform for ptxas; a divergent-looking exit around barriers would wrap every
@@ -517,7 +529,7 @@ int zb_engine_create(const ZbModel* model, const ZbOpts* opts, int device, ZbEng
   e->force_wpb = 0;
   if (const char* w = getenv("ZBPHYS_WPB")) {
     const int v = atoi(w);
-    if (v >= 1 && v <= ZB_WPB) e->force_wpb = v;
+    if (v >= 1 && v <= ZB_WPB_WIDE) e->force_wpb = v;  // > ZB_WPB selects the throughput profile
   }
   rc = derive(&e->host);
   if (rc) { delete e; return rc; }
@@ -580,12 +592,14 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   ZbObs OB; memset(&OB, 0, sizeof(OB)); if (obs) OB = *obs;
-  const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
-#define ZB_LAUNCH_STEP(TR, OBSV) zb_kernel<ZB_MODE_STEP, TR, OBSV><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
-    e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR, OB)
   const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x;
-  if (O.solver_trace) { if (with_obs) ZB_LAUNCH_STEP(true, true); else ZB_LAUNCH_STEP(true, false); }
-  else { if (with_obs) ZB_LAUNCH_STEP(false, true); else ZB_LAUNCH_STEP(false, false); }
+  const CtaShape cs = pick_shape(e, n_envs, !O.solver_trace);  // the diagnostics instantiation exists in the latency profile only
+  const int wpb = cs.wpb, grid = (n_envs + wpb - 1) / wpb;
+#define ZB_LAUNCH_STEP(TR, OBSV, W) zb_kernel<ZB_MODE_STEP, TR, OBSV, W><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
+    e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR, OB)
+  if (O.solver_trace) { if (with_obs) ZB_LAUNCH_STEP(true, true, ZB_WPB); else ZB_LAUNCH_STEP(true, false, ZB_WPB); }
+  else if (cs.wide) { if (with_obs) ZB_LAUNCH_STEP(false, true, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); }
+  else { if (with_obs) ZB_LAUNCH_STEP(false, true, ZB_WPB); else ZB_LAUNCH_STEP(false, false, ZB_WPB); }
 #undef ZB_LAUNCH_STEP
   return after_launch("zb_step_f32 launch: %s");
 }
@@ -616,10 +630,10 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   if (n_envs == 0) return ZB_OK;
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
-  const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
-  if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+  const int wpb = pick_shape(e, n_envs, false).wpb, grid = (n_envs + wpb - 1) / wpb;
+  if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true, false, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
                                                                             nullptr, nullptr, nullptr, nullptr, ZbAutoReset{}, ZbObs{});
-  else zb_kernel<ZB_MODE_FORWARD, false, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
+  else zb_kernel<ZB_MODE_FORWARD, false, false, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
                                                                             nullptr, nullptr, nullptr, nullptr, ZbAutoReset{}, ZbObs{});
   return after_launch("zb_forward_f32 launch: %s");
 }
@@ -641,8 +655,8 @@ static int reset_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, cons
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   ZbObs OB; memset(&OB, 0, sizeof(OB)); if (obs) OB = *obs;
-  const int wpb = pick_wpb(e, n_envs), grid = (n_envs + wpb - 1) / wpb;
-#define ZB_LAUNCH_RESET(TR, OBSV) zb_kernel<ZB_MODE_RESET, TR, OBSV><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
+  const int wpb = pick_shape(e, n_envs, false).wpb, grid = (n_envs + wpb - 1) / wpb;
+#define ZB_LAUNCH_RESET(TR, OBSV) zb_kernel<ZB_MODE_RESET, TR, OBSV, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
     e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done, reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{}, OB)
   const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x;
   if (O.solver_trace) { if (with_obs) ZB_LAUNCH_RESET(true, true); else ZB_LAUNCH_RESET(true, false); }

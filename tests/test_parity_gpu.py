@@ -604,3 +604,34 @@ def test_step_is_cuda_graph_capturable(zmodel):
                    {"actor": obs.actor_obs.clone(), "critic": obs.critic_obs.clone(), "x": obs.imu_x.clone()})
     for k in res[0]:
         assert torch.equal(res[0][k], res[1][k]), k
+
+
+def test_cta_shape_does_not_change_results(zmodel, monkeypatch):
+    """Warps per CTA are a launch-time choice (sub-wave batches are spread over the SMs).  An environment's result must not depend on
+    it, and the spare warps of a partly filled last CTA (they only keep the barrier count) must not disturb anything."""
+    n = 37
+    q, v = random_states(zmodel, n, 211, tilt=0.5)
+    rq, rv = random_states(zmodel, n, 212, tilt=0.01)
+    act = [torch.tensor(random_actions(n, 213 + t), device="cuda") for t in range(3)]
+    res = []
+    for wpb in (None, "16", "5", "1"):  # automatic (1 warp per CTA at n = 37), 16 + 16 + 5 (11 spare warps), 7 x 5 + 2, 37 x 1
+        if wpb is None:
+            monkeypatch.delenv("ZBPHYS_WPB", raising=False)
+        else:
+            monkeypatch.setenv("ZBPHYS_WPB", wpb)
+        eng = _engine(zmodel, n, dt=0.005, ctrl_dt=0.02)
+        ps = eng.reset(reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(v), reset_t_rem=torch.full((n,), 1e9))
+        done = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        obs = eng.new_observations(n)
+        obs.imu_lag.fill_(0.03)
+        for a in act:
+            eng.step(a, None, ps, auto_reset=(torch.tensor(rq, device="cuda"), torch.tensor(rv, device="cuda"), None), done_out=done, obs=obs,
+                     reset_imu_lag=torch.full((n,), 0.06, device="cuda"))
+        r = _to_np(ps)
+        r["done"], r["actor"], r["critic"] = done.cpu().numpy(), obs.actor_obs.cpu().numpy(), obs.critic_obs.cpu().numpy()
+        res.append(r)
+        eng.close()
+    monkeypatch.delenv("ZBPHYS_WPB", raising=False)
+    for other in res[1:]:
+        for k in ("qpos", "qvel", "qacc_warmstart", "xpos", "cinert", "sensordata", "efc_force", "contact_mask", "solver_niter", "done", "actor", "critic"):
+            np.testing.assert_array_equal(res[0][k], other[k], err_msg=k)
