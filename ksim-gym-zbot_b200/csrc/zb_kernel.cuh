@@ -119,7 +119,7 @@ struct WarpEnv {
   float sxpos[3], sxmat[9];
   // dynamics
   float Bm[6], C[CHD];
-  Factor F0, F1;
+  Factor F0;  // factor of M; replaced by the Newton Hessian's / by the factor of M + dt D when those are needed (solve_all)
   float qfrc_smooth, qacc_smooth, act_force, qfrc_bias;
   // constraint rows
   bool fr_on, lm_on, c_on, any_limit, fr_quad;
@@ -473,7 +473,7 @@ struct WarpEnv {
 
   // smooth.solve_m: x <- (M + diag)^-1 x, x distributed over the dof lanes
   ZB_DI float solve(float x) {
-    const Factor& F = F0;  // solve_all moves the (M + dt D) factor into F0 before the integration solve
+    const Factor& F = F0;  // solve_all re-factors F0 (Newton Hessian, M + dt D) when another matrix is to be solved
     if (!hasdof) x = 0.f;
     // chains: unit forward substitution  y_c = Lt_c^-1 r_c
 #pragma unroll
@@ -1187,10 +1187,21 @@ struct WarpEnv {
           pg = grad; pMg = Mgrad;
           grad = hasdof ? Ma - qfrc_smooth - qfrc_c : 0.f;
         }
-        if (newton && phase >= 2 && phase < 99) {  // F0 (factor of M) is not needed any more once qacc_smooth exists
+        // ONE more call site of the factorisation serves the Newton Hessian of every iteration and the implicit-integration
+        // matrix M + dt D (phase 99).  The latter is factored only here, when it is needed: an up-front factor would sit in 19
+        // registers per lane through the whole solve.  F0 (factor of M) is dead once qacc_smooth exists (Newton) / once the
+        // solver has finished (phase 99).
+        const bool fac_newton = newton && phase >= 2 && phase < 99;
+        if (fac_newton || phase == 99) {
           float Hb[6], Hc[CHD];
-          newton_hessian(Hb, Hc);
-          factor(F0, Hb, Hc, 0.f);
+          float extra = 0.f;
+          if (fac_newton) newton_hessian(Hb, Hc);
+          else {
+#pragma unroll
+            for (int k = 0; k < CHD; k++) { Hb[k] = Bm[k]; Hc[k] = C[k]; }
+            extra = o.dt * damp;
+          }
+          factor(F0, Hb, Hc, extra);
         }
         const float rhs = phase == -1 ? qfrc_smooth : (phase == 99 ? qfrc_smooth + qfrc_c : grad);
         x = solve(rhs);
@@ -1222,7 +1233,6 @@ struct WarpEnv {
       done |= gradient < o.tolerance;
       if (__all_sync(ZB_FULL, done)) {
         if (!implicit_damp) { qa_int = qacc; finished = true; continue; }
-        F0 = F1;  // the factor of M is dead from here on
         phase = 99;
         continue;
       }

@@ -203,15 +203,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
     // ---- mjx.forward ----
     E.kinematics();
     E.mass_matrix();
-    {  // factor M and (for the implicit integrators) M + dt*diag(damping): one copy of the factorization code
-      const int nfac = (implicit_damp && stepping) ? 2 : 1;
-#pragma unroll 1
-      for (int p = 0; p < nfac; p++) {
-        Factor F;
-        E.factor(F, E.Bm, E.C, p ? dt * E.damp : 0.f);
-        if (p == 0) E.F0 = F; else E.F1 = F;
-      }
-    }
+    E.factor(E.F0, E.Bm, E.C, 0.f);  // (M + dt diag(damping) of the implicit integrators is factored inside solve_all, when needed)
     E.collision();
     float qfrc_passive;
     E.velocity(qfrc_passive);
