@@ -87,7 +87,7 @@ struct Factor {      // block LDL^T of M (or M + dt D); every entry is zero wher
 };
 
 struct LSPoint {
-  float alpha, d0, d1;  // step size, first and second derivative of the 1-D cost model
+  float alpha, d0;  // step size and first derivative of the 1-D cost model (the second derivative belongs to the active set: LSSet.d1)
 };
 struct LSSet {          // an active set of the line search: its summed quadratic and this lane's zone bits
   float t0, t1, t2;
@@ -889,7 +889,6 @@ struct WarpEnv {
     // the reference's bracket logic treats an exact zero as "not in bracket" (the point is rejected).  An FMA would
     // return the tiny residual instead and flip that decision in ~14 % of the states (tests/gpu_probe3.py).
     p.d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, a), S.t2), S.t1);
-    p.d1 = S.d1;
     return p;
   }
   static ZB_DI float ls_set_d1(float t2) { return __fadd_rn(__fmul_rn(2.f, t2), (t2 == 0.f ? MJ_MINVAL : 0.f)); }
@@ -968,12 +967,12 @@ struct WarpEnv {
       p0 = ls_make_point(0.f, S0);
     }
     const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * meaninertia * (float)NV);
-    al[0] = p0.alpha - p0.d0 / p0.d1;
+    al[0] = p0.alpha - p0.d0 / S0.d1;
     zz[0] = zone_at(r, al[0]);
     ls_eval<1>(r, al, zz, pt, st);  // lo = point(newton(p0)); order the bracket
     if (pt[0].d0 < p0.d0) { lo = pt[0]; Slo = st[0]; hi = p0; Shi = S0; } else { hi = pt[0]; Shi = st[0]; lo = p0; Slo = S0; }
     if (TRACE && trace && niter == 0 && L == 0) {
-      trace[32] = p0.alpha; trace[33] = p0.d0; trace[34] = p0.d1; trace[35] = pt[0].alpha; trace[36] = pt[0].d0; trace[37] = pt[0].d1;
+      trace[32] = p0.alpha; trace[33] = p0.d0; trace[34] = S0.d1; trace[35] = pt[0].alpha; trace[36] = pt[0].d0; trace[37] = st[0].d1;
       lscount = 2;
     }
     bool swap = true;
@@ -995,7 +994,7 @@ struct WarpEnv {
       const bool nz_lo = lo.d0 != 0.f, nz_hi = hi.d0 != 0.f;
       float n_lo = nz_lo ? lo.d0 : 1.f, n_hi = nz_hi ? hi.d0 : 1.f;
       asm volatile("" : "+f"(n_lo), "+f"(n_hi));
-      float q_lo = n_lo / lo.d1, q_hi = n_hi / hi.d1;
+      float q_lo = n_lo / Slo.d1, q_hi = n_hi / Shi.d1;
       q_lo = nz_lo ? q_lo : 0.f;
       q_hi = nz_hi ? q_hi : 0.f;
       al[0] = lo.alpha - q_lo;
@@ -1009,6 +1008,7 @@ struct WarpEnv {
         const LSPoint lo_next = ls_make_point(al[0], Slo), hi_next = ls_make_point(al[1], Shi);
         const LSPoint mid = f2l ? ls_make_point(al[2], Shi) : ls_make_point(al[2], Slo);
         pt[0] = lo_next; pt[1] = hi_next; pt[2] = mid;
+        if (TRACE) { st[0].d1 = Slo.d1; st[1].d1 = Shi.d1; st[2].d1 = f2l ? Shi.d1 : Slo.d1; }
         bool lo_hi = false, hi_lo = false;  // does the new lo (hi) take the OTHER end's active set?
         const LSPoint lo_old = lo, hi_old = hi;
         const bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
@@ -1036,7 +1036,7 @@ struct WarpEnv {
       if (TRACE && trace && niter == 0 && L == 0) {
         for (int j = 0; j < 3; j++)
           if (32 + 3 * lscount + 2 < ZB_NTRACE) {
-            trace[32 + 3 * lscount] = pt[j].alpha; trace[32 + 3 * lscount + 1] = pt[j].d0; trace[32 + 3 * lscount + 2] = pt[j].d1;
+            trace[32 + 3 * lscount] = pt[j].alpha; trace[32 + 3 * lscount + 1] = pt[j].d0; trace[32 + 3 * lscount + 2] = st[j].d1;
             lscount++;
           }
       }
