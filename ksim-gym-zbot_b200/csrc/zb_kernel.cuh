@@ -122,13 +122,15 @@ struct WarpEnv {
   Factor F0;  // factor of M; replaced by the Newton Hessian's / by the factor of M + dt D when those are needed (solve_all)
   float qfrc_smooth, qacc_smooth, act_force, qfrc_bias;
   // constraint rows
-  bool fr_on, lm_on, c_on, any_limit, fr_quad;
+  bool fr_on, lm_on, c_on, any_limit;
   float fr_D, fr_rf, fr_f, fr_aref, lm_sign, lm_D, lm_aref, c_D, c_aref, w[6];
   float cdist, cpos[3];
   // solver
   float qacc, Ma, grad, Mgrad, search, mv, qfrc_c;
-  float fr_ja, lm_ja, c_ja, fr_force, lm_force, c_force;
-  float Wf[6];  // total contact wrench of my half's foot (row lanes)
+  float fr_ja, lm_ja, c_ja;
+  float fr_force, lm_force, c_force;  // set by final_rows() only (after the solve of the last substep)
+  // (row forces and the per-foot contact wrench are NOT members: they are consumed right where a solver pass computes them and
+  //  recomputed from the final Jaref for the sensors / efc_force output — nine registers less through the line search)
   float gauss, cost, prev_cost;
   int niter;
   float* trace;  // optional global [ZB_NTRACE] solver trace (diagnostics), nullptr in production
@@ -552,14 +554,20 @@ struct WarpEnv {
     return dot6(w, Vf);
   }
 
-  // J^T f for the contact rows: per-box total wrench, projected on the dofs
-  ZB_DI float contact_jtf(float f) {
+  // total contact wrench of the foot box of my half-warp (row lanes): sum_r f_r w_r over its 16 rows
+  ZB_DI void contact_wrench(float f, float (&Wf)[6]) const {
 #pragma unroll
     for (int k = 0; k < 6; k++) {
       float t = c_on ? f * w[k] : 0.f;
       t += shx(t, 8); t += shx(t, 4); t += shx(t, 2); t += shx(t, 1);
       Wf[k] = t;
     }
+  }
+
+  // J^T f for the contact rows: per-box total wrench, projected on the dofs
+  ZB_DI float contact_jtf(float f) {
+    float Wf[6];
+    contact_wrench(f, Wf);
     float r = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -841,19 +849,27 @@ struct WarpEnv {
   //   phase 99 : implicit integration solve (M + dt D)^-1 (qfrc_smooth + qfrc_constraint)
   // ------------------------------------------------------------------------------------------
   // forces and cost of the rows at the current Jaref; returns this lane's partial constraint cost
-  ZB_DI float row_update() {
+  ZB_DI float row_update(float& fr_force, float& lm_force, float& c_force) const {
     float cst = 0.f;
-    fr_force = 0.f; lm_force = 0.f; c_force = 0.f; fr_quad = false;
+    fr_force = 0.f; lm_force = 0.f; c_force = 0.f;
     if (fr_on) {
       const float x = fr_ja;
       if (x <= -fr_rf && fr_f > 0.f) { fr_force = fr_f; cst += fr_f * (-0.5f * fr_rf - x); }
       else if (x >= fr_rf && fr_f > 0.f) { fr_force = -fr_f; cst += fr_f * (-0.5f * fr_rf + x); }
-      else { fr_force = -fr_D * x; cst += 0.5f * fr_D * x * x; fr_quad = true; }
+      else { fr_force = -fr_D * x; cst += 0.5f * fr_D * x * x; }
     }
     if (lm_on && lm_ja < 0.f) { lm_force = -lm_D * lm_ja; cst += 0.5f * lm_D * lm_ja * lm_ja; }
     if (c_on && c_ja < 0.f) { c_force = -c_D * c_ja; cst += 0.5f * c_D * c_ja * c_ja; }
     return cst;
   }
+  // efc_force of this lane's rows at the final Jaref (what the last solver pass computed), for the sensors and the export
+  ZB_DI void final_rows() {
+    float a, b, c;
+    row_update(a, b, c);
+    fr_force = a; lm_force = b; c_force = c;
+  }
+  // is the friction row of this lane on its quadratic piece (Newton Hessian)
+  ZB_DI bool fr_quadratic() const { return !(fr_f > 0.f && (fr_ja <= -fr_rf || fr_ja >= fr_rf)); }
   // MJX: (x < y && y < 0) || (x > y && y > 0)  <=>  y lies strictly between x and 0  <=>  (y - x) * y < 0.
   // (the sign of a rounded difference/product is exact; a product underflowing to 0 would need |d0| < 1e-19)
   static ZB_DI bool in_bracket(float x, float y) { return __fmul_rn(y - x, y) < 0.f; }
@@ -1128,7 +1144,7 @@ struct WarpEnv {
       for (int i = 0; i < 6; i++) f[i] = Mx[i][0] * cdof[0] + Mx[i][1] * cdof[1] + Mx[i][2] * cdof[2] + Mx[i][3] * cdof[3] + Mx[i][4] * cdof[4] + Mx[i][5] * cdof[5];
     }
     assemble_rows(f, Hb, Hc);
-    const float dg = (fr_on && fr_quad ? fr_D : 0.f) + (lm_on && lm_ja < 0.f ? lm_D : 0.f);
+    const float dg = (fr_on && fr_quadratic() ? fr_D : 0.f) + (lm_on && lm_ja < 0.f ? lm_D : 0.f);
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
       Hc[k] = hinge ? Hc[k] + C[k] + (k == gp ? dg : 0.f) : 0.f;
@@ -1144,9 +1160,6 @@ struct WarpEnv {
     float v = 0.f, cost_s = 0.f, qa_int = 0.f, pg = 0.f, pMg = 0.f;
     cost = 0.f; prev_cost = 0.f; niter = 0; lscount = 0;
     qacc = 0.f; Ma = 0.f; fr_ja = lm_ja = c_ja = 0.f; qfrc_c = 0.f; grad = 0.f; Mgrad = 0.f; search = 0.f; mv = 0.f; gauss = 0.f;
-    fr_force = lm_force = c_force = 0.f;
-#pragma unroll
-    for (int k = 0; k < 6; k++) Wf[k] = 0.f;
     // LOCK: the warps of a CTA meet at a barrier before every pass (solver iteration).  They then stream the same
     // instructions and share I-cache lines (instruction fetch was the top stall); a warp whose solve has finished keeps
     // arriving at the barrier until the slowest one is done (it would wait for it at the next substep barrier anyway).
@@ -1156,6 +1169,7 @@ struct WarpEnv {
       if (LOCK) { if (__syncthreads_and(finished)) break; }
       else if (finished) break;
       if (finished) continue;
+      float fr_force = 0.f, lm_force = 0.f, c_force = 0.f;  // row forces of THIS pass
       if (phase >= 0 && phase < 99) {
         // ---- operator application: mv = M v, contact rows J v ----
         float vb[6];
@@ -1171,7 +1185,7 @@ struct WarpEnv {
           c_ja = cjv - c_aref;
         }
         // ---- _update_constraint: forces, cost ----
-        const float part = row_update();
+        const float part = row_update(fr_force, lm_force, c_force);
         float p2[2] = {part, hasdof ? 0.5f * (Ma - qfrc_smooth) * (qacc - qacc_smooth) : 0.f};
         reduce_scatter<2>(p2, L);
         gauss = shf(p2[0], 16);
@@ -1272,6 +1286,8 @@ struct WarpEnv {
     inert_mul(t, cinert, cvel);
     motion_cross_force(u, cvel, t);
     const int mybox = isbody ? D->body_box[L] : -1;
+    float Wf[6];
+    contact_wrench(c_force, Wf);  // cfrc_ext of a foot = the solver's total contact wrench of its box
 #pragma unroll
     for (int k = 0; k < 6; k++) {
       const float ext = shf(Wf[k], mybox >= 0 ? 16 * mybox : 0);

@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
     const float qfrc_act = E.actuation();
     E.qfrc_smooth = E.hasdof ? qfrc_passive - E.qfrc_bias + qfrc_act : 0.f;
     const float qa = E.solve_all(implicit_damp && stepping);
+    if (last || extra) E.final_rows();
     if (last || extra) E.sensors(sd, (OBS && want_obs) ? imu_keep[OBS ? wib : 0] : nullptr);
     if (extra) E.warm = 0.f;
     if (stepping) {
