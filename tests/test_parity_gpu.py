@@ -614,7 +614,10 @@ def test_cta_shape_does_not_change_results(zmodel, monkeypatch):
     rq, rv = random_states(zmodel, n, 212, tilt=0.01)
     act = [torch.tensor(random_actions(n, 213 + t), device="cuda") for t in range(3)]
     res = []
-    for wpb in (None, "16", "5", "1"):  # automatic (1 warp per CTA at n = 37), 16 + 16 + 5 (11 spare warps), 7 x 5 + 2, 37 x 1
+    # automatic (1 warp per CTA at n = 37), 16 + 16 + 5 (11 spare warps), 7 x 5 + 2, 37 x 1, and 20 + 17 / 28 + 9 warps of the
+    # 72-register throughput profile (forced: a batch this small would never pick it) — the two register profiles are the same
+    # arithmetic, so their results must agree bit for bit as well
+    for wpb in (None, "16", "5", "1", "20", "28"):
         if wpb is None:
             monkeypatch.delenv("ZBPHYS_WPB", raising=False)
         else:
