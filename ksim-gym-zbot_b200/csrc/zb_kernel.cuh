@@ -97,7 +97,8 @@ struct LSSet {          // an active set of the line search: its summed quadrati
 
 // TRACE: compile the solver-trace diagnostics in (tests/gpu_probe*.py); the production instantiation carries none of it.
 // LOCK: CTA-lockstep barriers (see solve_all).
-template <bool TRACE, bool LOCK>
+// FSM: the factor and the mass-matrix rows of a lane live in shared memory (throughput profile) instead of registers.
+template <bool TRACE, bool LOCK, bool FSM>
 struct WarpEnv {
   const ZbDev* D;
   ZbOpts o;           // by value from the kernel parameters: uniform-datapath registers, provably warp-uniform control flow
@@ -118,8 +119,25 @@ struct WarpEnv {
   float cinert[10], cdof[6], cdofd[6], cvel[6];
   float sxpos[3], sxmat[9];
   // dynamics
-  float Bm[6], C[CHD];
-  Factor F0;  // factor of M; replaced by the Newton Hessian's / by the factor of M + dt D when those are needed (solve_all)
+  // Mass-matrix rows (Bm[6], C[6]) and the factor F0 (lc[6], lt[6], inv, W[6]) of this lane: 31 floats that are read once or
+  // twice per solver pass.  In the 128-register profile they sit in registers (fst).  In the 72-register profile ptxas spilled
+  // exactly these (17 local loads in front of every solve, profiles/r1_final_hotspots.txt) and the 666 KB of stack per SM
+  // thrash the L1; there they live in shared memory instead (fsm: lane column, element i at fsm[32 i], conflict-free).
+  // F0 = factor of M, replaced by the Newton Hessian's / by the factor of M + dt D when those are needed (solve_all).
+  enum { F_LC = 0, F_LT = 6, F_INV = 12, F_W = 13, F_BM = 19, F_C = 25, F_N = 31 };
+  float fst[FSM ? 1 : F_N];
+  float* fsm;
+  ZB_DI float fget(int i) const { return FSM ? fsm[32 * i] : fst[FSM ? 0 : i]; }
+  ZB_DI void fput(int i, float v) { if (FSM) fsm[32 * i] = v; else fst[FSM ? 0 : i] = v; }
+  ZB_DI void load_factor(Factor& F) const {
+#pragma unroll
+    for (int k = 0; k < CHD; k++) { F.lc[k] = fget(F_LC + k); F.lt[k] = fget(F_LT + k); F.W[k] = fget(F_W + k); }
+    F.inv = fget(F_INV);
+  }
+  ZB_DI void load_m(float (&Bm)[6], float (&C)[CHD]) const {
+#pragma unroll
+    for (int k = 0; k < CHD; k++) { Bm[k] = fget(F_BM + k); C[k] = fget(F_C + k); }
+  }
   float qfrc_smooth, qacc_smooth, act_force, qfrc_bias;
   // constraint rows
   bool fr_on, lm_on, c_on, any_limit;
@@ -380,13 +398,14 @@ struct WarpEnv {
     }
     float f[6];
     inert_mul(f, crb, cdof);
+    float Bm[6], C[CHD];
     assemble_rows(f, Bm, C);
     // armature on the diagonal
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
       // (select form on purpose: `if (k == gp) C[k] += ..` gets turned into a dynamic index -> local memory)
-      C[k] += (hinge && k == gp) ? arm : 0.f;
-      Bm[k] += (bdof && k == gp) ? arm : 0.f;
+      fput(F_C + k, C[k] + ((hinge && k == gp) ? arm : 0.f));
+      fput(F_BM + k, Bm[k] + ((bdof && k == gp) ? arm : 0.f));
     }
   }
 
@@ -412,7 +431,8 @@ struct WarpEnv {
   //   chains  C = Lt_c D_c Lt_c^T,  Wt = Lt_c^-1 B,  G = D_c^-1 Wt,  S = A - Wt^T G = Lt_s D_s Lt_s^T.
   // All stored coefficients are ZERO where they do not apply (other lanes, k >= gp, short chains), so the substitutions in
   // solve() are bare SHFL + FFMA steps without per-step predicates.
-  ZB_DI void factor(Factor& F, const float (&Bsrc)[6], const float (&Csrc)[CHD], float extra) {
+  ZB_DI void factor(const float (&Bsrc)[6], const float (&Csrc)[CHD], float extra) {
+    Factor F;
     float r[CHD];
 #pragma unroll
     for (int k = 0; k < CHD; k++) r[k] = hinge ? Csrc[k] + (k == gp ? extra : 0.f) : 0.f;
@@ -471,11 +491,21 @@ struct WarpEnv {
       F.lt[k] = (hasdof && k > gp && k < gn) ? t : 0.f;
     }
     __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CHD; k++) { fput(F_LC + k, F.lc[k]); fput(F_LT + k, F.lt[k]); fput(F_W + k, F.W[k]); }
+    fput(F_INV, F.inv);
+  }
+  // factor of M + diag(extra) from the stored mass-matrix rows
+  ZB_DI void factor_m(float extra) {
+    float Bm[6], C[CHD];
+    load_m(Bm, C);
+    factor(Bm, C, extra);
   }
 
   // smooth.solve_m: x <- (M + diag)^-1 x, x distributed over the dof lanes
   ZB_DI float solve(float x) {
-    const Factor& F = F0;  // solve_all re-factors F0 (Newton Hessian, M + dt D) when another matrix is to be solved
+    Factor F;  // solve_all re-factors F0 (Newton Hessian, M + dt D) when another matrix is to be solved
+    load_factor(F);
     if (!hasdof) x = 0.f;
     // chains: unit forward substitution  y_c = Lt_c^-1 r_c
 #pragma unroll
@@ -521,6 +551,8 @@ struct WarpEnv {
   // support.mul_m: y = M v; also returns the broadcast base part of v
   ZB_DI float mul_m(float v, float (&vb)[6]) {
     if (!hasdof) v = 0.f;
+    float Bm[6], C[CHD];
+    load_m(Bm, C);
 #pragma unroll
     for (int a = 0; a < 6; a++) vb[a] = shf(v, BL0 + a);
     float y = 0.f;
@@ -1147,8 +1179,8 @@ struct WarpEnv {
     const float dg = (fr_on && fr_quadratic() ? fr_D : 0.f) + (lm_on && lm_ja < 0.f ? lm_D : 0.f);
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
-      Hc[k] = hinge ? Hc[k] + C[k] + (k == gp ? dg : 0.f) : 0.f;
-      Hb[k] = Hb[k] + Bm[k] + ((bdof && k == gp) ? dg : 0.f);
+      Hc[k] = hinge ? Hc[k] + fget(F_C + k) + (k == gp ? dg : 0.f) : 0.f;
+      Hb[k] = Hb[k] + fget(F_BM + k) + ((bdof && k == gp) ? dg : 0.f);
     }
   }
 
@@ -1211,11 +1243,10 @@ struct WarpEnv {
           float extra = 0.f;
           if (fac_newton) newton_hessian(Hb, Hc);
           else {
-#pragma unroll
-            for (int k = 0; k < CHD; k++) { Hb[k] = Bm[k]; Hc[k] = C[k]; }
+            load_m(Hb, Hc);
             extra = o.dt * damp;
           }
-          factor(F0, Hb, Hc, extra);
+          factor(Hb, Hc, extra);
         }
         const float rhs = phase == -1 ? qfrc_smooth : (phase == 99 ? qfrc_smooth + qfrc_c : grad);
         x = solve(rhs);

@@ -15,7 +15,8 @@
 #include "../../include/zbphys.h"
 #include "zb_kernel.cuh"
 
-#define ZB_ABI_VERSION 2
+#define ZB_ABI_VERSION 3
+#define ZB_FSM_BYTES_PER_WARP (31 * 32 * 4) /* WarpEnv::F_N floats per lane */
 
 // auto-reset pass of the step kernel (zb_step_autoreset_f32)
 struct ZbAutoReset {
@@ -92,8 +93,12 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   }
   if (MODE == ZB_MODE_RESET && done && !done[env]) return;
   const ZbModel& m = D->m;
-  WarpEnv<TRACE, (ZB_CTA_LOCKSTEP >= 2) && MODE == ZB_MODE_STEP> E;
+  // throughput profile: factor + mass-matrix rows of every lane in (dynamic) shared memory, 31 x 128 B per warp
+  constexpr bool FSM = WPB > ZB_WPB;
+  extern __shared__ float dyn_smem[];
+  WarpEnv<TRACE, (ZB_CTA_LOCKSTEP >= 2) && MODE == ZB_MODE_STEP, FSM> E;
   E.init_topology(D, o, meaninertia, scratch[wib], L);
+  E.fsm = FSM ? dyn_smem + (size_t)wib * (32 * 31) + L : nullptr;
   const int b = E.isbody ? L : 0;
   const int d = E.hasdof ? E.dof : 0;
   // ---- per-environment model (randomizers, train.py:1439-1455) ----
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
     // ---- mjx.forward ----
     E.kinematics();
     E.mass_matrix();
-    E.factor(E.F0, E.Bm, E.C, 0.f);  // (M + dt diag(damping) of the implicit integrators is factored inside solve_all, when needed)
+    E.factor_m(0.f);  // (M + dt diag(damping) of the implicit integrators is factored inside solve_all, when needed)
     E.collision();
     float qfrc_passive;
     E.velocity(qfrc_passive);
@@ -529,6 +534,16 @@ int zb_engine_create(const ZbModel* model, const ZbOpts* opts, int device, ZbEng
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(device);
+  {  // the throughput-profile kernels keep 31 floats per lane in dynamic shared memory: 28 warps x 3968 B = 108.5 KB > the 48 KB default
+    const int bytes = ZB_WPB_WIDE * ZB_FSM_BYTES_PER_WARP;
+    cudaError_t a1 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, false, ZB_WPB_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t a2 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, true, ZB_WPB_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (a1 != cudaSuccess || a2 != cudaSuccess) {
+      cudaSetDevice(prev);
+      delete e;
+      return fail(ZB_ECUDA, "zb_engine_create: cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(a1 != cudaSuccess ? a1 : a2));
+    }
+  }
   cudaError_t ce = cudaMalloc(&e->dev, sizeof(ZbDev));
   if (ce == cudaSuccess) ce = cudaMemcpy(e->dev, &e->host, sizeof(ZbDev), cudaMemcpyHostToDevice);
   cudaSetDevice(prev);
@@ -588,7 +603,7 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x;
   const CtaShape cs = pick_shape(e, n_envs, !O.solver_trace);  // the diagnostics instantiation exists in the latency profile only
   const int wpb = cs.wpb, grid = (n_envs + wpb - 1) / wpb;
-#define ZB_LAUNCH_STEP(TR, OBSV, W) zb_kernel<ZB_MODE_STEP, TR, OBSV, W><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
+#define ZB_LAUNCH_STEP(TR, OBSV, W) zb_kernel<ZB_MODE_STEP, TR, OBSV, W><<<grid, wpb * 32, (W > ZB_WPB) ? (size_t)wpb * ZB_FSM_BYTES_PER_WARP : 0, (cudaStream_t)stream>>>( \
     e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR, OB)
   if (O.solver_trace) { if (with_obs) ZB_LAUNCH_STEP(true, true, ZB_WPB); else ZB_LAUNCH_STEP(true, false, ZB_WPB); }
   else if (cs.wide) { if (with_obs) ZB_LAUNCH_STEP(false, true, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); }
