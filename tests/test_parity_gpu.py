@@ -638,3 +638,37 @@ def test_cta_shape_does_not_change_results(zmodel, monkeypatch):
     for other in res[1:]:
         for k in ("qpos", "qvel", "qacc_warmstart", "xpos", "cinert", "sensordata", "efc_force", "contact_mask", "solver_niter", "done", "actor", "critic"):
             np.testing.assert_array_equal(res[0][k], other[k], err_msg=k)
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_option_combinations(zmodel, case):
+    """Seeded random COMBINATIONS of the engine options (solver x integrator x eulerdamp x warmstart x substep order x
+    iteration caps x dt x substeps x impratio x pushes x per-env randomisation): each single option has its own test above,
+    this guards the interactions (e.g. Newton + Euler without eulerdamp + pushes at dt = 0.002)."""
+    from ksim_gym_zbot_b200 import model as M
+
+    rg = np.random.default_rng(1000 + case)
+    S = int(rg.choice([1, 2, 4, 7]))
+    dt = float(rg.choice([0.001, 0.002, 0.005]))
+    kw = dict(solver=int(rg.choice([M.SOLVER_CG, M.SOLVER_NEWTON])), integrator=int(rg.choice([M.INT_EULER, M.INT_IMPLICITFAST])),
+              eulerdamp=int(rg.integers(0, 2)), warmstart=int(rg.integers(0, 2)), substep_order=int(rg.integers(0, 2)),
+              iterations=int(rg.choice([1, 3, 8, 30])), ls_iterations=int(rg.choice([2, 8, 20])), impratio=float(rg.choice([1.0, 2.0])))
+    n = 200 + int(rg.integers(0, 100))
+    params = _params(zmodel, n, 50 + case) if rg.integers(0, 2) else None
+    push = None
+    if rg.integers(0, 2):
+        push = {"t_rem": rg.uniform(0.0, 2 * S * dt, n).astype(np.float32),
+                "rand": [np.concatenate([rg.uniform(-0.3, 0.3, (n, 6)), rg.uniform(0.001, 0.01, (n, 1))], axis=1).astype(np.float32) for _ in range(2)]}
+    r = _run_both(zmodel, n, S, 400 + case, dt=dt, params=params, push=push, opts_kw=kw, n_ctrl=2)
+    c, b = r["cuda"], r["f64"]
+    tag = f"case {case}: S={S} dt={dt} {kw} params={params is not None} push={push is not None}"
+    assert np.isfinite(c["qpos"]).all() and c["flags"].sum() == 0, tag
+    # the loose end of the tolerance is the iteration-capped solver (see _assert_close); quantiles against the fp32 oracles
+    _assert_close(tag + " qpos", r, "qpos", 5e-5)
+    _assert_close(tag + " qvel", r, "qvel", 5e-4)
+    _assert_close(tag + " qacc", r, "qacc", 5e-3, floor=10.0)
+    _assert_close(tag + " sensordata", r, "sensordata", 5e-3, floor=10.0)
+    for k in ("act_pos", "act_vel", "act_torque", "push_t_rem", "time"):
+        _assert_close(tag + " " + k, r, k, 5e-5)
+    assert (c["contact_mask"] == b["contact_mask"]).mean() > 0.95, tag
+    assert np.abs(c["solver_niter"].astype(int) - b["solver_niter"].astype(int)).mean() < 1.5, tag
