@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-shards", type=int, default=0, help="environment blocks (streams) the end-to-end loop drives the batch in; "
                     "0 = pick the fastest of 1 / 2 / 4 in a short untimed calibration")
+    ap.add_argument("--e2e-blocking", action="store_true", help="end-to-end loop: wait for the WHOLE read-back before the next step "
+                    "(default: only for what the next action depends on; the trajectory arrays stream out double-buffered)")
     ap.add_argument("--obs", action="store_true", help="observation epilogue: the launch also writes the actor [50] / critic [484] input vectors "
                     "(train.py:1624-1681); only those + the reward inputs are written / read back instead of every mjx.Data array")
     ap.add_argument("--seed", type=int, default=0)
@@ -282,12 +284,15 @@ def main():
     # ---------------- timed region 2: end to end through the public API with HOST buffers ----------------
     # Every step: H2D of that step's actions from pinned memory -> engine.step (one launch incl. termination + reset) -> D2H of
     # everything the reference's observations, rewards and trajectory read back (train.py:452-461, 476, 681, 854, 882, 1307)
-    # + the done mask; the host waits for all of it before it issues the next step.  The batch is driven as `--e2e-shards`
-    # environment blocks on separate streams (the C ABI takes any [lo, hi) block), so one block's read-back overlaps the other
-    # block's kernel; each block's outputs are views into ONE device buffer, i.e. one D2H copy per block.
-    out_fields = ("qpos", "qvel", "xpos", "xquat", "cinert", "cvel", "qacc", "actuator_force", "sensordata")
+    # + the done mask.  The host waits, before it issues the next step, for what the next action can depend on (the new state,
+    # the sensors, the servo state, the done mask [+ the actor observation with --obs]: `gate_fields`); the arrays that only the
+    # trajectory / critic / rewards consume (`bulk_fields`) are written into one of two device buffers in turn and stream out on a
+    # copy stream while the next step computes (--e2e-blocking waits for them as well).  The batch can additionally be driven as
+    # several environment blocks on separate streams (the C ABI takes any [lo, hi) block); every group of arrays is ONE D2H copy.
+    gate_fields = ("qpos", "qvel", "sensordata")
+    bulk_fields = ("xpos", "xquat", "cinert", "cvel", "qacc", "actuator_force")
     if a.obs:
-        out_fields = ("qpos", "qvel", "xpos", "qacc", "actuator_force", "sensordata", "site_xpos")
+        bulk_fields = ("xpos", "qacc", "actuator_force", "site_xpos")
     from ksim_gym_zbot_b200.sharding import shard_range
 
     def build_shards(nsh):
@@ -300,33 +305,42 @@ def main():
             for f in ("position", "velocity", "last_computed_torque"):
                 getattr(sp.actuator_state, f).copy_(getattr(ps.actuator_state, f)[lo:hi])
             sp.event_states["push_t_rem"].copy_(ps.event_states["push_t_rem"][lo:hi])
-            sizes = {f: getattr(sp.data, f).numel() for f in out_fields}
-            sizes["act_torque"] = sp.actuator_state.last_computed_torque.numel()
             sob = None
             if a.obs:
                 sob = eng.new_observations(hi - lo)
                 sob.imu_x.copy_(obs.imu_x[lo:hi]); sob.imu_lag.copy_(obs.imu_lag[lo:hi])
-                sizes["actor_obs"], sizes["critic_obs"] = sob.actor_obs.numel(), sob.critic_obs.numel()
-            flat = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
-            off = 0
-            for f, nel in sizes.items():
-                cur = sp.actuator_state.last_computed_torque if f == "act_torque" else (getattr(sob, f) if f.endswith("_obs") else getattr(sp.data, f))
-                view = flat[off:off + nel].view(cur.shape)
-                view.copy_(cur)
+
+            def owner(f):  # (object, attribute) holding array f
                 if f == "act_torque":
-                    sp.actuator_state.last_computed_torque = view
-                elif f.endswith("_obs"):
-                    setattr(sob, f, view)
-                else:
-                    setattr(sp.data, f, view)
-                off += nel
-            shards.append(dict(lo=lo, hi=hi, ps=sp, flat=flat, h_flat=torch.empty_like(flat, device="cpu").pin_memory(),
+                    return sp.actuator_state, "last_computed_torque"
+                return (sob, f) if f.endswith("_obs") else (sp.data, f)
+
+            def pack(fields):  # one flat device buffer with a view per field (initialised from the current arrays)
+                sizes = {f: getattr(*owner(f)).numel() for f in fields}
+                flat = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
+                views, off = {}, 0
+                for f, nel in sizes.items():
+                    cur = getattr(*owner(f))
+                    views[f] = flat[off:off + nel].view(cur.shape)
+                    views[f].copy_(cur)
+                    off += nel
+                return flat, views
+
+            gate = gate_fields + ("act_torque",) + (("actor_obs",) if a.obs else ())
+            bulk = bulk_fields + (("critic_obs",) if a.obs else ())
+            g_flat, g_views = pack(gate)
+            for f, v in g_views.items():
+                setattr(*owner(f), v)
+            b_flat, b_views = zip(*[pack(bulk) for _ in range(2)])
+            shards.append(dict(lo=lo, hi=hi, ps=sp, owner=owner, g_flat=g_flat, h_gate=torch.empty_like(g_flat, device="cpu").pin_memory(),
+                               b_flat=b_flat, b_views=b_views, h_bulk=[torch.empty_like(b, device="cpu").pin_memory() for b in b_flat],
                                done=torch.zeros((hi - lo,), dtype=torch.uint8, device=dev),
                                h_done=torch.empty((hi - lo,), dtype=torch.uint8).pin_memory(),
                                d_act=torch.empty((hi - lo, M.NU), dtype=torch.float32, device=dev),
                                obs=sob, lag=None if obs_lag is None else obs_lag[lo:hi].contiguous(),
                                ep=None if ep is None else ep.slice(lo, hi), rq=rq[lo:hi].contiguous(), rv=rv[lo:hi].contiguous(),
-                               rt=rt[lo:hi].contiguous(), stream=torch.cuda.Stream(device=dev)))
+                               rt=rt[lo:hi].contiguous(), stream=torch.cuda.Stream(device=dev), copy_stream=torch.cuda.Stream(device=dev),
+                               ev_kernel=[torch.cuda.Event() for _ in range(2)], ev_copy=[torch.cuda.Event() for _ in range(2)]))
         return shards
 
     h_act = actions[W:W + K].cpu().pin_memory()
@@ -338,19 +352,36 @@ def main():
         e0.record()
         for sh in shards:
             sh["stream"].wait_stream(main)
+            sh["copy_stream"].wait_stream(main)
         for i in range(steps):
-            t = W + i
+            t, b = W + i, i & 1
             for sh in shards:
                 with torch.cuda.stream(sh["stream"]):
+                    if i >= 2:
+                        sh["stream"].wait_event(sh["ev_copy"][b])  # bulk buffer b has been read out
+                    for f, v in sh["b_views"][b].items():  # this step's trajectory arrays go to bulk buffer b
+                        setattr(*sh["owner"](f), v)
                     sh["d_act"].copy_(h_act[i, sh["lo"]:sh["hi"]], non_blocking=True)
                     eng.step(sh["d_act"], sh["ep"], sh["ps"], push_rand=None if pushes is None else pushes[t, sh["lo"]:sh["hi"]],
                              auto_reset=(sh["rq"], sh["rv"], sh["rt"]), done_out=sh["done"], obs=sh["obs"], reset_imu_lag=sh["lag"])
-                    sh["h_flat"].copy_(sh["flat"], non_blocking=True)
+                    sh["h_gate"].copy_(sh["g_flat"], non_blocking=True)
                     sh["h_done"].copy_(sh["done"], non_blocking=True)
+                    # recorded AFTER the gating copies: all D2H copies share one DMA queue, and the bulk copy must not get in front
+                    # of the small one the host is waiting for
+                    sh["ev_kernel"][b].record(sh["stream"])
+                    if a.e2e_blocking:
+                        sh["h_bulk"][b].copy_(sh["b_flat"][b], non_blocking=True)
+                        sh["ev_copy"][b].record(sh["stream"])
+                if not a.e2e_blocking:
+                    with torch.cuda.stream(sh["copy_stream"]):
+                        sh["copy_stream"].wait_event(sh["ev_kernel"][b])
+                        sh["h_bulk"][b].copy_(sh["b_flat"][b], non_blocking=True)
+                        sh["ev_copy"][b].record(sh["copy_stream"])
             for sh in shards:
-                sh["stream"].synchronize()  # the caller reads the result of step i before issuing step i+1
+                sh["stream"].synchronize()  # the caller has the gating result of step i before it issues step i+1
         for sh in shards:
             main.wait_stream(sh["stream"])
+            main.wait_stream(sh["copy_stream"])
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
@@ -372,7 +403,8 @@ def main():
         nsh = cands[0]
     shards = build_shards(nsh)
     h2d = h_act[0].numel() * 4
-    d2h = sum(sh["h_flat"].numel() * 4 + sh["h_done"].numel() for sh in shards)
+    d2h_gate = sum(sh["h_gate"].numel() * 4 + sh["h_done"].numel() for sh in shards)
+    d2h = d2h_gate + sum(sh["h_bulk"][0].numel() * 4 for sh in shards)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -439,7 +471,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "streams": nsh,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "d2h_gating_bytes_per_step": d2h if a.e2e_blocking else d2h_gate,
+                "readback": "blocking" if a.e2e_blocking else "gating arrays blocking, trajectory arrays double-buffered on a copy stream", "streams": nsh,
                 "streams_calibration_ms_per_step": calib or None},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         "stats": {"solver_niter_mean_last_step": niter_mean, "active_contacts_mean_last_step": ncon_mean, "resets_per_step": resets_per_step,
