@@ -332,14 +332,19 @@ def main():
             for f, v in g_views.items():
                 setattr(*owner(f), v)
             b_flat, b_views = zip(*[pack(bulk) for _ in range(2)])
-            shards.append(dict(lo=lo, hi=hi, ps=sp, owner=owner, g_flat=g_flat, h_gate=torch.empty_like(g_flat, device="cpu").pin_memory(),
+            done_k = torch.zeros((hi - lo,), dtype=torch.uint8, device=dev)
+            ep_k = None if ep is None else ep.slice(lo, hi)
+            rq_k, rv_k, rt_k = rq[lo:hi].contiguous(), rv[lo:hi].contiguous(), rt[lo:hi].contiguous()
+            lag_k = None if obs_lag is None else obs_lag[lo:hi].contiguous()
+            plans = []
+            for b in range(2):  # one pre-bound control step per bulk buffer (engine.plan_step: argument structs built once)
+                for f, v in b_views[b].items():
+                    setattr(*owner(f), v)
+                plans.append(eng.plan_step(sp, ep_k, auto_reset=(rq_k, rv_k, rt_k), done_out=done_k, obs=sob, reset_imu_lag=lag_k))
+            shards.append(dict(lo=lo, hi=hi, ps=sp, owner=owner, plans=plans, g_flat=g_flat, h_gate=torch.empty_like(g_flat, device="cpu").pin_memory(),
                                b_flat=b_flat, b_views=b_views, h_bulk=[torch.empty_like(b, device="cpu").pin_memory() for b in b_flat],
-                               done=torch.zeros((hi - lo,), dtype=torch.uint8, device=dev),
-                               h_done=torch.empty((hi - lo,), dtype=torch.uint8).pin_memory(),
-                               d_act=torch.empty((hi - lo, M.NU), dtype=torch.float32, device=dev),
-                               obs=sob, lag=None if obs_lag is None else obs_lag[lo:hi].contiguous(),
-                               ep=None if ep is None else ep.slice(lo, hi), rq=rq[lo:hi].contiguous(), rv=rv[lo:hi].contiguous(),
-                               rt=rt[lo:hi].contiguous(), stream=torch.cuda.Stream(device=dev), copy_stream=torch.cuda.Stream(device=dev),
+                               done=done_k, h_done=torch.empty((hi - lo,), dtype=torch.uint8).pin_memory(),
+                               d_act=torch.empty((hi - lo, M.NU), dtype=torch.float32, device=dev), stream=torch.cuda.Stream(device=dev), copy_stream=torch.cuda.Stream(device=dev),
                                ev_kernel=[torch.cuda.Event() for _ in range(2)], ev_copy=[torch.cuda.Event() for _ in range(2)]))
         return shards
 
@@ -359,11 +364,9 @@ def main():
                 with torch.cuda.stream(sh["stream"]):
                     if i >= 2:
                         sh["stream"].wait_event(sh["ev_copy"][b])  # bulk buffer b has been read out
-                    for f, v in sh["b_views"][b].items():  # this step's trajectory arrays go to bulk buffer b
-                        setattr(*sh["owner"](f), v)
                     sh["d_act"].copy_(h_act[i, sh["lo"]:sh["hi"]], non_blocking=True)
-                    eng.step(sh["d_act"], sh["ep"], sh["ps"], push_rand=None if pushes is None else pushes[t, sh["lo"]:sh["hi"]],
-                             auto_reset=(sh["rq"], sh["rv"], sh["rt"]), done_out=sh["done"], obs=sh["obs"], reset_imu_lag=sh["lag"])
+                    # this step's trajectory arrays go to bulk buffer b (plan b is bound to it)
+                    sh["plans"][b](sh["d_act"], None if pushes is None else pushes[t, sh["lo"]:sh["hi"]])
                     sh["h_gate"].copy_(sh["g_flat"], non_blocking=True)
                     sh["h_done"].copy_(sh["done"], non_blocking=True)
                     # recorded AFTER the gating copies: all D2H copies share one DMA queue, and the bulk copy must not get in front

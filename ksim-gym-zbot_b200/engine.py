@@ -491,6 +491,63 @@ class ZbotCudaEngine:
             ps.action_latency = torch.where(dn, lo_ + (hi_ - lo_) * torch.rand((n,), generator=self.gen, device=self.device), ps.action_latency)
         return ps
 
+    def plan_step(self, physics_state: PhysicsState, physics_model: EnvParams | None = None, n_substeps: int | None = None,
+                  auto_reset: tuple | None = None, done_out: torch.Tensor | None = None, z_lo: float = 0.05, z_hi: float = 0.5,
+                  max_tilt: float = math.radians(60), obs: Observations | None = None, command: torch.Tensor | None = None,
+                  reset_imu_lag: torch.Tensor | None = None, obs_noise: tuple | None = None, push_per_substep: bool = False):
+        """Pre-bind one control step: all argument structs of the C call are built once, the returned function
+        ``run(action, push_rand=None)`` only passes the two pointers that change per step and enqueues the launch on the
+        current stream (what an XLA custom call does with its operand buffers; ~10x less host time per step than ``step``).
+        The tensors bound here must stay alive and in place; action latency / drop-action are not handled by a plan."""
+        if self.drop_action_prob > 0 or self.action_latency_range[1] > 0:
+            raise ValueError("plan_step does not cover action latency / drop-action: use step()")
+        ps = physics_state
+        n = ps.data.qpos.shape[0]
+        S = self.phys_steps_per_ctrl_steps if n_substeps is None else int(n_substeps)
+        st, out = self._c_state(ps), self._c_out(ps)
+        params = physics_model.c_struct() if physics_model is not None else None
+        keep = [ps, physics_model, auto_reset, done_out, obs, command, reset_imu_lag, obs_noise, st, out, params]
+        p_params = ctypes.byref(params) if params is not None else None
+        p_st, p_out, h, lib, pps = ctypes.byref(st), ctypes.byref(out), self._h, self.lib, int(bool(push_per_substep))
+        ar = None
+        if auto_reset is not None:
+            rq, rv, rt = auto_reset
+            ar = ZbAutoResetArgs(rq.data_ptr(), rv.data_ptr(), None if rt is None else rt.data_ptr(),
+                                 None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt)
+            keep.append(ar)
+        if obs is not None:
+            if auto_reset is not None and reset_imu_lag is None:
+                reset_imu_lag = self.sample_imu_lag(n, obs.lag_range)
+                keep.append(reset_imu_lag)
+            nq, na = obs_noise if obs_noise is not None else (None, None)
+            ob = obs.c_struct(command, reset_imu_lag, nq, na)
+            keep.append(ob)
+            p_ob, p_ar = ctypes.byref(ob), (ctypes.byref(ar) if ar is not None else None)
+            fn = lib.zb_step_obs_f32
+
+            def call(stream, a_ptr, pr_ptr):
+                return fn(h, stream, p_params, p_st, a_ptr, pr_ptr, pps, p_out, p_ob, n, S, p_ar)
+        elif ar is not None:
+            fn = lib.zb_step_autoreset_f32
+
+            def call(stream, a_ptr, pr_ptr):
+                return fn(h, stream, p_params, p_st, a_ptr, pr_ptr, pps, p_out, n, S, ar.reset_qpos, ar.reset_qvel, ar.reset_t_rem, ar.done_out,
+                          z_lo, z_hi, max_tilt)
+        else:
+            fn = lib.zb_step_f32
+
+            def call(stream, a_ptr, pr_ptr):
+                return fn(h, stream, p_params, p_st, a_ptr, pr_ptr, pps, p_out, n, S)
+        dev, current_stream, check = self.device, torch.cuda.current_stream, self._check
+
+        def run(action: torch.Tensor, push_rand: torch.Tensor | None = None, _keep=keep):
+            rc = call(current_stream(dev).cuda_stream, action.data_ptr(), None if push_rand is None else push_rand.data_ptr())
+            if rc != ZB_OK:
+                check(rc)
+            ps.most_recent_action = action
+
+        return run
+
     def forward(self, physics_model: EnvParams | None, physics_state: PhysicsState) -> PhysicsState:
         """mjx.forward on the current state (ctrl = last computed actuator torque)."""
         ps = physics_state

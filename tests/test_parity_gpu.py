@@ -672,3 +672,40 @@ def test_option_combinations(zmodel, case):
         _assert_close(tag + " " + k, r, k, 5e-5)
     assert (c["contact_mask"] == b["contact_mask"]).mean() > 0.95, tag
     assert np.abs(c["solver_niter"].astype(int) - b["solver_niter"].astype(int)).mean() < 1.5, tag
+
+
+def test_plan_step_equals_step(zmodel):
+    """engine.plan_step (argument structs pre-bound, one C call per control step) is the same launch as engine.step."""
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import EnvParams, PushEventConfig
+
+    n = 300
+    q, v = random_states(zmodel, n, 71, tilt=0.5)
+    rq, rv = random_states(zmodel, n, 72, tilt=0.01)
+    res = []
+    for planned in (False, True):
+        eng = _engine(zmodel, n, opts=M.make_opts(dt=0.005), ctrl_dt=0.02, push=PushEventConfig())
+        ep = EnvParams(n, eng.device, **_params(zmodel, n, 9))
+        ps = eng.reset(ep, reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(v), reset_t_rem=torch.full((n,), 0.03))
+        obs = eng.new_observations(n)
+        obs.imu_lag.fill_(0.04)
+        done = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        ar = (torch.tensor(rq, device="cuda"), torch.tensor(rv, device="cuda"), torch.full((n,), 0.05, device="cuda"))
+        lag = torch.full((n,), 0.02, device="cuda")
+        g = np.random.default_rng(5)
+        run = eng.plan_step(ps, ep, auto_reset=ar, done_out=done, obs=obs, reset_imu_lag=lag) if planned else None
+        for t in range(5):
+            a = torch.tensor(random_actions(n, 500 + t), device="cuda")
+            pr = torch.tensor(np.concatenate([g.uniform(-0.2, 0.2, (n, 6)), g.uniform(0.01, 0.05, (n, 1))], axis=1).astype(np.float32), device="cuda")
+            if planned:
+                run(a, pr)
+            else:
+                eng.step(a, ep, ps, push_rand=pr, auto_reset=ar, done_out=done, obs=obs, reset_imu_lag=lag)
+        r = _to_np(ps)
+        r["actor"], r["critic"], r["done"] = obs.actor_obs.cpu().numpy(), obs.critic_obs.cpu().numpy(), done.cpu().numpy()
+        res.append(r)
+        eng.close()
+    for k in res[0]:
+        np.testing.assert_array_equal(res[0][k], res[1][k], err_msg=k)
+    with pytest.raises(ValueError):
+        _engine(zmodel, 4, opts=M.make_opts(dt=0.005), ctrl_dt=0.02, drop_action_prob=0.1).plan_step(None)
