@@ -453,7 +453,7 @@ def main():
     traffic = None  # DRAM bytes per launch of the step kernel from the committed ncu capture of THIS workload, if there is one
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(a.workload)
-        if tr and tr["envs"] == n_env and tr["substeps"] == S:
+        if tr and tr["envs"] == n_env and tr["substeps"] == S and not a.obs and a.solver == "cg":
             traffic = tr["bytes_per_launch"]
     except Exception:
         pass
