@@ -79,6 +79,17 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   __shared__ float scratch[WPB][32 * ZB_SCR];
   __shared__ float imu_keep[OBS ? WPB : 1][16];  // sensors() -> observe() hand-over of the IMU sensor values
   const int L = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#ifndef ZB_BAR_GROUPS
+#define ZB_BAR_GROUPS 2
+#endif
+  // lockstep groups: the warps of a CTA meet at substep boundaries in ZB_BAR_GROUPS groups (named barriers 1..G).  The
+  // lockstep exists for instruction-fetch sharing, but every barrier also waits for the slowest environment of its group; two
+  // groups measured +1 % over one (4096 and 16 384 envs), four no better (scripts/sweep_variants.sh).
+  const int nwarp = blockDim.x >> 5;
+  const int bar_g = (ZB_BAR_GROUPS > 1) ? (wib * ZB_BAR_GROUPS) / nwarp : 0;
+  const int bar_lo = (bar_g * nwarp + ZB_BAR_GROUPS - 1) / ZB_BAR_GROUPS, bar_hi = ((bar_g + 1) * nwarp + ZB_BAR_GROUPS - 1) / ZB_BAR_GROUPS;
+  const int bar_cnt = (bar_hi - bar_lo) * 32;
+#define ZB_LOCKSTEP_BARRIER() do { if (ZB_BAR_GROUPS > 1) asm volatile("bar.sync %0, %1;" ::"r"(bar_g + 1), "r"(bar_cnt) : "memory"); else __syncthreads(); } while (0)
   const int env = blockIdx.x * (blockDim.x >> 5) + wib;  // warps per CTA is a launch-time choice (<= ZB_WPB, see pick_wpb)
   // (vote: makes the flag provably warp-uniform for ptxas; a divergent-looking exit around barriers would wrap every
   //  later shuffle in WARPSYNC)
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
 #if ZB_CTA_LOCKSTEP
     // a spare warp of the last CTA only keeps the barrier count: one per substep + one for the auto-reset pass
     if (MODE == ZB_MODE_STEP)
-      for (int s = 0; s <= n_substeps; s++) __syncthreads();
+      for (int s = 0; s <= n_substeps; s++) ZB_LOCKSTEP_BARRIER();
 #endif
     return;
   }
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
     const bool last = s == nsub - 1;
     const bool extra = s == nsub;
 #if ZB_CTA_LOCKSTEP
-    if (MODE == ZB_MODE_STEP) __syncthreads();
+    if (MODE == ZB_MODE_STEP) ZB_LOCKSTEP_BARRIER();
 #endif
     if (extra) {
       if (!(MODE == ZB_MODE_STEP && AR.enabled)) break;
