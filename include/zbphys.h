@@ -40,6 +40,7 @@ extern "C" {
 #define ZB_NCOMMAND 7     /* commands["zero_command"], train.py:416-427       */
 #define ZB_NACTOR_OBS 50  /* NUM_ACTOR_INPUTS, train.py:31-38, 53             */
 #define ZB_NCRITIC_OBS 484 /* NUM_CRITIC_INPUTS, train.py:40-52, 54           */
+#define ZB_NREWARD_TERMS 6 /* see ZbObs.reward_terms                          */
 
 enum { ZB_SOLVER_CG = 0, ZB_SOLVER_NEWTON = 1 };
 enum { ZB_INT_EULER = 0, ZB_INT_IMPLICITFAST = 1 };
@@ -245,6 +246,18 @@ typedef struct ZbObs {
   const float* noise_imu_acc;  /* [N, 3]  NULL = none                                                     */
   float* actor_obs;            /* [N, ZB_NACTOR_OBS]                                                      */
   float* critic_obs;           /* [N, ZB_NCRITIC_OBS]                                                     */
+  /* Reward inputs (first part): per-step quantities of the reference's OWN reward / observation
+   * classes, raw (before ksim's scale / curriculum factors), as functions of this launch's mjx.Data:
+   *   feet_pos_obs [N, 6]  FeetPositionObservation, /root/reference/train.py:430-465 (in_robot_frame, floor_threshold 0):
+   *                        left_foot | right_foot site positions rotated by the inverse base quaternion qpos[3:7]
+   *   reward_terms [N, ZB_NREWARD_TERMS]:
+   *     [0] SimpleSingleFootContactReward (stand_still_threshold=None), train.py:691-713: xor(touch_l > 0.1, touch_r > 0.1)
+   *     [1] FeetOrientationReward(target_rp=(0,0), error_scale=0.25), train.py:647-689, on the bodies of the two foot sites
+   *     [2] FeetTooClosePenalty(threshold_m=0.12), train.py:729-748, on feet_pos_obs
+   *     [3] BaseHeightReward(error_scale=0.25, standard_height=0.27), train.py:468-483: exp(-|xpos[1].z - (cmd[4] + 0.27)| / 0.25)
+   *     [4], [5] left / right contact flags (touch > 0.1): what FeetAirtimeReward's scan consumes, train.py:524-525 */
+  float* feet_pos_obs;         /* [N, 6]                                                                  */
+  float* reward_terms;         /* [N, ZB_NREWARD_TERMS]                                                   */
 } ZbObs;
 
 /* Arguments of the auto-reset pass (see zb_step_autoreset_f32). */

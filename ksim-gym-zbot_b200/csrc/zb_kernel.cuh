@@ -1291,10 +1291,14 @@ struct WarpEnv {
   // ------------------------------------------------------------------------------------------
   // sensors + rne_postconstraint (A.11); only evaluated when outputs are written
   // ------------------------------------------------------------------------------------------
-  // keep: shared [10] (or nullptr) that receives framequat (4), accelerometer (3), gyro (3) for the observation epilogue —
+  // keep: shared [16] (or nullptr) that receives framequat (4), accelerometer (3), gyro (3), touch l / r (2) for the observation epilogue —
   // shared memory, not registers: the values would otherwise stay live across the substep loop and the solver
   ZB_DI void sensors(float* sd /* global [18] or nullptr */, float* keep) {
     if (!sd && !keep) return;
+    if (keep) {  // touch values default to 0 (a foot box without a touch site)
+      if (L == 0) { keep[10] = 0.f; keep[11] = 0.f; }
+      __syncwarp();
+    }
     const ZbModel& m = D->m;
     // cacc with qacc: base part uniform, chain part by prefix scan
     float ab[6];
@@ -1357,8 +1361,7 @@ struct WarpEnv {
         for (int k = 0; k < 3; k++) { sd[ZB_SENS_IMU_ACC + k] = simu[4 + k]; sd[ZB_SENS_IMU_GYRO + k] = simu[7 + k]; }
       }
     }
-    if (!sd) return;  // (the warp is converged here: sd and keep are warp-uniform)
-    if (s == 1 || s == 2) {  // foot force sensors
+    if (sd && (s == 1 || s == 2)) {  // foot force sensors
       float fo[3];
       matT_vec(fo, sxmat, cf + 3);
       const int o = s == 1 ? ZB_SENS_FORCE_L : ZB_SENS_FORCE_R;
@@ -1382,7 +1385,10 @@ struct WarpEnv {
         if (fabsf(loc[0]) <= m.site_size[ts][0] && fabsf(loc[1]) <= m.site_size[ts][1] && fabsf(loc[2]) <= m.site_size[ts][2]) val = c_force;
       }
       val += shx(val, 8); val += shx(val, 4); val += shx(val, 2); val += shx(val, 1);
-      if ((L & 15) == 0 && ts >= 0) sd[ts == 1 ? ZB_SENS_TOUCH_L : ZB_SENS_TOUCH_R] = val;
+      if ((L & 15) == 0 && ts >= 0) {
+        if (sd) sd[ts == 1 ? ZB_SENS_TOUCH_L : ZB_SENS_TOUCH_R] = val;
+        if (keep) keep[ts == 1 ? 10 : 11] = val;
+      }
     }
   }
 
@@ -1391,7 +1397,7 @@ struct WarpEnv {
   // ImuOrientationObservation.observe_stateful train.py:837-866 with rotate_quat_by_quat train.py:751-787.
   // reinit: this environment was (re)initialised by the launch -> carry restarts from (0, reset lag) (train.py:846-848).
   // ------------------------------------------------------------------------------------------
-  ZB_DI void observe(const ZbObs& OB, int env, bool reinit, const float* keep /* shared [10] written by sensors() */) {
+  ZB_DI void observe(const ZbObs& OB, int env, bool reinit, const float* keep /* shared [16] written by sensors() */) {
     __syncwarp();
     float sq[10];
 #pragma unroll
@@ -1466,6 +1472,57 @@ struct WarpEnv {
         float* t = c + 2 * NU + 417 + NU;
 #pragma unroll
         for (int k = 0; k < 7; k++) t[k] = bq[k];
+      }
+    }
+    // ---- reward inputs (ZbObs.feet_pos_obs / reward_terms): the reference's own per-step reward / observation code ----
+    if (OB.feet_pos_obs || OB.reward_terms) {
+      const ZbModel& m = D->m;
+      const int ll = m.site_body[1], lr = m.site_body[2];  // bodies of the left_foot / right_foot sites (train.py:1519-1520)
+      float fl[3], fr[3], ql[4], qr[4];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { fl[k] = shf(sxpos[k], ll); fr[k] = shf(sxpos[k], lr); }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { ql[k] = shf(xquat[k], ll); qr[k] = shf(xquat[k], lr); }
+      const float zb1 = shf(xpos[2], 1);  // xpos[1, 2]: height of the base body as forward() of the last substep left it
+      // FeetPositionObservation train.py:452-465: site positions rotated by the inverse of the base quaternion qpos[3:7]
+      // (xax.rotate_vector_by_quat(v, q, inverse=True) [R]: v' = R(q)^T v with the quaternion normalised first)
+      float qn[4] = {bq[3], bq[4], bq[5], bq[6]};
+      {
+        const float nq = sqrtf(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]) + 1e-6f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) qn[k] = qn[k] / nq;
+      }
+      float Rq[9], pl[3], pr[3];
+      quat_to_mat(Rq, qn);
+      matT_vec(pl, Rq, fl);
+      matT_vec(pr, Rq, fr);
+      if (OB.feet_pos_obs && L == 0) {
+        float* t = OB.feet_pos_obs + (size_t)env * 6;
+        t[0] = pl[0]; t[1] = pl[1]; t[2] = pl[2]; t[3] = pr[0]; t[4] = pr[1]; t[5] = pr[2];
+      }
+      if (OB.reward_terms && L == 0) {
+        const float tl = keep[10], tr = keep[11];
+        const bool cl = tl > 0.1f, cr = tr > 0.1f;  // train.py:699-703
+        // FeetOrientationReward train.py:680-689: |roll| + |pitch| of both foot bodies (xax.quat_to_euler [R])
+        float err = 0.f;
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          const float* qq = f ? qr : ql;
+          const float nq = sqrtf(qq[0] * qq[0] + qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3]) + 1e-6f;
+          const float w = qq[0] / nq, x = qq[1] / nq, y = qq[2] / nq, z = qq[3] / nq;
+          const float roll = atan2f(2.f * (w * x + y * z), 1.f - 2.f * (x * x + y * y));
+          const float sp = 2.f * (w * y - z * x);
+          const float pitch = fabsf(sp) >= 1.f ? copysignf(1.57079632679489662f, sp) : asinf(sp);
+          err += fabsf(roll) + fabsf(pitch);
+        }
+        const float dx = pl[0] - pr[0], dy = pl[1] - pr[1], dz = pl[2] - pr[2];
+        float* t = OB.reward_terms + (size_t)env * ZB_NREWARD_TERMS;
+        t[0] = (cl != cr) ? 1.f : 0.f;
+        t[1] = expf(-err / 0.25f);
+        t[2] = sqrtf(dx * dx + dy * dy + dz * dz) < 0.12f ? 1.f : 0.f;                 // train.py:741-748
+        t[3] = expf(-fabsf(zb1 - (cmd[4] + 0.27f)) / 0.25f);                              // train.py:476-483
+        t[4] = cl ? 1.f : 0.f;
+        t[5] = cr ? 1.f : 0.f;
       }
     }
   }

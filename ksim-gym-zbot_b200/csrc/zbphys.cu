@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   const int nsub = MODE == ZB_MODE_STEP ? n_substeps : 1;
   float* sd = O.sensordata ? O.sensordata + (size_t)env * ZB_NSENSORDATA : nullptr;
   E.trace = (TRACE && O.solver_trace) ? O.solver_trace + (size_t)env * ZB_NTRACE : nullptr;
-  const bool want_obs = OBS && MODE != ZB_MODE_FORWARD && (OB.actor_obs || OB.critic_obs || OB.imu_x);
+  const bool want_obs = OBS && MODE != ZB_MODE_FORWARD && (OB.actor_obs || OB.critic_obs || OB.imu_x || OB.feet_pos_obs || OB.reward_terms);
   bool reinit = MODE == ZB_MODE_RESET;  // observation carry restarts for environments this launch (re)initialises
 
   // s == nsub is the optional auto-reset pass (zb_step_autoreset_f32): terminate -> reset state -> forward(), i.e.
@@ -611,7 +611,7 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   ZbObs OB; memset(&OB, 0, sizeof(OB)); if (obs) OB = *obs;
-  const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x;
+  const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x || OB.feet_pos_obs || OB.reward_terms;
   const CtaShape cs = pick_shape(e, n_envs, !O.solver_trace);  // the diagnostics instantiation exists in the latency profile only
   const int wpb = cs.wpb, grid = (n_envs + wpb - 1) / wpb;
 #define ZB_LAUNCH_STEP(TR, OBSV, W) zb_kernel<ZB_MODE_STEP, TR, OBSV, W><<<grid, wpb * 32, (W > ZB_WPB) ? (size_t)wpb * ZB_FSM_BYTES_PER_WARP : 0, (cudaStream_t)stream>>>( \
@@ -677,7 +677,7 @@ static int reset_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, cons
   const int wpb = pick_shape(e, n_envs, false).wpb, grid = (n_envs + wpb - 1) / wpb;
 #define ZB_LAUNCH_RESET(TR, OBSV) zb_kernel<ZB_MODE_RESET, TR, OBSV, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
     e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done, reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{}, OB)
-  const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x;
+  const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x || OB.feet_pos_obs || OB.reward_terms;
   if (O.solver_trace) { if (with_obs) ZB_LAUNCH_RESET(true, true); else ZB_LAUNCH_RESET(true, false); }
   else { if (with_obs) ZB_LAUNCH_RESET(false, true); else ZB_LAUNCH_RESET(false, false); }
 #undef ZB_LAUNCH_RESET

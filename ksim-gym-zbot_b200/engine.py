@@ -54,7 +54,9 @@ def _ptr_struct(name, names):
 ZbEnvParams = _ptr_struct("ZbEnvParams", _PARAM_FIELDS)
 ZbState = _ptr_struct("ZbState", _STATE_FIELDS)
 ZbOut = _ptr_struct("ZbOut", _OUT_F32 + _OUT_I32 + ["solver_trace"])
-_OBS_FIELDS = ["command", "imu_x", "imu_lag", "reset_imu_lag", "noise_imu_quat", "noise_imu_acc", "actor_obs", "critic_obs"]
+_OBS_FIELDS = ["command", "imu_x", "imu_lag", "reset_imu_lag", "noise_imu_quat", "noise_imu_acc", "actor_obs", "critic_obs", "feet_pos_obs",
+               "reward_terms"]
+NUM_REWARD_TERMS = 6  # ZB_NREWARD_TERMS
 ZbObs = _ptr_struct("ZbObs", _OBS_FIELDS)
 NUM_ACTOR_INPUTS, NUM_CRITIC_INPUTS, NUM_COMMANDS = 50, 484, 7  # train.py:53-54, 416-427
 
@@ -174,12 +176,16 @@ class Observations:
     actor_obs: torch.Tensor
     critic_obs: torch.Tensor | None
     lag_range: tuple[float, float] = (0.0, 0.1)  # train.py:1497
+    # reward inputs (ZbObs.feet_pos_obs / reward_terms): FeetPositionObservation train.py:430-465 and the per-step values of
+    # SimpleSingleFootContactReward, FeetOrientationReward, FeetTooClosePenalty, BaseHeightReward + the two contact flags
+    feet_pos_obs: torch.Tensor | None = None
+    reward_terms: torch.Tensor | None = None
 
     def c_struct(self, command=None, reset_imu_lag=None, noise_imu_quat=None, noise_imu_acc=None) -> ZbObs:
         s = ZbObs()
         for k, t in (("command", command), ("imu_x", self.imu_x), ("imu_lag", self.imu_lag), ("reset_imu_lag", reset_imu_lag),
                      ("noise_imu_quat", noise_imu_quat), ("noise_imu_acc", noise_imu_acc), ("actor_obs", self.actor_obs),
-                     ("critic_obs", self.critic_obs)):
+                     ("critic_obs", self.critic_obs), ("feet_pos_obs", self.feet_pos_obs), ("reward_terms", self.reward_terms)):
             if t is not None:
                 assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), k
                 setattr(s, k, t.data_ptr())
@@ -306,12 +312,14 @@ class ZbotCudaEngine:
             actuator_state=PlannerState(z((M.NU,)), z((M.NU,)), z((M.NU,))), action_latency=z(()),
         )
 
-    def new_observations(self, n: int | None = None, critic: bool = True, lag_range: tuple[float, float] = (0.0, 0.1)) -> Observations:
+    def new_observations(self, n: int | None = None, critic: bool = True, lag_range: tuple[float, float] = (0.0, 0.1),
+                         rewards: bool = False) -> Observations:
         """Buffers + carry of the observation epilogue (ImuOrientationObservation.initial_carry, train.py:846-848)."""
         n = self.n_envs if n is None else n
         z = lambda *shape: torch.zeros((n,) + shape, dtype=torch.float32, device=self.device)  # noqa: E731
         return Observations(imu_x=z(4), imu_lag=self.sample_imu_lag(n, lag_range), actor_obs=z(NUM_ACTOR_INPUTS),
-                            critic_obs=z(NUM_CRITIC_INPUTS) if critic else None, lag_range=tuple(lag_range))
+                            critic_obs=z(NUM_CRITIC_INPUTS) if critic else None, lag_range=tuple(lag_range),
+                            feet_pos_obs=z(6) if rewards else None, reward_terms=z(NUM_REWARD_TERMS) if rewards else None)
 
     def sample_imu_lag(self, n: int, lag_range: tuple[float, float]) -> torch.Tensor:
         lo, hi = lag_range

@@ -1446,6 +1446,63 @@ int SUF(zbo_observe)(int n_envs, const real* qpos, const real* qvel, const real*
   return 0;
 }
 
+/* Reward inputs (include/zbphys.h ZbObs.feet_pos_obs / reward_terms).  [V] FeetPositionObservation train.py:430-465,
+ * SimpleSingleFootContactReward train.py:691-713 (stand_still_threshold=None, train.py:1559), FeetOrientationReward
+ * train.py:647-689, FeetTooClosePenalty train.py:729-748, BaseHeightReward train.py:468-483, contact flags of
+ * FeetAirtimeReward train.py:524-525; [R] xax.quat_to_euler (roll = atan2(2(wx+yz), 1-2(x^2+y^2)), pitch = asin(2(wy-zx))
+ * clamped to +-pi/2) and xax.rotate_vector_by_quat(v, q, inverse=True) = R(q/|q|)^T v.
+ * left_body / right_body: body ids of the left_foot / right_foot sites. */
+int SUF(zbo_reward_inputs)(int n_envs, const real* qpos, const real* xpos, const real* xquat, const real* site_xpos, const real* sensordata,
+                           const real* command, int left_body, int right_body, real* feet_pos_obs, real* reward_terms) {
+  if (n_envs < 0 || !qpos || !xpos || !xquat || !site_xpos || !sensordata) return ZB_EINVAL;
+  const real eps = (real)1e-6;
+  for (int i = 0; i < n_envs; i++) {
+    const real* q = qpos + (size_t)i * NQ;
+    real bq[4];
+    real nq = R_SQRT(q[3] * q[3] + q[4] * q[4] + q[5] * q[5] + q[6] * q[6]) + eps;
+    for (int k = 0; k < 4; k++) bq[k] = q[3 + k] / nq;
+    real R[9], feet[6];
+    quat_to_mat(R, bq);
+    for (int f = 0; f < 2; f++) matT_vec(feet + 3 * f, R, site_xpos + ((size_t)i * NS + 1 + f) * 3);
+    if (feet_pos_obs) memcpy(feet_pos_obs + (size_t)i * 6, feet, sizeof(feet));
+    if (reward_terms) {
+      const real* sd = sensordata + (size_t)i * ZB_NSENSORDATA;
+      const int cl = sd[ZB_SENS_TOUCH_L] > (real)0.1, cr = sd[ZB_SENS_TOUCH_R] > (real)0.1;
+      real err = 0;
+      const int bodies[2] = {left_body, right_body};
+      for (int f = 0; f < 2; f++) {
+        const real* qq = xquat + ((size_t)i * NB + bodies[f]) * 4;
+        real n2 = R_SQRT(qq[0] * qq[0] + qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3]) + eps;
+        real w = qq[0] / n2, x = qq[1] / n2, y = qq[2] / n2, z = qq[3] / n2;
+#if ZBO_F64
+        real roll = atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y));
+        real sp = 2 * (w * y - z * x);
+        real pitch = fabs(sp) >= 1 ? copysign(1.57079632679489662, sp) : asin(sp);
+#else
+        real roll = atan2f(2 * (w * x + y * z), 1 - 2 * (x * x + y * y));
+        real sp = 2 * (w * y - z * x);
+        real pitch = fabsf(sp) >= 1 ? copysignf(1.57079632679489662f, sp) : asinf(sp);
+#endif
+        err += R_ABS(roll) + R_ABS(pitch);
+      }
+      real d[3] = {feet[0] - feet[3], feet[1] - feet[4], feet[2] - feet[5]};
+      real* t = reward_terms + (size_t)i * ZB_NREWARD_TERMS;
+      real c4 = command ? command[(size_t)i * ZB_NCOMMAND + 4] : 0;
+#if ZBO_F64
+      t[1] = exp(-err / 0.25);
+      t[3] = exp(-fabs(xpos[((size_t)i * NB + 1) * 3 + 2] - (c4 + 0.27)) / 0.25);
+#else
+      t[1] = expf(-err / 0.25f);
+      t[3] = expf(-fabsf(xpos[((size_t)i * NB + 1) * 3 + 2] - (c4 + 0.27f)) / 0.25f);
+#endif
+      t[0] = (cl != cr) ? 1 : 0;
+      t[2] = R_SQRT(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) < (real)0.12 ? 1 : 0;
+      t[4] = cl; t[5] = cr;
+    }
+  }
+  return 0;
+}
+
 int SUF(zbo_sizeof_data)(void) { return (int)sizeof(ZboData); }
 
 void SUF(zbo_set_variant)(int v) { g_variant = v; }

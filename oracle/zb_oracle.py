@@ -252,6 +252,18 @@ class Oracle:
         assert rc == 0, rc
         return actor, crit
 
+    def reward_inputs(self, state, out, command=None):
+        """ZbObs.feet_pos_obs [n,6] / reward_terms [n,6] from the arrays a step / reset produced."""
+        n = state["qpos"].shape[0]
+        feet, terms = np.zeros((n, 6), dtype=self.dtype), np.zeros((n, 6), dtype=self.dtype)
+        cmd = self._arr(command)
+        P = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        rc = getattr(self.lib, "zbo_reward_inputs" + self.suf)(
+            n, P(state["qpos"]), P(out["xpos"]), P(out["xquat"]), P(out["site_xpos"]), P(out["sensordata"]), P(cmd),
+            int(self.model.site_body[1]), int(self.model.site_body[2]), P(feet), P(terms))
+        assert rc == 0, rc
+        return feet, terms
+
     def set_variant(self, v: int) -> None:
         """bit 0: contact rows applied matrix-free like the CUDA kernel (diagnostics)."""
         getattr(self.lib, "zbo_set_variant" + self.suf)(int(v))

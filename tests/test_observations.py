@@ -198,3 +198,117 @@ def test_observation_argument_checks(zmodel):
     eng.step(act, None, ps, obs=obs2)
     torch.cuda.synchronize()
     assert torch.isfinite(obs2.actor_obs).all() and float(obs2.actor_obs[:, 40:44].norm(dim=1).min()) > 0.5
+
+
+# ---- reward inputs: transcription of the reference's reward / observation classes ---------------------------------------
+def quat_to_euler(q):  # xax.quat_to_euler [R]
+    q = q / (np.linalg.norm(q, axis=-1, keepdims=True) + q.dtype.type(1e-6))
+    w, x, y, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    roll = np.arctan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
+    sp = 2 * (w * y - z * x)
+    pitch = np.where(np.abs(sp) >= 1, np.sign(sp) * np.pi / 2, np.arcsin(np.clip(sp, -1, 1)))
+    yaw = np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+    return np.stack([roll, pitch, yaw], axis=-1)
+
+
+def rotate_vector_by_quat_inverse(v, q):  # xax.rotate_vector_by_quat(v, q, inverse=True) [R]: q^-1 v q
+    q = q / (np.linalg.norm(q, axis=-1, keepdims=True) + q.dtype.type(1e-6))
+    w, u = q[..., 0:1], -q[..., 1:]
+    t = 2 * np.cross(u, v)
+    return v + w * t + np.cross(u, t)
+
+
+def reference_reward_inputs(qpos, xpos, xquat, site_xpos, sensordata, command, left_body, right_body):
+    # FeetPositionObservation.observe, train.py:452-465 (floor_threshold = 0, in_robot_frame)
+    fl = rotate_vector_by_quat_inverse(site_xpos[:, 1], qpos[:, 3:7])
+    fr = rotate_vector_by_quat_inverse(site_xpos[:, 2], qpos[:, 3:7])
+    feet = np.concatenate([fl, fr], axis=-1)
+    # SimpleSingleFootContactReward.get_reward, train.py:698-711 with stand_still_threshold=None (train.py:1559)
+    lc, rc = sensordata[:, 10] > 0.1, sensordata[:, 11] > 0.1
+    single = np.logical_xor(lc, rc)
+    # FeetOrientationReward.get_reward, train.py:680-689
+    err = np.abs(quat_to_euler(xquat[:, left_body])[:, :2]).sum(-1) + np.abs(quat_to_euler(xquat[:, right_body])[:, :2]).sum(-1)
+    orient = np.exp(-err / 0.25)
+    # FeetTooClosePenalty.get_reward, train.py:740-748
+    close = np.linalg.norm(feet[:, :3] - feet[:, 3:], axis=-1) < 0.12
+    # BaseHeightReward.get_reward, train.py:476-483
+    height = np.exp(-np.abs(xpos[:, 1, 2] - (command[:, 4] + 0.27)) / 0.25)
+    terms = np.stack([single, orient, close, height, lc, rc], axis=-1).astype(qpos.dtype)
+    return feet, terms
+
+
+# (tolerance 6e-6 also in fp64 — the test quaternions have norms down to 0.5: the reference normalises quaternions as q / (|q| + 1e-6); rotating with the rotation matrix of that
+#  slightly-short quaternion or with the quaternion-product formula differs at that 1e-6 level — the exact xax formula is [R])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 6e-6), (np.float32, 8e-6)])
+def test_oracle_reward_inputs_match_reference_transcription(zmodel, dtype, tol):
+    import zb_oracle
+    from ksim_gym_zbot_b200 import model as M
+
+    n = 400
+    r = np.random.default_rng(17)
+    orc = zb_oracle.Oracle(zmodel, M.make_opts(), dtype)
+    q = r.normal(size=(n, 27))
+    q[:, 3:7] = r.normal(size=(n, 4)) * r.uniform(0.5, 1.5, (n, 1))
+    xq = r.normal(size=(n, NB, 4))
+    xq /= np.linalg.norm(xq, axis=-1, keepdims=True)
+    sx = r.normal(size=(n, 3, 3)) * 0.1
+    sx[: n // 2, 2] = sx[: n // 2, 1] + r.normal(size=(n // 2, 3)) * 0.06  # feet around the 0.12 m threshold
+    sd = r.normal(size=(n, 18))
+    sd[:, 10:12] = r.choice([0.0, 0.05, 0.2, 3.0], size=(n, 2))
+    f = dict(qpos=q, xpos=r.normal(size=(n, NB, 3)) * 0.3, xquat=xq, site_xpos=sx, sensordata=sd, command=r.uniform(-0.2, 0.2, (n, 7)))
+    f = {k: v.astype(dtype) for k, v in f.items()}
+    lb, rb = int(zmodel.site_body[1]), int(zmodel.site_body[2])
+    feet_ref, terms_ref = reference_reward_inputs(f["qpos"], f["xpos"], f["xquat"], f["site_xpos"], f["sensordata"], f["command"], lb, rb)
+    feet, terms = orc.reward_inputs({"qpos": f["qpos"]}, f, command=f["command"])
+    np.testing.assert_allclose(feet, feet_ref, rtol=0, atol=tol)
+    edge = np.abs(np.linalg.norm(feet_ref[:, :3] - feet_ref[:, 3:], axis=-1) - 0.12) < 1e-5  # threshold ties may flip at rounding
+    np.testing.assert_allclose(terms[~edge], terms_ref[~edge], rtol=0, atol=tol)
+    assert 0.2 < terms[:, 0].mean() < 0.8 and 0.05 < terms[:, 2].mean() < 0.95  # both branches exercised
+
+
+@pytest.mark.gpu
+def test_reward_inputs_epilogue_matches_oracle(zmodel):
+    import os
+
+    import torch
+    import zb_oracle
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import ZbotCudaEngine
+
+    n = 300
+    opts = M.make_opts(dt=0.005)
+    eng = ZbotCudaEngine(zmodel, n, device=0, opts=opts, ctrl_dt=0.02)
+    orc = zb_oracle.Oracle(zmodel, opts, np.float32, threads=os.cpu_count() or 1)
+    q, v = random_states(zmodel, n, 31, tilt=0.3)
+    r = np.random.default_rng(4)
+    cmd = r.uniform(-0.1, 0.1, (n, 7)).astype(np.float32)
+    T = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device=eng.device)  # noqa: E731
+    obs = eng.new_observations(n, rewards=True)
+    ps = eng.reset(reset_qpos=T(q), reset_qvel=T(v), reset_t_rem=torch.full((n,), 1e9), obs=obs, command=T(cmd))
+
+    def check(tag):
+        torch.cuda.synchronize()
+        st = {"qpos": ps.data.qpos.cpu().numpy()}
+        out = {k: getattr(ps.data, k).cpu().numpy() for k in ("xpos", "xquat", "site_xpos", "sensordata")}
+        feet, terms = orc.reward_inputs(st, out, command=cmd)
+        np.testing.assert_allclose(obs.feet_pos_obs.cpu().numpy(), feet, rtol=0, atol=2e-6, err_msg=tag)
+        got = obs.reward_terms.cpu().numpy()
+        edge = (np.abs(np.linalg.norm(feet[:, :3] - feet[:, 3:], axis=-1) - 0.12) < 1e-5) | (np.abs(out["sensordata"][:, 10:12] - 0.1) < 1e-6).any(axis=1)
+        np.testing.assert_allclose(got[~edge], terms[~edge], rtol=0, atol=5e-6, err_msg=tag)
+        return got
+
+    got = check("reset")
+    seen = [got]
+    for t in range(6):
+        eng.step(T(random_actions(n, 80 + t)), None, ps, obs=obs, command=T(cmd))
+        seen.append(check(f"step {t}"))
+    allv = np.concatenate(seen)
+    assert 0 < allv[:, 0].mean() < 1 and allv[:, 4].mean() > 0.1 and (allv[:, 1] < 0.99).any()  # contacts and tilted feet occur
+    # reward inputs alone (no network vectors, no filter carry) are a valid request
+    from ksim_gym_zbot_b200.engine import Observations
+
+    only = Observations(imu_x=None, imu_lag=None, actor_obs=None, critic_obs=None, feet_pos_obs=torch.zeros((n, 6), device=eng.device),
+                        reward_terms=torch.zeros((n, 6), device=eng.device))
+    eng.step(T(random_actions(n, 99)), None, ps, obs=only, command=T(cmd))
+    torch.cuda.synchronize()
+    assert torch.isfinite(only.reward_terms).all() and float(only.feet_pos_obs.abs().max()) > 0
