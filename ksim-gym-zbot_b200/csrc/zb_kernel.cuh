@@ -1254,7 +1254,7 @@ struct WarpEnv {
       // ---- transitions ----
       if (phase == -1) { qacc_smooth = x; v = x; phase = o.warmstart ? 0 : 2; continue; }
       if (phase == 0) { cost_s = cost; v = warm; phase = 1; continue; }
-      if (phase == 1) { v = __all_sync(ZB_FULL, cost < cost_s) ? warm : qacc_smooth; phase = 2; continue; }
+      if (phase == 1) { v = __all_sync(ZB_FULL, cost < cost_s) ? warm : qacc_smooth; warm = 0.f; /* dead from here on: frees its register for the iterations */ phase = 2; continue; }
       if (phase == 99) { qa_int = x; finished = true; continue; }
       Mgrad = x;
       float gnorm2;
