@@ -334,6 +334,20 @@ long long zb_launch_count(void);
 int zb_terminations_f32(void* cuda_stream, const float* qpos, const int32_t* flags, uint8_t* done, int n_envs, float z_lo,
                         float z_hi, float max_tilt_rad);
 
+/* FeetAirtimeReward.get_reward_stateful over one rollout chunk (/root/reference/train.py:503-546), raw
+ * (before ksim's `scale`), with stand_still_threshold = None as the task configures it (train.py:1560-1565):
+ *   airtime scan   t <- (contact | done) ? 0 : t + ctrl_dt, per foot, starting from carry[i] (train.py:503-516)
+ *   touchdown      contact[t] & !contact[t-1], with contact[-1] := false at the start of the chunk (train.py:528-533)
+ *   reward[t]      sum over the feet of (airtime[t-1] - touchdown_penalty) * touchdown[t], where airtime[-1] is airtime[T-1] of
+ *                  the SAME chunk (the reference shifts with jnp.roll, train.py:535-536 — kept as it is)
+ * left_contact / right_contact / done / reward are [T, N]-shaped views given by strides in elements (element (t, i) at
+ * t * time_stride + i * env_stride), contacts as floats (> 0.5 = contact, e.g. ZbObs.reward_terms[:, 4] / [:, 5] stacked over
+ * the rollout), done as uint8.  carry [N, 2] (left, right) is updated in place.  One thread per environment. */
+int zb_feet_airtime_f32(void* cuda_stream, const float* left_contact, const float* right_contact, long long contact_time_stride,
+                        long long contact_env_stride, const uint8_t* done, long long done_time_stride, long long done_env_stride,
+                        float* carry, float* reward, long long reward_time_stride, long long reward_env_stride, int n_envs,
+                        int n_steps, float ctrl_dt, float touchdown_penalty);
+
 /* FP32 FFMA throughput probe (bench.py: the FP32 roofline denominator).  Enqueues grid x 256 threads doing
  * iters x 16 independent FMAs each; scratch needs grid * 256 floats.  flops = grid * 256 * iters * 32. */
 int zb_bench_ffma(void* cuda_stream, float* scratch, int grid, int iters);

@@ -346,6 +346,28 @@ __global__ void zb_term_kernel(const float* __restrict__ qpos, const int32_t* __
   done[i] = bad ? 1 : 0;
 }
 
+// FeetAirtimeReward.get_reward_stateful of one rollout chunk (train.py:503-546), one thread per environment.
+__global__ void zb_airtime_kernel(const float* __restrict__ lc, const float* __restrict__ rc, long long cts, long long ces,
+                                  const uint8_t* __restrict__ done, long long dts, long long des, float* __restrict__ carry,
+                                  float* __restrict__ reward, long long rts, long long res, int n_envs, int T, float ctrl_dt, float penalty) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_envs || T <= 0) return;
+  float tl = carry[2 * i], tr = carry[2 * i + 1];  // time since lift-off
+  float pl = 0.f, pr = 0.f;                        // airtime[t-1]
+  bool cl_prev = false, cr_prev = false, cl0 = false, cr0 = false;
+  for (int t = 0; t < T; t++) {
+    const bool cl = lc[t * cts + i * ces] > 0.5f, cr = rc[t * cts + i * ces] > 0.5f, dn = done[t * dts + i * des] != 0;
+    tl = (cl || dn) ? 0.f : tl + ctrl_dt;
+    tr = (cr || dn) ? 0.f : tr + ctrl_dt;
+    if (t == 0) { cl0 = cl; cr0 = cr; }
+    else reward[t * rts + i * res] = (pl - penalty) * ((cl && !cl_prev) ? 1.f : 0.f) + (pr - penalty) * ((cr && !cr_prev) ? 1.f : 0.f);
+    pl = tl; pr = tr; cl_prev = cl; cr_prev = cr;
+  }
+  // t = 0: touchdown against contact[-1] = false, airtime shifted in from the END of the chunk (jnp.roll)
+  reward[i * res] = (tl - penalty) * (cl0 ? 1.f : 0.f) + (tr - penalty) * (cr0 ? 1.f : 0.f);
+  carry[2 * i] = tl; carry[2 * i + 1] = tr;
+}
+
 // FP32 FFMA throughput probe: the roofline denominator for this path is the CUDA-core FP32 peak, which
 // MEASURED_PEAKS.json does not carry (it has HBM GB/s and bf16 tensor TF/s only).  16 independent FMA chains per thread.
 __global__ void __launch_bounds__(256) zb_ffma_kernel(float* __restrict__ out, int iters, float a, float b) {
@@ -718,6 +740,16 @@ int zb_terminations_f32(void* stream, const float* qpos, const int32_t* flags, u
   if (n_envs == 0) return ZB_OK;
   zb_term_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(qpos, flags, done, n_envs, z_lo, z_hi, cosf(max_tilt_rad));
   return after_launch("zb_terminations_f32 launch: %s");
+}
+
+int zb_feet_airtime_f32(void* stream, const float* left_contact, const float* right_contact, long long cts, long long ces,
+                        const uint8_t* done, long long dts, long long des, float* carry, float* reward, long long rts, long long res,
+                        int n_envs, int n_steps, float ctrl_dt, float touchdown_penalty) {
+  if (!left_contact || !right_contact || !done || !carry || !reward || n_envs < 0 || n_steps < 0) return fail(ZB_EINVAL, "zb_feet_airtime_f32: bad argument%s");
+  if (n_envs == 0 || n_steps == 0) return ZB_OK;
+  zb_airtime_kernel<<<(n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(left_contact, right_contact, cts, ces, done, dts, des, carry, reward, rts, res,
+                                                                          n_envs, n_steps, ctrl_dt, touchdown_penalty);
+  return after_launch("zb_feet_airtime_f32 launch: %s");
 }
 
 /* Launches the FFMA probe: grid x 256 threads, `iters` x 16 FMAs per thread.  The caller times it with CUDA events;

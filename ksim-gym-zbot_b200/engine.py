@@ -69,7 +69,7 @@ class ZbAutoResetArgs(ctypes.Structure):
 ZB_OK, ZB_EINVAL, ZB_ENODEV, ZB_ECUDA, ZB_EUNSUP = 0, -1, -2, -3, -4
 EXPORTS = ["zb_engine_create", "zb_engine_destroy", "zb_engine_set_opts", "zb_step_f32", "zb_forward_f32", "zb_reset_f32",
            "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count", "zb_bench_ffma", "zb_terminations_f32", "zb_step_autoreset_f32",
-           "zb_step_obs_f32", "zb_reset_obs_f32"]
+           "zb_step_obs_f32", "zb_reset_obs_f32", "zb_feet_airtime_f32"]
 
 
 class ZbError(RuntimeError):
@@ -102,6 +102,9 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         [ctypes.c_void_p] * 4 + [ctypes.c_float] * 3
     lib.zb_step_obs_f32.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.zb_reset_obs_f32.argtypes = [ctypes.c_void_p] * 10 + [ctypes.c_int]
+    LL = ctypes.c_longlong
+    lib.zb_feet_airtime_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, LL, LL, ctypes.c_void_p, LL, LL, ctypes.c_void_p,
+                                        ctypes.c_void_p, LL, LL, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]
     lib.zb_forward_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     lib.zb_reset_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -576,6 +579,23 @@ class ZbotCudaEngine:
                                           z_lo, z_hi, max_tilt)
         self._check(rc)
         return done
+
+    def feet_airtime_reward(self, left_contact: torch.Tensor, right_contact: torch.Tensor, done: torch.Tensor, carry: torch.Tensor,
+                            reward: torch.Tensor | None = None, ctrl_dt: float | None = None, touchdown_penalty: float = 0.3) -> torch.Tensor:
+        """FeetAirtimeReward.get_reward_stateful over one rollout chunk (train.py:503-546, raw: before ``scale``).
+        ``left_contact`` / ``right_contact`` [T, N] float (any strides, e.g. ``terms[:, :, 4]`` of stacked ``reward_terms``),
+        ``done`` [T, N] uint8, ``carry`` [N, 2] float32 contiguous (updated in place); returns ``reward`` [T, N]."""
+        T, n = left_contact.shape
+        assert right_contact.shape == (T, n) and done.shape == (T, n) and done.dtype == torch.uint8 and carry.shape == (n, 2) and carry.is_contiguous()
+        assert left_contact.stride() == right_contact.stride() and left_contact.dtype == torch.float32 == right_contact.dtype
+        if reward is None:
+            reward = torch.empty((T, n), dtype=torch.float32, device=self.device)
+        rc = self.lib.zb_feet_airtime_f32(self._stream(), ctypes.c_void_p(left_contact.data_ptr()), ctypes.c_void_p(right_contact.data_ptr()),
+                                          left_contact.stride(0), left_contact.stride(1), ctypes.c_void_p(done.data_ptr()), done.stride(0),
+                                          done.stride(1), ctypes.c_void_p(carry.data_ptr()), ctypes.c_void_p(reward.data_ptr()), reward.stride(0),
+                                          reward.stride(1), n, T, self.ctrl_dt if ctrl_dt is None else ctrl_dt, touchdown_penalty)
+        self._check(rc)
+        return reward
 
     def launch_count(self) -> int:
         return int(self.lib.zb_launch_count())

@@ -276,3 +276,24 @@ class Oracle:
         buf = (ctypes.c_double * len(STAGES))()
         self.lib.zbo_flops_get(buf)
         return dict(zip(STAGES, list(buf)))
+
+
+def feet_airtime(left_contact, right_contact, done, carry, ctrl_dt=0.02, touchdown_penalty=0.3):
+    """Restatement of FeetAirtimeReward.get_reward_stateful (/root/reference/train.py:503-546) for a batch of environments:
+    contacts / done [T, N] booleans, carry [N, 2] float32 -> (reward [T, N], new carry [N, 2]), raw (before ``scale``),
+    stand_still_threshold = None (train.py:1560-1565).  fp32 accumulation like jax's default dtype."""
+    lc, rc, dn = (np.asarray(a, dtype=bool) for a in (left_contact, right_contact, done))
+    T, n = lc.shape
+    time = np.asarray(carry, dtype=np.float32).copy()
+    air = np.zeros((T, n, 2), np.float32)
+    dt, pen = np.float32(ctrl_dt), np.float32(touchdown_penalty)
+    for t in range(T):
+        cod = np.stack([lc[t] | dn[t], rc[t] | dn[t]], axis=-1)
+        time = np.where(cod, np.float32(0), time + dt).astype(np.float32)
+        air[t] = time
+    c = np.stack([lc, rc], axis=-1)
+    prev = np.concatenate([np.zeros((1, n, 2), bool), c[:-1]], axis=0)
+    td = (c & ~prev).astype(np.float32)
+    shifted = np.roll(air, 1, axis=0)
+    reward = ((shifted - pen) * td).astype(np.float32)
+    return (reward[..., 0] + reward[..., 1]).astype(np.float32), time

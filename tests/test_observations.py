@@ -312,3 +312,93 @@ def test_reward_inputs_epilogue_matches_oracle(zmodel):
     eng.step(T(random_actions(n, 99)), None, ps, obs=only, command=T(cmd))
     torch.cuda.synchronize()
     assert torch.isfinite(only.reward_terms).all() and float(only.feet_pos_obs.abs().max()) > 0
+
+
+# ---- FeetAirtimeReward over a rollout chunk (train.py:485-546) -----------------------------------------------------------
+def feet_airtime_reference_one_env(touch_l, touch_r, done, carry, ctrl_dt=0.02, touchdown_penalty=0.3):
+    """Line-by-line numpy transcription of FeetAirtimeReward.get_reward_stateful for ONE environment (the reference vmaps it),
+    stand_still_threshold = None (train.py:1560-1565)."""
+    f32 = np.float32
+
+    def airtime_sequence(initial, contact_bool, done):  # train.py:503-516
+        t, out = f32(initial), []
+        for c in np.logical_or(contact_bool, done):
+            t = f32(0.0) if c else f32(t + f32(ctrl_dt))
+            out.append(t)
+        return t, np.array(out, dtype=f32)
+
+    left_contact = np.where(touch_l > 0.1, True, False)[:, 0]   # train.py:519-520
+    right_contact = np.where(touch_r > 0.1, True, False)[:, 0]
+    left_carry, left_air = airtime_sequence(carry[0], left_contact, done)
+    right_carry, right_air = airtime_sequence(carry[1], right_contact, done)
+
+    def touchdown(c):  # train.py:528-531
+        prev = np.concatenate([np.array([False]), c[:-1]])
+        return np.logical_and(c, np.logical_not(prev))
+
+    td_l, td_r = touchdown(left_contact), touchdown(right_contact)
+    left_air_shifted, right_air_shifted = np.roll(left_air, 1), np.roll(right_air, 1)
+    reward = (left_air_shifted - f32(touchdown_penalty)) * td_l.astype(f32) + (right_air_shifted - f32(touchdown_penalty)) * td_r.astype(f32)
+    return reward.astype(f32), np.array([left_carry, right_carry], dtype=f32)
+
+
+def _airtime_case(T, n, seed):
+    r = np.random.default_rng(seed)
+    # contact phases of random length so that swing times and touchdowns both occur
+    lc = np.zeros((T, n), bool); rc = np.zeros((T, n), bool)
+    for arr in (lc, rc):
+        for i in range(n):
+            t, s = 0, bool(r.integers(0, 2))
+            while t < T:
+                k = int(r.integers(1, 12))
+                arr[t:t + k, i] = s
+                s, t = not s, t + k
+    done = r.uniform(size=(T, n)) < 0.03
+    carry = r.uniform(0, 0.3, (n, 2)).astype(np.float32)
+    return lc, rc, done, carry
+
+
+def test_feet_airtime_oracle_matches_reference_transcription():
+    import zb_oracle
+
+    T, n = 57, 40
+    lc, rc, done, carry = _airtime_case(T, n, 3)
+    rew, new_carry = zb_oracle.feet_airtime(lc, rc, done, carry, ctrl_dt=0.02, touchdown_penalty=0.3)
+    for i in range(n):
+        touch_l = np.where(lc[:, i], 2.0, 0.05)[:, None].astype(np.float32)
+        touch_r = np.where(rc[:, i], 0.7, 0.0)[:, None].astype(np.float32)
+        r_ref, c_ref = feet_airtime_reference_one_env(touch_l, touch_r, done[:, i], carry[i])
+        np.testing.assert_array_equal(rew[:, i], r_ref)
+        np.testing.assert_array_equal(new_carry[i], c_ref)
+    assert (rew != 0).mean() > 0.02 and (rew > 0).any() and (rew < 0).any()
+
+
+@pytest.mark.gpu
+def test_feet_airtime_kernel_is_exact(zmodel):
+    import torch
+    import zb_oracle
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import ZbotCudaEngine
+
+    eng = ZbotCudaEngine(zmodel, 4, device=0, opts=M.make_opts(dt=0.005), ctrl_dt=0.02)
+    for T, n, seed in ((1, 5, 1), (200, 333, 2), (64, 4096, 3)):
+        lc, rc, done, carry = _airtime_case(T, n, seed)
+        rew, new_carry = zb_oracle.feet_airtime(lc, rc, done, carry, ctrl_dt=0.02, touchdown_penalty=0.3)
+        # contacts as slices 4 / 5 of the stacked per-step reward_terms [T, N, 6] (non-contiguous views), done time-major
+        terms = torch.zeros((T, n, 6), device="cuda")
+        terms[:, :, 4] = torch.tensor(lc, dtype=torch.float32)
+        terms[:, :, 5] = torch.tensor(rc, dtype=torch.float32)
+        c = torch.tensor(carry, device="cuda")
+        out = eng.feet_airtime_reward(terms[:, :, 4], terms[:, :, 5], torch.tensor(done.astype(np.uint8), device="cuda"), c, touchdown_penalty=0.3)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.cpu().numpy(), rew)
+        np.testing.assert_array_equal(c.cpu().numpy(), new_carry)
+        # env-major layout ([N, T] storage viewed as [T, N]) gives the same
+        lcT = torch.tensor(lc.T.copy(), dtype=torch.float32, device="cuda").T
+        rcT = torch.tensor(rc.T.copy(), dtype=torch.float32, device="cuda").T
+        dT = torch.tensor(done.T.copy().astype(np.uint8), device="cuda").T
+        c2 = torch.tensor(carry, device="cuda")
+        out2 = torch.empty((n, T), device="cuda").T
+        eng.feet_airtime_reward(lcT, rcT, dT, c2, reward=out2, touchdown_penalty=0.3)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out2.cpu().numpy(), rew)
