@@ -325,6 +325,9 @@ int zb_abi_version(void);
 int zb_sizeof_model(void);
 int zb_sizeof_opts(void);
 const char* zb_last_error(void);
+/* The CTA shape a step launch of n_envs environments gets on a GPU with num_sms SMs (host logic, no device needed):
+ * *wide = 1 for the 28-warp / 72-register throughput profile, 0 for the 16-warp / 128-register latency profile. */
+int zb_cta_shape(int n_envs, int num_sms, int* wide, int* warps_per_cta);
 /* Number of kernel launches issued through this library since load (bench accounting). */
 long long zb_launch_count(void);
 

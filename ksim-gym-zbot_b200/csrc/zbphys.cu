@@ -44,9 +44,9 @@ struct ZbEngine {
 //                    (0.605 vs 0.737 ms), 8192 in two instead of 3.5 (1.18 vs 1.39 ms), 16 384: 2.29 vs 2.48 ms
 //                    (profiles/r1_occupancy_sweep2.txt).  The CTAs are balanced over the waves: ceil(n / (waves SMs)) warps.
 struct CtaShape { bool wide; int wpb; };
-static CtaShape pick_shape(const ZbEngine* e, int n_envs, bool wide_available) {
-  const int sms = e->num_sms > 0 ? e->num_sms : 148;
-  if (e->force_wpb > 0) return {wide_available && e->force_wpb > ZB_WPB, e->force_wpb > ZB_WPB && !wide_available ? ZB_WPB : e->force_wpb};
+static CtaShape shape_policy(int n_envs, int sms, int force_wpb, bool wide_available) {
+  if (sms <= 0) sms = 148;
+  if (force_wpb > 0) return {wide_available && force_wpb > ZB_WPB, force_wpb > ZB_WPB && !wide_available ? ZB_WPB : force_wpb};
   if (n_envs <= ZB_WPB * sms || !wide_available) {
     const int w = (n_envs + sms - 1) / sms;
     return {false, w < 1 ? 1 : (w > ZB_WPB ? ZB_WPB : w)};
@@ -57,6 +57,7 @@ static CtaShape pick_shape(const ZbEngine* e, int n_envs, bool wide_available) {
   if (w > ZB_WPB_WIDE) w = ZB_WPB_WIDE;
   return {true, w};
 }
+static CtaShape pick_shape(const ZbEngine* e, int n_envs, bool wide_available) { return shape_policy(n_envs, e->num_sms, e->force_wpb, wide_available); }
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -530,6 +531,13 @@ static int check_opts(const ZbOpts* o) {
 extern "C" {
 
 int zb_abi_version(void) { return ZB_ABI_VERSION; }
+int zb_cta_shape(int n_envs, int num_sms, int* wide, int* warps_per_cta) {
+  if (n_envs < 1 || !wide || !warps_per_cta) return fail(ZB_EINVAL, "zb_cta_shape: bad argument%s");
+  const CtaShape cs = shape_policy(n_envs, num_sms, 0, true);
+  *wide = cs.wide ? 1 : 0;
+  *warps_per_cta = cs.wpb;
+  return ZB_OK;
+}
 int zb_sizeof_model(void) { return (int)sizeof(ZbModel); }
 int zb_sizeof_opts(void) { return (int)sizeof(ZbOpts); }
 const char* zb_last_error(void) { return g_err; }

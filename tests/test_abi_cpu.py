@@ -82,3 +82,27 @@ def test_model_compile_constants(zmodel):
     scale = p["body_mass"][:, 1] / zmodel.field("body_mass")[1]
     assert scale.min() >= 0.95 - 1e-6 and scale.max() <= 1.15 + 1e-6  # train.py:1443
     assert np.abs(p["qpos0"][:, 7:] - zmodel.field("qpos0")[7:]).max() <= np.radians(2) + 1e-6  # train.py:1445
+
+
+def test_cta_shape_policy(lib):
+    """pick_shape: sub-wave batches are spread over the SMs with small 128-register CTAs, larger ones run in the fewest waves of
+    (balanced) 72-register CTAs of up to 28 warps."""
+    import ctypes
+
+    def shape(n, sms=148):
+        w, k = ctypes.c_int(), ctypes.c_int()
+        assert lib.zb_cta_shape(n, sms, ctypes.byref(w), ctypes.byref(k)) == 0
+        return w.value, k.value
+
+    assert shape(1) == (0, 1) and shape(148) == (0, 1) and shape(1024) == (0, 7) and shape(16 * 148) == (0, 16)
+    assert shape(16 * 148 + 1) == (1, 17)
+    assert shape(4096) == (1, 28)            # ONE wave of 147 CTAs
+    assert shape(5000) == (1, 17)            # two balanced waves instead of 28 + 6
+    assert shape(8192) == (1, 28) and shape(16384) == (1, 28) and shape(65536) == (1, 28)
+    for n in (2369, 3000, 4144, 4145, 10000, 12345, 262144):
+        wide, k = shape(n)
+        waves = -(-n // (28 * 148))
+        assert wide == 1 and 1 <= k <= 28 and -(-n // k) <= waves * 148  # fits the minimal number of waves
+    assert shape(4096, sms=132) == (1, 16)   # another SM count: two waves of 16 (4096 / 264 = 15.5)
+    w, k = ctypes.c_int(), ctypes.c_int()
+    assert lib.zb_cta_shape(0, 148, ctypes.byref(w), ctypes.byref(k)) == -1
