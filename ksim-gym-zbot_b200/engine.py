@@ -509,7 +509,9 @@ class ZbotCudaEngine:
         """Pre-bind one control step: all argument structs of the C call are built once, the returned function
         ``run(action, push_rand=None)`` only passes the two pointers that change per step and enqueues the launch on the
         current stream (what an XLA custom call does with its operand buffers; ~10x less host time per step than ``step``).
-        The tensors bound here must stay alive and in place; action latency / drop-action are not handled by a plan."""
+        The tensors bound here must stay alive and in place (refill ``reset_imu_lag`` / the reset arrays / ``command`` in place to
+        change them between steps; a ``reset_imu_lag`` of None is sampled ONCE here); action latency / drop-action are not handled
+        by a plan."""
         if self.drop_action_prob > 0 or self.action_latency_range[1] > 0:
             raise ValueError("plan_step does not cover action latency / drop-action: use step()")
         ps = physics_state
