@@ -586,25 +586,36 @@ struct WarpEnv {
     return dot6(w, Vf);
   }
 
-  // total contact wrench of the foot box of my half-warp (row lanes): sum_r f_r w_r over its 16 rows
-  ZB_DI void contact_wrench(float f, float (&Wf)[6]) const {
+  // Total contact wrench of the foot box of my half-warp, sum_r f_r w_r over its 16 row lanes, as a transpose-reduce inside the
+  // half: 8 shuffles instead of 24.  Afterwards component k of box g sits in lanes 16 g + 2k (+1).  Every component is still
+  // summed over the lanes in the butterfly order 8, 4, 2, 1, i.e. bit for bit what six separate butterflies give.
+  ZB_DI float contact_wrench(float f) const {
+    float v[8];
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-      float t = c_on ? f * w[k] : 0.f;
-      t += shx(t, 8); t += shx(t, 4); t += shx(t, 2); t += shx(t, 1);
-      Wf[k] = t;
+    for (int k = 0; k < 6; k++) v[k] = c_on ? f * w[k] : 0.f;
+    v[6] = v[7] = 0.f;
+    int m = 8;
+#pragma unroll
+    for (int half = 4; half >= 1; half >>= 1, m >>= 1) {
+      const bool up = (L & m) != 0;
+#pragma unroll
+      for (int j = 0; j < half; j++) {
+        const float send = up ? v[j] : v[j + half], keep = up ? v[j + half] : v[j];
+        v[j] = keep + __shfl_xor_sync(ZB_FULL, send, m);
+      }
     }
+    return v[0] + shx(v[0], 1);
   }
 
   // J^T f for the contact rows: per-box total wrench, projected on the dofs
   ZB_DI float contact_jtf(float f) {
-    float Wf[6];
-    contact_wrench(f, Wf);
+    const float tot = contact_wrench(f);
+    const float both_t = tot + shx(tot, 16);
     float r = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-      const float mine = shf(Wf[k], lbox >= 0 ? 16 * lbox : 0);
-      const float both = Wf[k] + shx(Wf[k], 16);
+      const float mine = shf(tot, (lbox >= 0 ? 16 * lbox : 0) + 2 * k);
+      const float both = shf(both_t, 2 * k);
       if (hinge && lbox >= 0) r += cdof[k] * mine;
       if (bdof) r += cdof[k] * both;
     }
@@ -1321,11 +1332,10 @@ struct WarpEnv {
     inert_mul(t, cinert, cvel);
     motion_cross_force(u, cvel, t);
     const int mybox = isbody ? D->body_box[L] : -1;
-    float Wf[6];
-    contact_wrench(c_force, Wf);  // cfrc_ext of a foot = the solver's total contact wrench of its box
+    const float Wtot = contact_wrench(c_force);  // cfrc_ext of a foot = the solver's total contact wrench of its box
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-      const float ext = shf(Wf[k], mybox >= 0 ? 16 * mybox : 0);
+      const float ext = shf(Wtot, (mybox >= 0 ? 16 * mybox : 0) + 2 * k);
       cf[k] = isbody ? cf[k] + u[k] - (mybox >= 0 ? ext : 0.f) : 0.f;
     }
     chain_suffix<6>(cf);
