@@ -610,14 +610,17 @@ struct WarpEnv {
   // J^T f for the contact rows: per-box total wrench, projected on the dofs
   ZB_DI float contact_jtf(float f) {
     const float tot = contact_wrench(f);
-    const float both_t = tot + shx(tot, 16);
+    // even lanes keep the wrench of their own box, odd lanes the sum over both boxes: a leg dof pulls component k from lane
+    // 16 box + 2k, a base dof from lane 2k + 1 — one shuffle per component for either kind of lane
+    const float both_t = tot + shx(tot, 16);  // (the shuffle must be executed by ALL lanes: not inside the select)
+    const float pub = (L & 1) ? both_t : tot;
+    const bool leg = hinge && lbox >= 0;
+    const int src = leg ? 16 * lbox : 1;
     float r = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-      const float mine = shf(tot, (lbox >= 0 ? 16 * lbox : 0) + 2 * k);
-      const float both = shf(both_t, 2 * k);
-      if (hinge && lbox >= 0) r += cdof[k] * mine;
-      if (bdof) r += cdof[k] * both;
+      const float wk = shf(pub, src + 2 * k);
+      if (leg || bdof) r += cdof[k] * wk;
     }
     return r;
   }
