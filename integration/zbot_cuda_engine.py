@@ -19,6 +19,7 @@ import ctypes
 
 import jax
 import jax.numpy as jnp
+import numpy as np
 import ksim  # noqa: F401  (PhysicsEngine, PhysicsState)
 
 _lib = ctypes.CDLL("libzb_ffi.so")
@@ -44,7 +45,7 @@ def zb_step_obs(engine_handle: int, n_substeps: int, state: dict, action, push_r
     outs = call(*[state[k] for k in _STATE], action, push_rand, command, reset["qpos"], reset["qvel"], reset["t_rem"], reset["imu_lag"],
                 *[model_fields[k] for k in ("body_mass", "body_inertia", "dof_armature", "dof_damping", "dof_frictionloss", "qpos0",
                                             "floor_friction", "imu_site_pos", "imu_site_quat")],
-                engine=jnp.int64(engine_handle), n_substeps=jnp.int32(n_substeps), z_lo=jnp.float32(z_lo), z_hi=jnp.float32(z_hi),
-                max_tilt_rad=jnp.float32(max_tilt_rad))
+                engine=np.int64(engine_handle), n_substeps=np.int32(n_substeps), z_lo=np.float32(z_lo), z_hi=np.float32(z_hi),
+                max_tilt_rad=np.float32(max_tilt_rad))  # attributes are static (numpy scalars), operands are traced
     new_state = dict(zip(_STATE, outs[:len(_STATE)]))
     return new_state, {k: v for (k, _), v in zip(_OUT, outs[len(_STATE):])}
