@@ -95,7 +95,7 @@ struct LSSet {          // an active set of the line search: its summed quadrati
   int z;
 };
 
-// TRACE: compile the solver-trace diagnostics in (tests/gpu_probe*.py); the production instantiation carries none of it.
+// TRACE: compile the solver-trace diagnostics in (scripts/gpu_probe*.py); the production instantiation carries none of it.
 // LOCK: CTA-lockstep barriers (see solve_all).
 // FSM: the factor and the mass-matrix rows of a lane live in shared memory (throughput profile) instead of registers.
 template <bool TRACE, bool LOCK, bool FSM>
@@ -949,7 +949,7 @@ struct WarpEnv {
     // NOT fused on purpose (__fmul_rn/__fadd_rn are never contracted into FMA): when the active set did not change, the
     // Newton point alpha = -t1 / (2 t2) makes 2*alpha*t2 + t1 round to EXACTLY 0 with separately rounded products, and
     // the reference's bracket logic treats an exact zero as "not in bracket" (the point is rejected).  An FMA would
-    // return the tiny residual instead and flip that decision in ~14 % of the states (tests/gpu_probe3.py).
+    // return the tiny residual instead and flip that decision in ~14 % of the states (scripts/gpu_probe3.py).
     p.d0 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, a), S.t2), S.t1);
     return p;
   }

@@ -1,4 +1,4 @@
-"""Diagnostic (not a test): CUDA vs oracle error statistics for several solver budgets.  python tests/gpu_probe.py"""
+"""Diagnostic (not a test): CUDA vs oracle error statistics for several solver budgets.  python scripts/gpu_probe.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]

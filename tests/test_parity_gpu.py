@@ -103,7 +103,7 @@ def _assert_close(name, r, key, tol, floor=1.0, slack=3.0, which=""):
     (bracket swaps, early exit when nothing swapped) on derivative values that sit at rounding level whenever a Newton
     step lands on the 1-D minimum.  Any change of rounding — another summation order, one ulp on the inputs,
     XLA:GPU vs XLA:CPU — flips some of those decisions and the capped solve ends somewhere else: O(1e-2) relative on
-    qacc for a few percent of states (tests/gpu_probe3.py prints per-iteration traces).  The plain fp32 oracle shares
+    qacc for a few percent of states (scripts/gpu_probe3.py prints per-iteration traces).  The plain fp32 oracle shares
     its operation order with the fp64 one, so its decisions are correlated with fp64's and it under-states that
     spread; the perturbed run shows it.  With the solver out of the picture (iterations=0) or run to convergence
     the agreement is at rounding level: test_deterministic_part_is_tight.
