@@ -452,7 +452,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None  # DRAM bytes per launch of the step kernel from the committed ncu capture of THIS workload, if there is one
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(a.workload)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("c2_s20" if (a.workload == "c2" and S == 20) else a.workload)
         if tr and tr["envs"] == n_env and tr["substeps"] == S and not a.obs and a.solver == "cg":
             traffic = tr["bytes_per_launch"]
     except Exception:
