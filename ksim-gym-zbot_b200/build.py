@@ -1,4 +1,9 @@
-"""In-tree build of the CUDA extension (libzbphys.so) with nvcc for sm_100a."""
+"""In-tree build of the CUDA extension (libzbphys.so) with nvcc for sm_100a.
+
+``build_extension()`` builds the product library.  ``build_variant(name, defines)`` builds tuning / mutation variants of the
+same sources into ``csrc/variants/libzbphys_<name>.so`` (``-DZB_MINIMAL``: only the plain step and reset instantiations, a
+quarter of the compile time); the engine loads one with ``ZbotCudaEngine(..., lib_path=...)`` or ``ZBPHYS_LIB``.
+"""
 
 from __future__ import annotations
 
@@ -10,25 +15,63 @@ _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SOURCES = ["zbphys.cu"]
 HEADERS = ["zb_kernel.cuh", "zb_math.cuh", os.path.join("..", "..", "include", "zbphys.h")]
 LIB = os.path.join(_CSRC, "libzbphys.so")
+VARIANT_DIR = os.path.join(_CSRC, "variants")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
+# Mutation builds (tests/test_parity_tail.py): each plants ONE bug in a rarely taken path of the step kernel; the parity
+# checks must turn red on every one of them ("make the parity tests able to fail on a tail bug").
+MUTANTS = {
+    "mut1": ["-DZB_MUTANT=1"],  # wrong sign on the second tangent of manifold slot 3 (only 4-contact feet are affected)
+    "mut2": ["-DZB_MUTANT=2"],  # the line search's full re-summation hands the wrong active set to a swapped bracket end
+    "mut3": ["-DZB_MUTANT=3"],  # joint-limit rows drop out of the line search's zone test
+}
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(_CSRC, f)) > t for f in SOURCES + HEADERS)
+
+def _newer_than_sources(path: str) -> bool:
+    if not os.path.exists(path):
+        return False
+    t = os.path.getmtime(path)
+    return not any(os.path.getmtime(os.path.join(_CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def _nvcc_cmd(out: str, defines=(), verbose: bool = False) -> list[str]:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return [nvcc, *NVCC_FLAGS, *defines, *(["-Xptxas", "-v"] if verbose else []), "-o", out, *[os.path.join(_CSRC, s) for s in SOURCES]]
 
 
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu -> csrc/libzbphys.so (nvcc cross-compiles without a GPU)."""
-    if not force and not _stale():
+    if not force and _newer_than_sources(LIB):
         return LIB
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *[os.path.join(_CSRC, s) for s in SOURCES]]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run(_nvcc_cmd(LIB, (), verbose), capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
     return LIB
+
+
+def variant_path(name: str) -> str:
+    return os.path.join(VARIANT_DIR, f"libzbphys_{name}.so")
+
+
+def build_variants(variants: dict[str, list[str]], force: bool = False, minimal: bool = True) -> dict[str, str]:
+    """Build several variants concurrently (one nvcc process each)."""
+    os.makedirs(VARIANT_DIR, exist_ok=True)
+    procs, out = [], {}
+    for name, defines in variants.items():
+        path = variant_path(name)
+        out[name] = path
+        if not force and _newer_than_sources(path):
+            continue
+        d = list(defines) + (["-DZB_MINIMAL"] if minimal else [])
+        procs.append((name, subprocess.Popen(_nvcc_cmd(path, d), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for name, p in procs:
+        log, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for variant {name}:\n{log}")
+    return out
+
+
+def build_mutants(force: bool = False) -> dict[str, str]:
+    return build_variants(MUTANTS, force=force, minimal=True)

@@ -41,6 +41,9 @@
 #define ZB_CTA_LOCKSTEP 1 /* 1: the warps of a CTA meet at every substep (shared instruction fetch: +30 %); 2: also before every solver pass (measured slower: waits for the slowest line search) */
 #endif
 #define ZB_SCR 8     /* scratch floats per lane */
+#ifndef ZB_LS_SAME
+#define ZB_LS_SAME 2 /* line search: 1 = no zone evaluation while both bracket ends share one active set, 2 = + the one-sided loop (see linesearch) */
+#endif
 
 static_assert(ZB_NBODY + 6 == 32, "lane mapping assumes 26 bodies + 6 free-joint dofs == one warp");
 
@@ -1039,8 +1042,60 @@ struct WarpEnv {
     }
     bool swap = true;
     int it = 0;
+#if ZB_LS_SAME
+    // `same`: both bracket ends sit on the same piece of EVERY row of the warp (their active sets are identical).  Each row's
+    // piece is a monotone step function of the step size (x0 + a jv is monotone in a, rounding included), so every step size
+    // BETWEEN the two ends then lies on those pieces as well: no zone evaluation, no votes, and the iteration is pure
+    // warp-uniform scalar work.  Measured with the oracle on the bench workload (oracle set_variant(4)): 92 % of the bracket
+    // iterations start in this state, 83 % also propose all three candidates inside the bracket, and 65 % have one end resting
+    // on an exactly zero derivative (then only the other end can still move: the one-sided loop below).  Bit for bit the same
+    // decisions and numbers as the general iteration.
+    bool same = !__any_sync(ZB_FULL, Slo.z != Shi.z);
+#endif
 #pragma unroll 1
     while (true) {
+#if ZB_LS_SAME >= 2
+      if (!(TRACE && trace && niter == 0)) {
+        const bool zlo = lo.d0 == 0.f, zhi = hi.d0 == 0.f;
+        if (__all_sync(ZB_FULL, same && (zlo != zhi))) {
+          // ---- one-sided loop: the end Z rests on the exact minimum of its quadratic (d0 == 0), so its Newton candidate is Z
+          // itself and no candidate can replace it (in_bracket(0, y) and in_bracket(x, 0) are false); only the other end M moves:
+          // first to its Newton candidate, then to the midpoint, exactly the s1/s2 (M = lo) or s4/s5 (M = hi) tests of the
+          // general iteration.  The midpoint is evaluated on lo's active set, and hi takes that set along with the midpoint.
+          const bool mhi = zlo;
+          float Ma_ = mhi ? hi.alpha : lo.alpha, Md = mhi ? hi.d0 : lo.d0;
+          const float Za = mhi ? lo.alpha : hi.alpha, sg = mhi ? 1.f : -1.f;
+          float m0 = mhi ? Shi.t0 : Slo.t0, m1 = mhi ? Shi.t1 : Slo.t1, m2 = mhi ? Shi.t2 : Slo.t2, md1 = mhi ? Shi.d1 : Slo.d1;
+          const float z0 = mhi ? Slo.t0 : Shi.t0, z1 = mhi ? Slo.t1 : Shi.t1, z2 = mhi ? Slo.t2 : Shi.t2, zd1 = mhi ? Slo.d1 : Shi.d1;
+#pragma unroll 1
+          while (true) {
+            bool dn = it >= o.ls_iterations;
+            dn |= !swap;
+            const float sd = sg * Md;
+            dn |= (sd > 0.f) && (sd < gtol);
+            if (dn) break;
+            const bool nz = Md != 0.f;
+            float nn = nz ? Md : 1.f;
+            asm volatile("" : "+f"(nn));
+            float q = nn / md1;
+            q = nz ? q : 0.f;
+            const float c1 = Ma_ - q, c2 = 0.5f * (Za + Ma_);
+            const float amin = fminf(Za, Ma_), amax = fmaxf(Za, Ma_);
+            if (!(c1 >= amin && c1 <= amax)) break;  // Newton candidate outside the bracket: its pieces must be looked at (general iteration)
+            const float e1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, c1), m2), m1);
+            const float e2 = mhi ? __fadd_rn(__fmul_rn(__fmul_rn(2.f, c2), z2), z1) : __fadd_rn(__fmul_rn(__fmul_rn(2.f, c2), m2), m1);
+            const bool t1 = in_bracket(Md, e1);
+            if (t1) { Ma_ = c1; Md = e1; }
+            const bool t2 = in_bracket(Md, e2);
+            if (t2) { Ma_ = c2; Md = e2; if (mhi) { m0 = z0; m1 = z1; m2 = z2; md1 = zd1; } }
+            swap = t1 | t2;
+            it++;
+          }
+          if (mhi) { hi.alpha = Ma_; hi.d0 = Md; Shi.t0 = m0; Shi.t1 = m1; Shi.t2 = m2; Shi.d1 = md1; }
+          else { lo.alpha = Ma_; lo.d0 = Md; }
+        }
+      }
+#endif
       bool done = it >= o.ls_iterations;
       done |= !swap;
       done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
@@ -1062,9 +1117,17 @@ struct WarpEnv {
       al[0] = lo.alpha - q_lo;
       al[1] = hi.alpha - q_hi;
       al[2] = 0.5f * (lo.alpha + hi.alpha);
-      zz[0] = zone_at(r, al[0]); zz[1] = zone_at(r, al[1]); zz[2] = zone_at(r, al[2]);
-      const bool f0 = __any_sync(ZB_FULL, zz[0] != Slo.z), f1 = __any_sync(ZB_FULL, zz[1] != Shi.z);
-      const bool f2l = __any_sync(ZB_FULL, zz[2] != Slo.z), f2h = __any_sync(ZB_FULL, zz[2] != Shi.z);
+      bool f0 = false, f1 = false, f2l = false, f2h = false;
+#if ZB_LS_SAME
+      const float amin = fminf(lo.alpha, hi.alpha), amax = fmaxf(lo.alpha, hi.alpha);
+      const bool inside = same && al[0] >= amin && al[0] <= amax && al[1] >= amin && al[1] <= amax && al[2] >= amin && al[2] <= amax;
+      if (!__all_sync(ZB_FULL, inside))
+#endif
+      {
+        zz[0] = zone_at(r, al[0]); zz[1] = zone_at(r, al[1]); zz[2] = zone_at(r, al[2]);
+        f0 = __any_sync(ZB_FULL, zz[0] != Slo.z); f1 = __any_sync(ZB_FULL, zz[1] != Shi.z);
+        f2l = __any_sync(ZB_FULL, zz[2] != Slo.z); f2h = __any_sync(ZB_FULL, zz[2] != Shi.z);
+      }
       if (!f0 && !f1 && !(f2l && f2h)) {
         // ---- fast path: every candidate lives on the active set of a bracket end ----
         const LSPoint lo_next = ls_make_point(al[0], Slo), hi_next = ls_make_point(al[1], Shi);
@@ -1072,18 +1135,20 @@ struct WarpEnv {
         pt[0] = lo_next; pt[1] = hi_next; pt[2] = mid;
         if (TRACE) { st[0].d1 = Slo.d1; st[1].d1 = Shi.d1; st[2].d1 = f2l ? Shi.d1 : Slo.d1; }
         bool lo_hi = false, hi_lo = false;  // does the new lo (hi) take the OTHER end's active set?
-        const LSPoint lo_old = lo, hi_old = hi;
+        const LSPoint hi_old = hi;
         const bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
         const bool s2 = in_bracket(lo.d0, mid.d0); if (s2) { lo = mid; lo_hi = f2l; }
         const bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) { lo = hi_next; lo_hi = true; }
         const bool s4 = in_bracket(hi_old.d0, hi_next.d0); if (s4) hi = hi_next;
         const bool s5 = in_bracket(hi.d0, mid.d0); if (s5) { hi = mid; hi_lo = !f2l; }
         const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) { hi = lo_next; hi_lo = true; }
-        (void)lo_old;
         swap = s1 | s2 | s3 | s4 | s5 | s6;
         const LSSet a = Slo, b = Shi;
         if (lo_hi) Slo = b;
         if (hi_lo) Shi = a;
+#if ZB_LS_SAME
+        same = same || (lo_hi != hi_lo);  // one end took over the other's set: identical; both did: the sets only changed sides
+#endif
       } else {
         ls_eval<3>(r, al, zz, pt, st);
         const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
@@ -1094,6 +1159,9 @@ struct WarpEnv {
         const bool s5 = in_bracket(hi.d0, mid.d0); if (s5) { hi = mid; Shi = st[2]; }
         const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) { hi = lo_next; Shi = st[0]; }
         swap = s1 | s2 | s3 | s4 | s5 | s6;
+#if ZB_LS_SAME
+        same = !__any_sync(ZB_FULL, Slo.z != Shi.z);
+#endif
       }
       if (TRACE && trace && niter == 0 && L == 0) {
         for (int j = 0; j < 3; j++)

@@ -578,7 +578,11 @@ int zb_engine_create(const ZbModel* model, const ZbOpts* opts, int device, ZbEng
   {  // the throughput-profile kernels keep 31 floats per lane in dynamic shared memory: 28 warps x 3968 B = 108.5 KB > the 48 KB default
     const int bytes = ZB_WPB_WIDE * ZB_FSM_BYTES_PER_WARP;
     cudaError_t a1 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, false, ZB_WPB_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#ifdef ZB_MINIMAL
+    cudaError_t a2 = cudaSuccess;
+#else
     cudaError_t a2 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, true, ZB_WPB_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#endif
     if (a1 != cudaSuccess || a2 != cudaSuccess) {
       cudaSetDevice(prev);
       delete e;
@@ -646,9 +650,14 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   const int wpb = cs.wpb, grid = (n_envs + wpb - 1) / wpb;
 #define ZB_LAUNCH_STEP(TR, OBSV, W) zb_kernel<ZB_MODE_STEP, TR, OBSV, W><<<grid, wpb * 32, (W > ZB_WPB) ? (size_t)wpb * ZB_FSM_BYTES_PER_WARP : 0, (cudaStream_t)stream>>>( \
     e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR, OB)
+#ifdef ZB_MINIMAL  // development / mutation builds: only the plain step (both register profiles) and the plain reset are compiled
+  if (O.solver_trace || with_obs) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no trace / observation instantiations%s");
+  if (cs.wide) ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB);
+#else
   if (O.solver_trace) { if (with_obs) ZB_LAUNCH_STEP(true, true, ZB_WPB); else ZB_LAUNCH_STEP(true, false, ZB_WPB); }
   else if (cs.wide) { if (with_obs) ZB_LAUNCH_STEP(false, true, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); }
   else { if (with_obs) ZB_LAUNCH_STEP(false, true, ZB_WPB); else ZB_LAUNCH_STEP(false, false, ZB_WPB); }
+#endif
 #undef ZB_LAUNCH_STEP
   return after_launch("zb_step_f32 launch: %s");
 }
@@ -680,11 +689,16 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int wpb = pick_shape(e, n_envs, false).wpb, grid = (n_envs + wpb - 1) / wpb;
+#ifdef ZB_MINIMAL
+  (void)wpb; (void)grid;
+  return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no forward instantiation%s");
+#else
   if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true, false, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
                                                                             nullptr, nullptr, nullptr, nullptr, ZbAutoReset{}, ZbObs{});
   else zb_kernel<ZB_MODE_FORWARD, false, false, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
                                                                             nullptr, nullptr, nullptr, nullptr, ZbAutoReset{}, ZbObs{});
   return after_launch("zb_forward_f32 launch: %s");
+#endif
 }
 
 static int check_obs(const ZbObs* obs) {
@@ -708,8 +722,13 @@ static int reset_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, cons
 #define ZB_LAUNCH_RESET(TR, OBSV) zb_kernel<ZB_MODE_RESET, TR, OBSV, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
     e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done, reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{}, OB)
   const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x || OB.feet_pos_obs || OB.reward_terms;
+#ifdef ZB_MINIMAL
+  if (O.solver_trace || with_obs) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no trace / observation instantiations%s");
+  ZB_LAUNCH_RESET(false, false);
+#else
   if (O.solver_trace) { if (with_obs) ZB_LAUNCH_RESET(true, true); else ZB_LAUNCH_RESET(true, false); }
   else { if (with_obs) ZB_LAUNCH_RESET(false, true); else ZB_LAUNCH_RESET(false, false); }
+#endif
 #undef ZB_LAUNCH_RESET
   return after_launch("zb_reset_f32 launch: %s");
 }

@@ -257,10 +257,10 @@ class ZbotCudaEngine:
                  integrator: int = M.INT_IMPLICITFAST, push: PushEventConfig | None = None,
                  resets: ResetConfig | None = None, opts: M.ZbOpts | None = None, seed: int = 0,
                  outputs: tuple[str, ...] | None = None, action_latency_range: tuple[float, float] = (0.0, 0.0),
-                 drop_action_prob: float = 0.0):
+                 drop_action_prob: float = 0.0, lib_path: str | None = None):
         if not torch.cuda.is_available():
             raise RuntimeError("ZbotCudaEngine needs a CUDA device: the physics step has no CPU fallback")
-        self.lib = load_library()
+        self.lib = load_library(lib_path)  # lib_path: a tuning / mutation variant of libzbphys.so (build.build_variants)
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.model = model
         self.n_envs = int(n_envs)

@@ -901,6 +901,23 @@ static LSPoint ls_point(const ZboData* d, const Ctx* c, real alpha, const real* 
 }
 static inline int in_bracket(real x, real y) { return (x < y && y < 0) || (x > y && y > 0); }
 
+/* Line-search statistics (diagnostics for the kernel design, single-threaded runs only; zbo_lsstats_get):
+ * [0] line searches, [1] bracket iterations, [2] iterations entered with an end on an exactly zero derivative,
+ * [3] iterations entered with both ends on the same pieces of every row ("same set"), [4] both, [5] same set and all three
+ * candidate step sizes inside the bracket, [6] same set + zero end + candidates inside, [7] line searches that ran out of iterations. */
+static double g_lsstat[8];
+static void zone_sig(const ZboData* d, const Ctx* c, real alpha, const real* jv, signed char* sig) {
+  for (int r = 0; r < NEFC; r++) {
+    sig[r] = 0;
+    if (d->efc_type[r] == 0) continue;
+    real x = c->Jaref[r] + alpha * jv[r];
+    if (d->efc_type[r] == 1) {
+      real f = d->efc_floss[r], rf = d->efc_R[r] * f;
+      sig[r] = (x <= -rf && f > 0) ? 1 : ((x >= rf && f > 0) ? 2 : 0);
+    } else sig[r] = x < 0 ? 4 : 0;
+  }
+}
+
 static void linesearch(const ZbModel* m, const ZbOpts* o, ZboData* d, Ctx* c) {
   real nrm = 0;
   for (int j = 0; j < NV; j++) nrm += c->search[j] * c->search[j];
@@ -931,12 +948,26 @@ static void linesearch(const ZbModel* m, const ZbOpts* o, ZboData* d, Ctx* c) {
   d->ls_evals += 2;
   if (lo.deriv_0 < p0.deriv_0) { hi = p0; } else { hi = lo; lo = p0; }
   int swap = 1, it = 0;
+  g_lsstat[0] += 1;
   while (1) {
     int done = it >= o->ls_iterations;
     done |= !swap;
     done |= (lo.deriv_0 < 0) && (lo.deriv_0 > -gtol);
     done |= (hi.deriv_0 > 0) && (hi.deriv_0 < gtol);
+    if ((g_variant & 2) && (lo.deriv_0 == 0 || hi.deriv_0 == 0)) done = 1; /* experiment: stop once an end sits on the exact minimum */
     if (done) break;
+    if (g_variant & 4) { /* statistics */
+      signed char za[NEFC], zb[NEFC];
+      zone_sig(d, c, lo.alpha, jv, za);
+      zone_sig(d, c, hi.alpha, jv, zb);
+      int same = memcmp(za, zb, sizeof(za)) == 0, zero = lo.deriv_0 == 0 || hi.deriv_0 == 0;
+      real a0 = lo.alpha - lo.deriv_0 / lo.deriv_1, a1 = hi.alpha - hi.deriv_0 / hi.deriv_1;
+      real mn = lo.alpha < hi.alpha ? lo.alpha : hi.alpha, mx = lo.alpha < hi.alpha ? hi.alpha : lo.alpha;
+      int inside = a0 >= mn && a0 <= mx && a1 >= mn && a1 <= mx;
+      g_lsstat[1] += 1; g_lsstat[2] += zero; g_lsstat[3] += same; g_lsstat[4] += same && zero; g_lsstat[5] += same && inside;
+      g_lsstat[6] += same && zero && inside;
+      if (it == o->ls_iterations - 1) g_lsstat[7] += 1;
+    }
     LSPoint lo_next = ls_point(d, c, lo.alpha - lo.deriv_0 / lo.deriv_1, jv, qg);
     LSPoint hi_next = ls_point(d, c, hi.alpha - hi.deriv_0 / hi.deriv_1, jv, qg);
     LSPoint mid = ls_point(d, c, (real)0.5 * (lo.alpha + hi.alpha), jv, qg);
@@ -1505,7 +1536,12 @@ int SUF(zbo_reward_inputs)(int n_envs, const real* qpos, const real* xpos, const
 
 int SUF(zbo_sizeof_data)(void) { return (int)sizeof(ZboData); }
 
+/* bit 0: contact rows applied matrix-free like the CUDA kernel; bit 1: the line search stops once a bracket end sits on an exactly
+ * zero derivative (experiment); bit 2: collect line-search statistics (single-threaded) */
 void SUF(zbo_set_variant)(int v) { g_variant = v; }
+void SUF(zbo_lsstats_get)(double* out, int reset) {
+  for (int k = 0; k < 8; k++) { out[k] = g_lsstat[k]; if (reset) g_lsstat[k] = 0; }
+}
 
 #if !ZBO_F64
 /* flop counters (meaningful only in the -DZBO_COUNT build, single-threaded) */

@@ -268,6 +268,12 @@ class Oracle:
         """bit 0: contact rows applied matrix-free like the CUDA kernel (diagnostics)."""
         getattr(self.lib, "zbo_set_variant" + self.suf)(int(v))
 
+    def lsstats(self, reset: bool = True):
+        """Line-search statistics collected with set_variant(4) (single-threaded runs), see zb_oracle.c."""
+        buf = (ctypes.c_double * 8)()
+        getattr(self.lib, "zbo_lsstats_get" + self.suf)(buf, int(reset))
+        return list(buf)
+
     # ---- flop counters (count build only) ------------------------------------------------
     def flops_reset(self):
         self.lib.zbo_flops_reset()
