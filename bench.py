@@ -269,7 +269,7 @@ def main():
         ctrl_step(t, actions[t])
         ev[i][1].record()
         ev[i][2].record()
-        n_done += done.sum()
+        n_done += (done != 0).sum()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -35,7 +35,10 @@ extern "C" {
 #define ZB_NBOX 2         /* foot collision boxes vs. the floor plane         */
 #define ZB_MAXCON 8       /* 4 manifold slots per foot box (MJX plane_convex) */
 #define ZB_NEFC_CON (4 * ZB_MAXCON) /* pyramidal condim-3 rows                */
-#define ZB_NTRACE 128     /* solver_trace floats per environment              */
+#define ZB_NTRACE 160     /* solver_trace floats per environment              */
+#define ZB_TRACE_POINTS 32  /* first index of the line-search points in solver_trace */
+#define ZB_TRACE_SEARCH 128 /* first index of the first search direction        */
+#define ZB_TRACE_START 154  /* start point of the solve: 1 qacc_warmstart, 2 qacc_smooth */
 #define ZB_NSENSORDATA 18 /* quat4 acc3 gyro3 touchL touchR forceL3 forceR3   */
 #define ZB_NCOMMAND 7     /* commands["zero_command"], train.py:416-427       */
 #define ZB_NACTOR_OBS 50  /* NUM_ACTOR_INPUTS, train.py:31-38, 53             */
@@ -215,7 +218,10 @@ typedef struct ZbOut {
   int32_t* contact_mask;  /* [N] bit c set <=> contact slot c active (dist < margin)    */
   int32_t* solver_niter;  /* [N]                                                         */
   int32_t* flags;         /* [N] bit0: non-finite state detected                         */
-  float* solver_trace;    /* [N, ZB_NTRACE] diagnostics: per solver iteration i (alpha, cost, ls_iters, |search|) at 4i; from 32 on the (alpha, d0, d1) of every point the FIRST line search evaluates */
+  float* solver_trace;    /* [N, ZB_NTRACE] diagnostics of the LAST substep: per solver iteration i (alpha, cost, ls_iters, |search|) at 4i;
+                           * from ZB_TRACE_POINTS on the (alpha, d0, d1) of every point the FIRST line search evaluates (p0, newton(p0), then
+                           * lo_next / hi_next / mid per bracket iteration); from ZB_TRACE_SEARCH on the first search direction by dof;
+                           * [ZB_TRACE_START] the start point the solve picked */
 } ZbOut;
 
 /* Observation epilogue: the two network input vectors of the reference, assembled by the step /
@@ -265,8 +271,9 @@ typedef struct ZbAutoResetArgs {
   const float* reset_qpos;  /* [N, ZB_NQ] */
   const float* reset_qvel;  /* [N, ZB_NV] */
   const float* reset_t_rem; /* [N] or NULL */
-  uint8_t* done_out;        /* [N] or NULL */
+  uint8_t* done_out;        /* [N] or NULL: 0 = running, 1 = terminated (bad z / not upright / non-finite), 2 = episode length reached */
   float z_lo, z_hi, max_tilt_rad;
+  float max_episode_sec;    /* ksim.EpisodeLengthTermination(max_length_sec), train.py:1592: time > max ends the episode; <= 0 disables */
 } ZbAutoResetArgs;
 
 typedef struct ZbEngine ZbEngine; /* opaque: device copy of ZbModel + ZbOpts */
@@ -285,16 +292,17 @@ int zb_step_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, 
                 int n_envs, int n_substeps);
 
 /* zb_step_f32 followed, inside the same launch, by the rollout's termination check and partial reset
- * (ksim RLTask._single_unroll: `done -> engine.reset`, BadZTermination / NotUprightTermination of
+ * (ksim RLTask._single_unroll: `done -> engine.reset`; BadZTermination / NotUprightTermination / EpisodeLengthTermination of
  * /root/reference/train.py:1588-1593): for every environment whose integrated state terminates
- * (z outside [z_lo, z_hi], base tilt above max_tilt_rad, or non-finite), the state is replaced by
+ * (z outside [z_lo, z_hi], base tilt above max_tilt_rad, non-finite, or time > max_episode_sec when that is > 0), the state is replaced by
  * reset_qpos/reset_qvel/reset_t_rem (host-sampled per ksim resets, train.py:1471-1476), PlannerState re-initialised
  * (train.py:1293-1298), time/warm-start cleared and forward() run on it — exactly zb_terminations_f32 +
- * zb_reset_f32(done).  done_out [N] (may be NULL) receives the termination mask. */
+ * zb_reset_f32(done).  done_out [N] (may be NULL) receives the termination mask (0 running, 1 failure, 2 episode length — ksim's
+ * terminations return -1 / +1 for failure / success, `done` is "non-zero"). */
 int zb_step_autoreset_f32(ZbEngine* engine, void* cuda_stream, const ZbEnvParams* params, const ZbState* state,
                           const float* action, const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs,
                           int n_substeps, const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem,
-                          uint8_t* done_out, float z_lo, float z_hi, float max_tilt_rad);
+                          uint8_t* done_out, float z_lo, float z_hi, float max_tilt_rad, float max_episode_sec);
 
 /* zb_step_f32 / zb_step_autoreset_f32 (autoreset != NULL) with the observation epilogue: ONE launch per control step produces
  * the next state, the mjx.Data outputs, the termination mask, the partial reset and both network input vectors. */
@@ -331,11 +339,12 @@ int zb_cta_shape(int n_envs, int num_sms, int* wide, int* warps_per_cta);
 /* Number of kernel launches issued through this library since load (bench accounting). */
 long long zb_launch_count(void);
 
-/* ksim.BadZTermination(z_lo, z_hi) | ksim.NotUprightTermination(max_tilt) as the task configures them
- * (/root/reference/train.py:1588-1593) plus the non-finite guard (flags from ZbOut, may be NULL): done[i] = 1 when
- * environment i terminates.  Feeds zb_reset_f32's done mask without a host round trip. */
-int zb_terminations_f32(void* cuda_stream, const float* qpos, const int32_t* flags, uint8_t* done, int n_envs, float z_lo,
-                        float z_hi, float max_tilt_rad);
+/* ksim.BadZTermination(z_lo, z_hi) | ksim.NotUprightTermination(max_tilt) | ksim.EpisodeLengthTermination(max_episode_sec) as the
+ * task configures them (/root/reference/train.py:1588-1593) plus the non-finite guard (flags from ZbOut, may be NULL):
+ * done[i] = 1 when environment i fails, 2 when only its episode length ran out (time [N] may be NULL / max_episode_sec <= 0: no
+ * episode-length check), 0 otherwise.  Feeds zb_reset_f32's done mask without a host round trip. */
+int zb_terminations_f32(void* cuda_stream, const float* qpos, const int32_t* flags, const float* time, uint8_t* done, int n_envs,
+                        float z_lo, float z_hi, float max_tilt_rad, float max_episode_sec);
 
 /* FeetAirtimeReward.get_reward_stateful over one rollout chunk (/root/reference/train.py:503-546), raw
  * (before ksim's `scale`), with stand_still_threshold = None as the task configures it (train.py:1560-1565):

@@ -21,9 +21,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # Mutation builds (tests/test_parity_tail.py): each plants ONE bug in a rarely taken path of the step kernel; the parity
 # checks must turn red on every one of them ("make the parity tests able to fail on a tail bug").
 MUTANTS = {
-    "mut1": ["-DZB_MUTANT=1"],  # wrong sign on the second tangent of manifold slot 3 (only 4-contact feet are affected)
+    "mut1": ["-DZB_MUTANT=1"],  # wrong sign on the second tangent of manifold slot 2 (only feet with three contact points are affected)
     "mut2": ["-DZB_MUTANT=2"],  # the line search's full re-summation hands the wrong active set to a swapped bracket end
     "mut3": ["-DZB_MUTANT=3"],  # joint-limit rows drop out of the line search's zone test
+    "mut4": ["-DZB_MUTANT=4"],  # one-sided loop (production instantiations only): the moved bracket end written back to the wrong side
 }
 
 

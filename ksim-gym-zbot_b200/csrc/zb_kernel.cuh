@@ -38,9 +38,12 @@
 #define ZB_WPB_WIDE 28 /* throughput profile: 28 warps per 896-thread CTA at 72 registers (spills, but 4096 envs fit ONE wave of 148 SMs) */
 #endif
 #ifndef ZB_CTA_LOCKSTEP
-#define ZB_CTA_LOCKSTEP 1 /* 1: the warps of a CTA meet at every substep (shared instruction fetch: +30 %); 2: also before every solver pass (measured slower: waits for the slowest line search) */
+#define ZB_CTA_LOCKSTEP 1 /* 1: the warps of a CTA meet at every substep (shared instruction fetch: +30 %).  (A barrier before every solver pass as well was measured slower — it waits for the slowest line search — and has been removed.) */
 #endif
 #define ZB_SCR 8     /* scratch floats per lane */
+#ifndef ZB_MUTANT
+#define ZB_MUTANT 0 /* mutation builds (build.py MUTANTS): one planted bug each, the parity tests must catch every one */
+#endif
 #ifndef ZB_LS_SAME
 #define ZB_LS_SAME 2 /* line search: 1 = no zone evaluation while both bracket ends share one active set, 2 = + the one-sided loop (see linesearch) */
 #endif
@@ -99,9 +102,8 @@ struct LSSet {          // an active set of the line search: its summed quadrati
 };
 
 // TRACE: compile the solver-trace diagnostics in (scripts/gpu_probe*.py); the production instantiation carries none of it.
-// LOCK: CTA-lockstep barriers (see solve_all).
 // FSM: the factor and the mass-matrix rows of a lane live in shared memory (throughput profile) instead of registers.
-template <bool TRACE, bool LOCK, bool FSM>
+template <bool TRACE, bool FSM>
 struct WarpEnv {
   const ZbDev* D;
   ZbOpts o;           // by value from the kernel parameters: uniform-datapath registers, provably warp-uniform control flow
@@ -865,7 +867,8 @@ struct WarpEnv {
       const float dist = cdist - D->con_includemargin[g];
       c_on = dist < 0.f;
       const int e = L & 3;
-      const float sgn = (e & 1) ? -1.f : 1.f;
+      float sgn = (e & 1) ? -1.f : 1.f;
+      if (ZB_MUTANT == 1 && ((L >> 2) & 3) == 2 && e == 3) sgn = 1.f;  // (mutant 1: manifold slot 2 loses a facet of its friction pyramid)
       const float* fr = D->frame;
       const float* tt = fr + 3 * (1 + (e >> 1));
       const float dir[3] = {fr[0] + sgn * cmu * tt[0], fr[1] + sgn * cmu * tt[1], fr[2] + sgn * cmu * tt[2]};
@@ -940,7 +943,7 @@ struct WarpEnv {
       z |= (x <= -fr_rf) ? 1 : 0;
       z |= (x >= fr_rf) ? 2 : 0;
     }
-    if (any_limit && lm_on && (lm_ja + a * r.lm_jv) < 0.f) z |= 4;
+    if (ZB_MUTANT != 3 && any_limit && lm_on && (lm_ja + a * r.lm_jv) < 0.f) z |= 4;  // (mutant 3: limit rows invisible to the line search)
     if (c_on && (c_ja + a * r.c_jv) < 0.f) z |= 8;
     return z;
   }
@@ -1036,6 +1039,7 @@ struct WarpEnv {
     zz[0] = zone_at(r, al[0]);
     ls_eval<1>(r, al, zz, pt, st);  // lo = point(newton(p0)); order the bracket
     if (pt[0].d0 < p0.d0) { lo = pt[0]; Slo = st[0]; hi = p0; Shi = S0; } else { hi = pt[0]; Shi = st[0]; lo = p0; Slo = S0; }
+    if (TRACE && trace && niter == 0 && hasdof) trace[ZB_TRACE_SEARCH + dof] = search;
     if (TRACE && trace && niter == 0 && L == 0) {
       trace[32] = p0.alpha; trace[33] = p0.d0; trace[34] = S0.d1; trace[35] = pt[0].alpha; trace[36] = pt[0].d0; trace[37] = st[0].d1;
       lscount = 2;
@@ -1092,6 +1096,7 @@ struct WarpEnv {
             it++;
           }
           if (mhi) { hi.alpha = Ma_; hi.d0 = Md; Shi.t0 = m0; Shi.t1 = m1; Shi.t2 = m2; Shi.d1 = md1; }
+          else if (ZB_MUTANT == 4) { hi.alpha = Ma_; hi.d0 = Md; }  // (mutant 4: the moved end is written back to the wrong side)
           else { lo.alpha = Ma_; lo.d0 = Md; }
         }
       }
@@ -1157,7 +1162,7 @@ struct WarpEnv {
         const bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) { lo = hi_next; Slo = st[1]; }
         const bool s4 = in_bracket(hi.d0, hi_next.d0); if (s4) { hi = hi_next; Shi = st[1]; }
         const bool s5 = in_bracket(hi.d0, mid.d0); if (s5) { hi = mid; Shi = st[2]; }
-        const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) { hi = lo_next; Shi = st[0]; }
+        const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) { hi = lo_next; Shi = st[ZB_MUTANT == 2 ? 1 : 0]; }  // (mutant 2: wrong active set)
         swap = s1 | s2 | s3 | s4 | s5 | s6;
 #if ZB_LS_SAME
         same = !__any_sync(ZB_FULL, Slo.z != Shi.z);
@@ -1165,7 +1170,7 @@ struct WarpEnv {
       }
       if (TRACE && trace && niter == 0 && L == 0) {
         for (int j = 0; j < 3; j++)
-          if (32 + 3 * lscount + 2 < ZB_NTRACE) {
+          if (32 + 3 * lscount + 2 < ZB_TRACE_SEARCH) {
             trace[32 + 3 * lscount] = pt[j].alpha; trace[32 + 3 * lscount + 1] = pt[j].d0; trace[32 + 3 * lscount + 2] = st[j].d1;
             lscount++;
           }
@@ -1274,15 +1279,9 @@ struct WarpEnv {
     float v = 0.f, cost_s = 0.f, qa_int = 0.f, pg = 0.f, pMg = 0.f;
     cost = 0.f; prev_cost = 0.f; niter = 0; lscount = 0;
     qacc = 0.f; Ma = 0.f; fr_ja = lm_ja = c_ja = 0.f; qfrc_c = 0.f; grad = 0.f; Mgrad = 0.f; search = 0.f; mv = 0.f; gauss = 0.f;
-    // LOCK: the warps of a CTA meet at a barrier before every pass (solver iteration).  They then stream the same
-    // instructions and share I-cache lines (instruction fetch was the top stall); a warp whose solve has finished keeps
-    // arriving at the barrier until the slowest one is done (it would wait for it at the next substep barrier anyway).
     bool finished = false;
 #pragma unroll 1
-    while (true) {
-      if (LOCK) { if (__syncthreads_and(finished)) break; }
-      else if (finished) break;
-      if (finished) continue;
+    while (!finished) {
       float fr_force = 0.f, lm_force = 0.f, c_force = 0.f;  // row forces of THIS pass
       if (phase >= 0 && phase < 99) {
         // ---- operator application: mv = M v, contact rows J v ----
@@ -1336,7 +1335,10 @@ struct WarpEnv {
       // ---- transitions ----
       if (phase == -1) { qacc_smooth = x; v = x; phase = o.warmstart ? 0 : 2; continue; }
       if (phase == 0) { cost_s = cost; v = warm; phase = 1; continue; }
-      if (phase == 1) { v = __all_sync(ZB_FULL, cost < cost_s) ? warm : qacc_smooth; warm = 0.f; /* dead from here on: frees its register for the iterations */ phase = 2; continue; }
+      if (phase == 1) {
+        const bool pick_warm = __all_sync(ZB_FULL, cost < cost_s);
+        if (TRACE && trace && L == 0) trace[ZB_TRACE_START] = pick_warm ? 1.f : 2.f;
+        v = pick_warm ? warm : qacc_smooth; warm = 0.f; /* dead from here on: frees its register for the iterations */ phase = 2; continue; }
       if (phase == 99) { qa_int = x; finished = true; continue; }
       Mgrad = x;
       float gnorm2;

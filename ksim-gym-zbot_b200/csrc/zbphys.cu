@@ -15,13 +15,13 @@
 #include "../../include/zbphys.h"
 #include "zb_kernel.cuh"
 
-#define ZB_ABI_VERSION 3
+#define ZB_ABI_VERSION 4
 #define ZB_FSM_BYTES_PER_WARP (31 * 32 * 4) /* WarpEnv::F_N floats per lane */
 
 // auto-reset pass of the step kernel (zb_step_autoreset_f32)
 struct ZbAutoReset {
   int enabled;
-  float z_lo, z_hi, cos_tilt;
+  float z_lo, z_hi, cos_tilt, max_time;
   const float *reset_qpos, *reset_qvel, *reset_t_rem;
   uint8_t* done_out;
 };
@@ -58,6 +58,19 @@ static CtaShape shape_policy(int n_envs, int sms, int force_wpb, bool wide_avail
   return {true, w};
 }
 static CtaShape pick_shape(const ZbEngine* e, int n_envs, bool wide_available) { return shape_policy(n_envs, e->num_sms, e->force_wpb, wide_available); }
+
+// Launches go to the engine's device whatever the caller's current device is (an engine on device k used from a thread whose
+// current device is another one launched on the wrong GPU).  The stream handed in must belong to the engine's device.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -108,7 +121,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   // throughput profile: factor + mass-matrix rows of every lane in (dynamic) shared memory, 31 x 128 B per warp
   constexpr bool FSM = WPB > ZB_WPB;
   extern __shared__ float dyn_smem[];
-  WarpEnv<TRACE, (ZB_CTA_LOCKSTEP >= 2) && MODE == ZB_MODE_STEP, FSM> E;
+  WarpEnv<TRACE, FSM> E;
   E.init_topology(D, o, meaninertia, scratch[wib], L);
   E.fsm = FSM ? dyn_smem + (size_t)wib * (32 * 31) + L : nullptr;
   const int b = E.isbody ? L : 0;
@@ -182,8 +195,9 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
       const bool nonfinite = !(isfinite(E.q) && isfinite(E.qv) && isfinite(E.bq[0]) && isfinite(E.bq[1]) && isfinite(E.bq[2]) && isfinite(E.bq[3]));
       bool bad = (E.bq[2] < AR.z_lo) || (E.bq[2] > AR.z_hi) || (up < AR.cos_tilt) || !isfinite(E.bq[2]) || !isfinite(up);
       bad = __any_sync(ZB_FULL, bad || nonfinite);
-      if (L == 0 && AR.done_out) AR.done_out[env] = bad ? 1 : 0;
-      if (!bad) break;
+      const bool timeout = __all_sync(ZB_FULL, AR.max_time > 0.f && tm > AR.max_time);  // EpisodeLengthTermination, train.py:1592
+      if (L == 0 && AR.done_out) AR.done_out[env] = bad ? 1 : (timeout ? 2 : 0);
+      if (!(bad || timeout)) break;
       reinit = true;
 #pragma unroll
       for (int k = 0; k < 7; k++) E.bq[k] = AR.reset_qpos[(size_t)env * NQ + k];
@@ -334,9 +348,10 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   }
 }
 
-// ksim BadZTermination + NotUprightTermination as configured at train.py:1588-1593 (+ non-finite guard), one thread per env.
-__global__ void zb_term_kernel(const float* __restrict__ qpos, const int32_t* __restrict__ flags, uint8_t* __restrict__ done,
-                               int n_envs, float z_lo, float z_hi, float cos_tilt) {
+// ksim BadZTermination + NotUprightTermination + EpisodeLengthTermination as configured at train.py:1588-1593 (+ non-finite guard),
+// one thread per env.
+__global__ void zb_term_kernel(const float* __restrict__ qpos, const int32_t* __restrict__ flags, const float* __restrict__ time,
+                               uint8_t* __restrict__ done, int n_envs, float z_lo, float z_hi, float cos_tilt, float max_time) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_envs) return;
   const float* q = qpos + (size_t)i * NQ;
@@ -344,7 +359,8 @@ __global__ void zb_term_kernel(const float* __restrict__ qpos, const int32_t* __
   const float up = w * w - x * x - y * y + zz * zz;  // R[2][2]: world z-axis component of the base z-axis
   bool bad = (z < z_lo) || (z > z_hi) || (up < cos_tilt) || !isfinite(z) || !isfinite(up);
   if (flags) bad = bad || flags[i] != 0;
-  done[i] = bad ? 1 : 0;
+  const bool timeout = time && max_time > 0.f && time[i] > max_time;
+  done[i] = bad ? 1 : (timeout ? 2 : 0);
 }
 
 // FeetAirtimeReward.get_reward_stateful of one rollout chunk (train.py:503-546), one thread per environment.
@@ -642,6 +658,7 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   int rc = check_state(state);
   if (rc) return rc;
   if (n_envs == 0) return ZB_OK;
+  DeviceGuard guard(e->device);
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   ZbObs OB; memset(&OB, 0, sizeof(OB)); if (obs) OB = *obs;
@@ -650,9 +667,10 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   const int wpb = cs.wpb, grid = (n_envs + wpb - 1) / wpb;
 #define ZB_LAUNCH_STEP(TR, OBSV, W) zb_kernel<ZB_MODE_STEP, TR, OBSV, W><<<grid, wpb * 32, (W > ZB_WPB) ? (size_t)wpb * ZB_FSM_BYTES_PER_WARP : 0, (cudaStream_t)stream>>>( \
     e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR, OB)
-#ifdef ZB_MINIMAL  // development / mutation builds: only the plain step (both register profiles) and the plain reset are compiled
-  if (O.solver_trace || with_obs) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no trace / observation instantiations%s");
-  if (cs.wide) ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB);
+#ifdef ZB_MINIMAL  // development / mutation builds: only the plain step (both register profiles, + trace) and the plain reset are compiled
+  if (with_obs) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no observation instantiations%s");
+  if (O.solver_trace) ZB_LAUNCH_STEP(true, false, ZB_WPB);
+  else if (cs.wide) ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB);
 #else
   if (O.solver_trace) { if (with_obs) ZB_LAUNCH_STEP(true, true, ZB_WPB); else ZB_LAUNCH_STEP(true, false, ZB_WPB); }
   else if (cs.wide) { if (with_obs) ZB_LAUNCH_STEP(false, true, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); }
@@ -672,10 +690,11 @@ int zb_step_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbSt
 int zb_step_autoreset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
                           const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps,
                           const float* reset_qpos, const float* reset_qvel, const float* reset_t_rem, uint8_t* done_out,
-                          float z_lo, float z_hi, float max_tilt_rad) {
+                          float z_lo, float z_hi, float max_tilt_rad, float max_episode_sec) {
   if (!reset_qpos || !reset_qvel) return fail(ZB_EINVAL, "zb_step_autoreset_f32: null reset_qpos/reset_qvel%s");
+  if (max_episode_sec > 0 && state && !state->time) return fail(ZB_EINVAL, "zb_step_autoreset_f32: max_episode_sec needs ZbState.time%s");
   ZbAutoReset AR;
-  AR.enabled = 1; AR.z_lo = z_lo; AR.z_hi = z_hi; AR.cos_tilt = cosf(max_tilt_rad);
+  AR.enabled = 1; AR.z_lo = z_lo; AR.z_hi = z_hi; AR.cos_tilt = cosf(max_tilt_rad); AR.max_time = max_episode_sec;
   AR.reset_qpos = reset_qpos; AR.reset_qvel = reset_qvel; AR.reset_t_rem = reset_t_rem; AR.done_out = done_out;
   return step_impl(e, stream, params, state, action, push_rand, push_per_substep, out, n_envs, n_substeps, AR);
 }
@@ -686,6 +705,7 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   int rc = check_state(state);
   if (rc) return rc;
   if (n_envs == 0) return ZB_OK;
+  DeviceGuard guard(e->device);
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int wpb = pick_shape(e, n_envs, false).wpb, grid = (n_envs + wpb - 1) / wpb;
@@ -715,6 +735,7 @@ static int reset_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, cons
   int rc = check_state(state);
   if (rc) return rc;
   if (n_envs == 0) return ZB_OK;
+  DeviceGuard guard(e->device);
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   ZbObs OB; memset(&OB, 0, sizeof(OB)); if (obs) OB = *obs;
@@ -755,17 +776,18 @@ int zb_step_obs_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const 
   memset(&AR, 0, sizeof(AR));
   if (ar) {
     if (!ar->reset_qpos || !ar->reset_qvel) return fail(ZB_EINVAL, "zb_step_obs_f32: null reset_qpos/reset_qvel%s");
-    AR.enabled = 1; AR.z_lo = ar->z_lo; AR.z_hi = ar->z_hi; AR.cos_tilt = cosf(ar->max_tilt_rad);
+    if (ar->max_episode_sec > 0 && state && !state->time) return fail(ZB_EINVAL, "zb_step_obs_f32: max_episode_sec needs ZbState.time%s");
+    AR.enabled = 1; AR.z_lo = ar->z_lo; AR.z_hi = ar->z_hi; AR.cos_tilt = cosf(ar->max_tilt_rad); AR.max_time = ar->max_episode_sec;
     AR.reset_qpos = ar->reset_qpos; AR.reset_qvel = ar->reset_qvel; AR.reset_t_rem = ar->reset_t_rem; AR.done_out = ar->done_out;
   }
   return step_impl(e, stream, params, state, action, push_rand, push_per_substep, out, n_envs, n_substeps, AR, obs);
 }
 
-int zb_terminations_f32(void* stream, const float* qpos, const int32_t* flags, uint8_t* done, int n_envs, float z_lo,
-                        float z_hi, float max_tilt_rad) {
+int zb_terminations_f32(void* stream, const float* qpos, const int32_t* flags, const float* time, uint8_t* done, int n_envs, float z_lo,
+                        float z_hi, float max_tilt_rad, float max_episode_sec) {
   if (!qpos || !done || n_envs < 0) return fail(ZB_EINVAL, "zb_terminations_f32: bad argument%s");
   if (n_envs == 0) return ZB_OK;
-  zb_term_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(qpos, flags, done, n_envs, z_lo, z_hi, cosf(max_tilt_rad));
+  zb_term_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(qpos, flags, time, done, n_envs, z_lo, z_hi, cosf(max_tilt_rad), max_episode_sec);
   return after_launch("zb_terminations_f32 launch: %s");
 }
 

@@ -63,7 +63,11 @@ NUM_ACTOR_INPUTS, NUM_CRITIC_INPUTS, NUM_COMMANDS = 50, 484, 7  # train.py:53-54
 
 class ZbAutoResetArgs(ctypes.Structure):
     _fields_ = [("reset_qpos", ctypes.c_void_p), ("reset_qvel", ctypes.c_void_p), ("reset_t_rem", ctypes.c_void_p),
-                ("done_out", ctypes.c_void_p), ("z_lo", ctypes.c_float), ("z_hi", ctypes.c_float), ("max_tilt_rad", ctypes.c_float)]
+                ("done_out", ctypes.c_void_p), ("z_lo", ctypes.c_float), ("z_hi", ctypes.c_float), ("max_tilt_rad", ctypes.c_float),
+                ("max_episode_sec", ctypes.c_float)]
+
+
+MAX_EPISODE_SEC = 80.0  # ksim.EpisodeLengthTermination(max_length_sec=80), train.py:1592
 
 
 ZB_OK, ZB_EINVAL, ZB_ENODEV, ZB_ECUDA, ZB_EUNSUP = 0, -1, -2, -3, -4
@@ -99,7 +103,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.zb_step_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     lib.zb_step_autoreset_f32.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + \
-        [ctypes.c_void_p] * 4 + [ctypes.c_float] * 3
+        [ctypes.c_void_p] * 4 + [ctypes.c_float] * 4
     lib.zb_step_obs_f32.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.zb_reset_obs_f32.argtypes = [ctypes.c_void_p] * 10 + [ctypes.c_int]
     LL = ctypes.c_longlong
@@ -108,8 +112,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.zb_forward_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     lib.zb_reset_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
-    lib.zb_terminations_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
-                                        ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    lib.zb_terminations_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]
     lib.zb_bench_ffma.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     assert lib.zb_sizeof_model() == ctypes.sizeof(M.ZbModel), "ZbModel layout mismatch between model.py and zbphys.h"
     assert lib.zb_sizeof_opts() == ctypes.sizeof(M.ZbOpts), "ZbOpts layout mismatch between model.py and zbphys.h"
@@ -280,7 +284,7 @@ class ZbotCudaEngine:
         rc = self.lib.zb_engine_create(ctypes.byref(model), ctypes.byref(self.opts), self.device.index or 0, ctypes.byref(handle))
         self._check(rc)
         self._h = handle
-        self.trace: torch.Tensor | None = None  # set to a [N, 64] float32 CUDA tensor to record the solver trace
+        self.trace: torch.Tensor | None = None  # set to a [N, ZB_NTRACE = 160] float32 CUDA tensor to record the solver trace
         self._default_qpos = torch.tensor(M.default_qpos(model), dtype=torch.float32, device=self.device)
 
     # ---- plumbing ------------------------------------------------------------------------
@@ -392,12 +396,20 @@ class ZbotCudaEngine:
         ps = physics_state if physics_state is not None else self.new_state()
         n = ps.data.qpos.shape[0]
         if reset_qpos is None:
-            reset_qpos, reset_qvel, t = self.sample_reset(n, physics_model)
+            reset_qpos, rv_, t = self.sample_reset(n, physics_model)
+            reset_qvel = rv_ if reset_qvel is None else reset_qvel
             reset_t_rem = t if reset_t_rem is None else reset_t_rem
+        if reset_qvel is None:
+            reset_qvel = torch.zeros((n, M.NV), device=self.device)
+        if reset_t_rem is None:  # a PushEvent timer of 0 would fire in the very first substep: sample it (ksim: U(interval_range)) or park it
+            if self.push is not None:
+                lo, hi = self.push.interval_range
+                reset_t_rem = lo + (hi - lo) * torch.rand((n,), generator=self.gen, device=self.device)
+            else:
+                reset_t_rem = torch.full((n,), 1e30, device=self.device)
         reset_qpos = reset_qpos.to(self.device, torch.float32).contiguous()
         reset_qvel = reset_qvel.to(self.device, torch.float32).contiguous()
-        if reset_t_rem is not None:
-            reset_t_rem = reset_t_rem.to(self.device, torch.float32).contiguous()
+        reset_t_rem = reset_t_rem.to(self.device, torch.float32).contiguous()
         dn = None
         if done is not None:
             dn = done.to(self.device, torch.uint8).contiguous()
@@ -422,7 +434,7 @@ class ZbotCudaEngine:
             if new_lat is not None:
                 ps.action_latency = new_lat
         else:
-            ps.most_recent_action[:] = torch.where(dn.bool()[:, None], ps.data.qpos[:, 7:], ps.most_recent_action)
+            torch.where(dn.bool()[:, None], ps.data.qpos[:, 7:], ps.most_recent_action, out=ps.most_recent_action)
             if new_lat is not None:
                 ps.action_latency = torch.where(dn.bool(), new_lat, ps.action_latency)
         return ps
@@ -432,7 +444,7 @@ class ZbotCudaEngine:
              n_substeps: int | None = None, auto_reset: tuple | None = None, done_out: torch.Tensor | None = None,
              z_lo: float = 0.05, z_hi: float = 0.5, max_tilt: float = math.radians(60), obs: Observations | None = None,
              command: torch.Tensor | None = None, reset_imu_lag: torch.Tensor | None = None,
-             obs_noise: tuple | None = None) -> PhysicsState:
+             obs_noise: tuple | None = None, max_episode_sec: float = MAX_EPISODE_SEC) -> PhysicsState:
         """MjxEngine.step: one control step = ``phys_steps_per_ctrl_steps`` fused physics substeps (in place).
 
         ``auto_reset=(reset_qpos, reset_qvel, reset_t_rem)`` folds the rollout's termination check + partial reset
@@ -453,7 +465,7 @@ class ZbotCudaEngine:
             lat = EnvParams.__new__(EnvParams)
             lat.n_envs = n
             lat.tensors = dict(physics_model.tensors) if physics_model is not None else {}
-            lat.tensors["prev_action"] = ps.most_recent_action.contiguous()
+            lat.tensors["prev_action"] = ps.most_recent_action  # (the launch reads it before the stream-ordered update below)
             lat.tensors["latency_steps"] = torch.round(ps.action_latency / self.dt).to(torch.int32).contiguous()
             physics_model = lat
         per_substep = 0
@@ -472,7 +484,7 @@ class ZbotCudaEngine:
                 for t in (rq, rv) + ((rt,) if rt is not None else ()):
                     assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
                 ar = ZbAutoResetArgs(rq.data_ptr(), rv.data_ptr(), None if rt is None else rt.data_ptr(),
-                                     None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt)
+                                     None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt, max_episode_sec)
                 if reset_imu_lag is None:
                     reset_imu_lag = self.sample_imu_lag(n, obs.lag_range)
             nq, na = obs_noise if obs_noise is not None else (None, None)
@@ -491,13 +503,13 @@ class ZbotCudaEngine:
                 self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st), ctypes.c_void_p(action.data_ptr()), pr,
                 per_substep, ctypes.byref(out), n, S, ctypes.c_void_p(rq.data_ptr()), ctypes.c_void_p(rv.data_ptr()),
                 None if rt is None else ctypes.c_void_p(rt.data_ptr()),
-                None if done_out is None else ctypes.c_void_p(done_out.data_ptr()), z_lo, z_hi, max_tilt)
+                None if done_out is None else ctypes.c_void_p(done_out.data_ptr()), z_lo, z_hi, max_tilt, max_episode_sec)
         self._check(rc)
-        ps.most_recent_action = action
+        ps.most_recent_action.copy_(action)  # engine-owned buffer: never alias the caller's action tensor
         if auto_reset is not None and done_out is not None and self.action_latency_range[1] > 0:
             # reset environments restart from the default action (get_default_action, train.py:1282-1283) with a fresh latency
             dn = done_out.bool()
-            ps.most_recent_action = torch.where(dn[:, None], ps.data.qpos[:, 7:], action).contiguous()
+            torch.where(dn[:, None], ps.data.qpos[:, 7:], ps.most_recent_action, out=ps.most_recent_action)
             lo_, hi_ = self.action_latency_range
             ps.action_latency = torch.where(dn, lo_ + (hi_ - lo_) * torch.rand((n,), generator=self.gen, device=self.device), ps.action_latency)
         return ps
@@ -505,7 +517,8 @@ class ZbotCudaEngine:
     def plan_step(self, physics_state: PhysicsState, physics_model: EnvParams | None = None, n_substeps: int | None = None,
                   auto_reset: tuple | None = None, done_out: torch.Tensor | None = None, z_lo: float = 0.05, z_hi: float = 0.5,
                   max_tilt: float = math.radians(60), obs: Observations | None = None, command: torch.Tensor | None = None,
-                  reset_imu_lag: torch.Tensor | None = None, obs_noise: tuple | None = None, push_per_substep: bool = False):
+                  reset_imu_lag: torch.Tensor | None = None, obs_noise: tuple | None = None, push_per_substep: bool = False,
+                  max_episode_sec: float = MAX_EPISODE_SEC, track_action: bool = True):
         """Pre-bind one control step: all argument structs of the C call are built once, the returned function
         ``run(action, push_rand=None)`` only passes the two pointers that change per step and enqueues the launch on the
         current stream (what an XLA custom call does with its operand buffers; ~10x less host time per step than ``step``).
@@ -526,7 +539,7 @@ class ZbotCudaEngine:
         if auto_reset is not None:
             rq, rv, rt = auto_reset
             ar = ZbAutoResetArgs(rq.data_ptr(), rv.data_ptr(), None if rt is None else rt.data_ptr(),
-                                 None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt)
+                                 None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt, max_episode_sec)
             keep.append(ar)
         if obs is not None:
             if auto_reset is not None and reset_imu_lag is None:
@@ -545,7 +558,7 @@ class ZbotCudaEngine:
 
             def call(stream, a_ptr, pr_ptr):
                 return fn(h, stream, p_params, p_st, a_ptr, pr_ptr, pps, p_out, n, S, ar.reset_qpos, ar.reset_qvel, ar.reset_t_rem, ar.done_out,
-                          z_lo, z_hi, max_tilt)
+                          z_lo, z_hi, max_tilt, max_episode_sec)
         else:
             fn = lib.zb_step_f32
 
@@ -557,7 +570,8 @@ class ZbotCudaEngine:
             rc = call(current_stream(dev).cuda_stream, action.data_ptr(), None if push_rand is None else push_rand.data_ptr())
             if rc != ZB_OK:
                 check(rc)
-            ps.most_recent_action = action
+            if track_action:  # (a device-to-device copy of 80 B per environment; track_action=False when the caller keeps the action)
+                ps.most_recent_action.copy_(action)
 
         return run
 
@@ -571,14 +585,15 @@ class ZbotCudaEngine:
         return ps
 
     def terminations(self, physics_state: PhysicsState, done: torch.Tensor | None = None, z_lo: float = 0.05,
-                     z_hi: float = 0.5, max_tilt: float = math.radians(60)) -> torch.Tensor:
-        """BadZTermination | NotUprightTermination (train.py:1588-1593) as one kernel; returns a uint8 [N] mask."""
+                     z_hi: float = 0.5, max_tilt: float = math.radians(60), max_episode_sec: float = MAX_EPISODE_SEC) -> torch.Tensor:
+        """BadZTermination | NotUprightTermination | EpisodeLengthTermination (train.py:1588-1593) as one kernel; returns a uint8 [N]
+        mask: 1 = failure, 2 = episode length reached (ksim: -1 / +1), 0 = running."""
         n = physics_state.data.qpos.shape[0]
         if done is None:
             done = torch.empty((n,), dtype=torch.uint8, device=self.device)
         rc = self.lib.zb_terminations_f32(self._stream(), ctypes.c_void_p(physics_state.data.qpos.data_ptr()),
-                                          ctypes.c_void_p(physics_state.data.flags.data_ptr()), ctypes.c_void_p(done.data_ptr()), n,
-                                          z_lo, z_hi, max_tilt)
+                                          ctypes.c_void_p(physics_state.data.flags.data_ptr()), ctypes.c_void_p(physics_state.data.time.data_ptr()),
+                                          ctypes.c_void_p(done.data_ptr()), n, z_lo, z_hi, max_tilt, max_episode_sec)
         self._check(rc)
         return done
 
@@ -608,12 +623,15 @@ def get_physics_engine(model: M.ZbModel, n_envs: int, **kw) -> ZbotCudaEngine:
     return ZbotCudaEngine(model, n_envs, **kw)
 
 
-def terminations(ps: PhysicsState, z_lo: float = 0.05, z_hi: float = 0.5, max_tilt: float = math.radians(60)) -> torch.Tensor:
-    """BadZTermination + NotUprightTermination of train.py:1588-1593 (used by the rollout harness)."""
+def terminations(ps: PhysicsState, z_lo: float = 0.05, z_hi: float = 0.5, max_tilt: float = math.radians(60),
+                 max_episode_sec: float = MAX_EPISODE_SEC) -> torch.Tensor:
+    """BadZTermination + NotUprightTermination + EpisodeLengthTermination of train.py:1588-1593 (used by the rollout harness)."""
     q = ps.data.qpos
     z = q[:, 2]
     w, x, y = q[:, 3], q[:, 4], q[:, 5]
     # z-axis of the base in the world frame: R[2,2] = w^2 - x^2 - y^2 + z^2 = 1 - 2(x^2 + y^2) for unit quats
     up = 1.0 - 2.0 * (x * x + y * y)
     bad = (z < z_lo) | (z > z_hi) | (up < math.cos(max_tilt)) | (ps.data.flags != 0) | ~torch.isfinite(z) | ~torch.isfinite(w)
+    if max_episode_sec > 0:
+        bad = bad | (ps.data.time > max_episode_sec)
     return bad

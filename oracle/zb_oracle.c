@@ -771,7 +771,17 @@ typedef struct {
   real gauss, cost, prev_cost;
   int active[NEFC]; /* quadratic-zone membership (Newton Hessian) */
   int niter;
+  real jascale[NEFC]; /* magnitude of the terms summed into Jaref (verification hooks: how well its sign is determined) */
 } Ctx;
+
+/* ---- verification hooks (zbo_step_follow / zbo_ls_points, see the entry points at the end of the file) ---- */
+typedef struct { int K; const real* alphas; real *d0, *d1, *scale, *margin, *cost, *search_out, *info; } LSQuery;
+static _Thread_local const real* g_follow_trace; /* solver trace of another implementation: take ITS step sizes */
+static _Thread_local int g_follow_niter;
+static _Thread_local int g_force_start;          /* 0: own choice, 1: qacc_warmstart, 2: qacc_smooth */
+static _Thread_local real* g_start_costs;        /* [2] cost at qacc_warmstart / qacc_smooth */
+static _Thread_local const LSQuery* g_ls_query;
+static _Thread_local const real* g_search_override; /* [NV] first search direction of another implementation */
 
 static void update_constraint(const ZboData* d, Ctx* c) {
   real cost = 0;
@@ -827,6 +837,12 @@ static void ctx_create(const ZboData* d, Ctx* c, const real* qacc) {
       for (int j = 0; j < NV; j++) s += d->efc_J[r][j] * qacc[j];
     c->Jaref[r] = s - d->efc_aref[r];
     if (d->efc_type[r]) FL(d->efc_type[r] == 3 ? 25 : 3);
+    c->jascale[r] = 0;
+    if (g_ls_query && d->efc_type[r]) {
+      real a = R_ABS(d->efc_aref[r]);
+      for (int j = 0; j < NV; j++) a += R_ABS(d->efc_J[r][j] * qacc[j]);
+      c->jascale[r] = a;
+    }
   }
   if (g_variant & 1) {
     real jv[NEFC];
@@ -893,7 +909,7 @@ static LSPoint ls_point(const ZboData* d, const Ctx* c, real alpha, const real* 
   p.deriv_0 = 2 * alpha * q2 + q1;
   p.deriv_1 = 2 * q2 + (q2 == 0 ? MJ_MINVAL : (real)0);
   FL(10);
-  if (g_lstrace && 32 + 3 * g_lscount + 2 < ZB_NTRACE) {
+  if (g_lstrace && 32 + 3 * g_lscount + 2 < ZB_TRACE_SEARCH) {
     g_lstrace[32 + 3 * g_lscount] = alpha; g_lstrace[32 + 3 * g_lscount + 1] = p.deriv_0; g_lstrace[32 + 3 * g_lscount + 2] = p.deriv_1;
     g_lscount++;
   }
@@ -915,6 +931,97 @@ static void zone_sig(const ZboData* d, const Ctx* c, real alpha, const real* jv,
       real f = d->efc_floss[r], rf = d->efc_R[r] * f;
       sig[r] = (x <= -rf && f > 0) ? 1 : ((x >= rf && f > 0) ? 2 : 0);
     } else sig[r] = x < 0 ? 4 : 0;
+  }
+}
+
+/* J search, M search and the Gauss part of the 1-D quadratic: the prelude of solver._linesearch */
+static _Thread_local real g_jvscale[NEFC]; /* magnitude of the terms summed into J search */
+static void ls_prelude(const ZboData* d, const Ctx* c, real* mv, real* jv, real* qg) {
+  mul_m(d, mv, c->search);
+  for (int r = 0; r < NEFC; r++) {
+    real s = 0, a = 0;
+    if (d->efc_type[r])
+      for (int j = 0; j < NV; j++) { s += d->efc_J[r][j] * c->search[j]; a += R_ABS(d->efc_J[r][j] * c->search[j]); }
+    jv[r] = s;
+    g_jvscale[r] = a;
+  }
+  if (g_variant & 1) jv_contacts(d, c->search, jv);
+  qg[0] = c->gauss; qg[1] = 0; qg[2] = 0;
+  for (int j = 0; j < NV; j++) {
+    qg[1] += c->search[j] * c->Ma[j] - c->search[j] * d->qfrc_smooth[j];
+    qg[2] += c->search[j] * mv[j];
+  }
+  qg[2] *= (real)0.5;
+}
+/* take a given step size along the current search direction (what _linesearch does with its own alpha) */
+static void follow_step(const ZboData* d, Ctx* c, real alpha) {
+  real mv[NV], jv[NEFC], qg[3];
+  ls_prelude(d, c, mv, jv, qg);
+  if (alpha != 0) {
+    for (int j = 0; j < NV; j++) { c->qacc[j] += c->search[j] * alpha; c->Ma[j] += mv[j] * alpha; }
+    for (int r = 0; r < NEFC; r++) c->Jaref[r] += jv[r] * alpha;
+  }
+}
+/* first and second derivative of the 1-D cost along the current search direction at given step sizes, with the magnitude of
+ * the summed terms (tolerance scale) and the relative distance of the nearest row to a change of its quadratic piece */
+static void ls_query(const ZboData* d, const Ctx* c, const LSQuery* Q) {
+  real mv[NV], jv[NEFC], qg[3];
+  ls_prelude(d, c, mv, jv, qg);
+  if (Q->info) {
+    /* info[0] contact set; info[1] / info[3]: distance of the nearest joint limit / contact slot to its activation threshold
+     * (rows that exist or not depending on rounding); info[2]: backward error of the search direction in use against
+     * M search = -grad, relative to the magnitude of the terms that were summed */
+    int mask = 0;
+    real lim = (real)1e30, con = (real)1e30, be = 0;
+    for (int k = 0; k < MAXCON; k++) {
+      mask |= d->con_active[k] << k;
+      con = R_FMIN(con, R_ABS(d->con_dist[k] - d->con_includemargin[k]));
+    }
+    for (int dof = 0; dof < NV; dof++)
+      if (g_model->jnt_limited[dof]) {
+        real q = d->qpos[dof + 1];
+        real dmin = q - (real)g_model->jnt_range[dof][0], dmax = (real)g_model->jnt_range[dof][1] - q;
+        lim = R_FMIN(lim, R_ABS(R_FMIN(dmin, dmax) - (real)g_model->jnt_margin[dof]));
+      }
+    for (int j = 0; j < NV; j++) {
+      real ga = R_ABS(c->Ma[j]) + R_ABS(d->qfrc_smooth[j]), ms = 0;
+      for (int r = 0; r < NEFC; r++) if (c->force[r] != 0) ga += R_ABS(d->efc_J[r][j] * c->force[r]);
+      for (int k = 0; k < NV; k++) ms += R_ABS(d->qM[j][k] * c->search[k]);
+      real den = ga + ms;
+      if (den > 0) be = R_FMAX(be, R_ABS(mv[j] + c->grad[j]) / den);
+    }
+    Q->info[0] = (real)mask; Q->info[1] = lim; Q->info[2] = be; Q->info[3] = con;
+  }
+  real g1 = 0, g2 = 0;
+  for (int j = 0; j < NV; j++) {
+    g1 += R_ABS(c->search[j] * c->Ma[j]) + R_ABS(c->search[j] * d->qfrc_smooth[j]);
+    g2 += (real)0.5 * R_ABS(c->search[j] * mv[j]);
+  }
+  for (int k = 0; k < Q->K; k++) {
+    real alpha = Q->alphas[k], q0 = qg[0], q1 = qg[1], q2 = qg[2], a1 = g1, a2 = g2, margin = (real)1e30;
+    for (int r = 0; r < NEFC; r++) {
+      if (d->efc_type[r] == 0) continue;
+      real x0 = c->Jaref[r], x = x0 + alpha * jv[r], D = d->efc_D[r];
+      real sc = c->jascale[r] + R_ABS(alpha) * g_jvscale[r]; /* magnitude of everything summed into x */
+      if (d->efc_type[r] == 1) {
+        real f = d->efc_floss[r], rf = d->efc_R[r] * f;
+        if (x <= -rf && f > 0) { q0 += f * ((real)-0.5 * rf - x0); q1 += -f * jv[r]; a1 += R_ABS(f * jv[r]); }
+        else if (x >= rf && f > 0) { q0 += f * ((real)-0.5 * rf + x0); q1 += f * jv[r]; a1 += R_ABS(f * jv[r]); }
+        else { q0 += (real)0.5 * D * x0 * x0; q1 += D * x0 * jv[r]; q2 += (real)0.5 * D * jv[r] * jv[r]; a1 += R_ABS(D * jv[r]) * c->jascale[r]; a2 += (real)0.5 * D * jv[r] * jv[r]; }
+        if (f > 0 && sc + rf > 0) {
+          real m1 = R_ABS(x + rf) / (sc + rf), m2 = R_ABS(x - rf) / (sc + rf);
+          margin = R_FMIN(margin, R_FMIN(m1, m2));
+        }
+      } else {
+        if (x < 0) { q0 += (real)0.5 * D * x0 * x0; q1 += D * x0 * jv[r]; q2 += (real)0.5 * D * jv[r] * jv[r]; a1 += R_ABS(D * jv[r]) * c->jascale[r]; a2 += (real)0.5 * D * jv[r] * jv[r]; }
+        if (sc > 0) margin = R_FMIN(margin, R_ABS(x) / sc);
+      }
+    }
+    Q->d0[k] = 2 * alpha * q2 + q1;
+    Q->d1[k] = 2 * q2 + (q2 == 0 ? MJ_MINVAL : (real)0);
+    Q->scale[k] = a1 + 2 * R_ABS(alpha) * a2;
+    Q->margin[k] = margin;
+    if (Q->cost) Q->cost[k] = alpha * alpha * q2 + alpha * q1 + q0;
   }
 }
 
@@ -942,6 +1049,7 @@ static void linesearch(const ZbModel* m, const ZbOpts* o, ZboData* d, Ctx* c) {
   qg[2] *= (real)0.5;
   FL(8 * NV);
   g_lstrace = c->niter == 0 ? d->trace : NULL;
+  if (c->niter == 0) for (int j = 0; j < NV; j++) d->trace[ZB_TRACE_SEARCH + j] = c->search[j];
   g_lscount = 0;
   LSPoint p0 = ls_point(d, c, 0, jv, qg);
   LSPoint lo = ls_point(d, c, p0.alpha - p0.deriv_0 / p0.deriv_1, jv, qg), hi;
@@ -1011,11 +1119,18 @@ static void solve(const ZbModel* m, const ZbOpts* o, ZboData* d) {
   if (o->warmstart) {
     ctx_create(d, &c, d->qacc_warmstart);
     ctx_create(d, &c2, d->qacc_smooth);
-    start = c.cost < c2.cost ? d->qacc_warmstart : d->qacc_smooth;
+    int warm = c.cost < c2.cost;
+    if (g_start_costs) { g_start_costs[0] = c.cost; g_start_costs[1] = c2.cost; }
+    if (g_force_start == 1) warm = 1;
+    if (g_force_start == 2) warm = 0;
+    start = warm ? d->qacc_warmstart : d->qacc_smooth;
+    d->trace[ZB_TRACE_START] = warm ? 1 : 2;
   }
   ctx_create(d, &c, start);
   update_gradient(o, d, &c);
   for (int j = 0; j < NV; j++) c.search[j] = -c.Mgrad[j];
+  if (g_ls_query && g_ls_query->search_out) memcpy(g_ls_query->search_out, c.search, sizeof(c.search));
+  if (g_search_override) memcpy(c.search, g_search_override, sizeof(c.search));
   real scale = (real)1 / ((real)m->meaninertia * (real)(NV > 1 ? NV : 1));
   d->ls_evals = 0;
   d->ls_iters = 0;
@@ -1028,8 +1143,11 @@ static void solve(const ZbModel* m, const ZbOpts* o, ZboData* d) {
     int done = c.niter >= o->iterations;
     done |= improvement < (real)o->tolerance;
     done |= gradient < (real)o->tolerance;
+    if (g_follow_trace) done = c.niter >= g_follow_niter; /* follow mode: as many iterations as the traced implementation ran */
+    if (g_ls_query) { ls_query(d, &c, g_ls_query); break; }
     if (done) break;
-    linesearch(m, o, d, &c);
+    if (g_follow_trace) follow_step(d, &c, g_follow_trace[4 * c.niter]);
+    else linesearch(m, o, d, &c);
     real pg[NV], pMg[NV];
     memcpy(pg, c.grad, sizeof(pg));
     memcpy(pMg, c.Mgrad, sizeof(pMg));
@@ -1356,6 +1474,73 @@ int SUF(zbo_step)(const ZbModel* m, const ZbOpts* o, const ZboParams* p, const Z
     if (!finite_state(d)) d->flags |= 1;
     store_state(d, st, i);
     write_out(out, d, i);
+    free(d);
+  }
+  return 0;
+}
+
+/* ONE physics step like zbo_step (n_substeps = 1, no PushEvent), but the solver takes the STEP SIZES of another implementation's
+ * solver trace (ZbOut.solver_trace layout: alpha of iteration i at [4 i]) and runs exactly niter[i] iterations: everything except
+ * the line search's bracket decisions — the one chaotic element of the capped solver, DESIGN.md §5 — is then a continuous function
+ * of the inputs, and the traced implementation must agree with this fp64 evaluation at rounding level on EVERY environment.
+ * force_start [n] (or NULL): 0 = own warm-start choice, 1 = qacc_warmstart, 2 = qacc_smooth; start_costs [n, 2] (or NULL). */
+int SUF(zbo_step_follow)(const ZbModel* m, const ZbOpts* o, const ZboParams* p, const ZboState* st, const real* action, const ZboOut* out,
+                         int n_envs, int n_threads, const real* trace, const int32_t* niter, const int32_t* force_start, real* start_costs) {
+  if (!m || !o || !st || !action || !trace || !niter || n_envs < 0) return ZB_EINVAL;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int i = 0; i < n_envs; i++) {
+    ZboData* d = (ZboData*)malloc(sizeof(ZboData));
+    EnvModel e;
+    env_model(&e, m, p, i);
+    load_state(d, st, i);
+    real dt = (real)o->dt;
+    feetech(m, dt, action + (size_t)i * NU, d->qpos, d->qvel, st->act_pos + (size_t)i * NU, st->act_vel + (size_t)i * NU,
+            st->act_torque + (size_t)i * NU, d->ctrl);
+    g_follow_trace = trace + (size_t)i * ZB_NTRACE;
+    g_follow_niter = niter[i];
+    g_force_start = force_start ? force_start[i] : 0;
+    g_start_costs = start_costs ? start_costs + 2 * (size_t)i : NULL;
+    forward(m, o, &e, d);
+    g_follow_trace = NULL; g_force_start = 0; g_start_costs = NULL;
+    integrate(m, o, &e, d);
+    if (st->time) st->time[i] += dt;
+    if (!finite_state(d)) d->flags |= 1;
+    store_state(d, st, i);
+    write_out(out, d, i);
+    free(d);
+  }
+  return 0;
+}
+
+/* Derivatives of the FIRST line search's 1-D cost at given step sizes (alphas [n, K]) for the state + action a step would start
+ * from (the state is not modified): d0, d1 [n, K] as solver._linesearch's point function defines them, scale [n, K] = magnitude of
+ * the summed terms of d0, margin [n, K] = relative distance of the nearest constraint row to a change of its quadratic piece,
+ * cost [n, K] (or NULL) = the 1-D cost itself.  search_in [n, NV] (or NULL): take this first search direction (another implementation's,
+ * ZbOut.solver_trace[ZB_TRACE_SEARCH..]) instead of the oracle's own -M^-1 grad; search_out [n, NV] (or NULL) receives the oracle's own;
+ * info [n, 4] (or NULL): see ls_query. */
+int SUF(zbo_ls_points)(const ZbModel* m, const ZbOpts* o, const ZboParams* p, const ZboState* st, const real* action, int n_envs,
+                       int n_threads, const int32_t* force_start, const real* alphas, int K, real* d0, real* d1, real* scale,
+                       real* margin, real* cost, real* start_costs, const real* search_in, real* search_out, real* info) {
+  if (!m || !o || !st || !action || !alphas || K < 1 || n_envs < 0) return ZB_EINVAL;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int i = 0; i < n_envs; i++) {
+    ZboData* d = (ZboData*)malloc(sizeof(ZboData));
+    EnvModel e;
+    env_model(&e, m, p, i);
+    load_state(d, st, i);
+    real pos[NU], vel[NU], tq[NU];
+    memcpy(pos, st->act_pos + (size_t)i * NU, sizeof(pos));
+    memcpy(vel, st->act_vel + (size_t)i * NU, sizeof(vel));
+    memcpy(tq, st->act_torque + (size_t)i * NU, sizeof(tq));
+    feetech(m, (real)o->dt, action + (size_t)i * NU, d->qpos, d->qvel, pos, vel, tq, d->ctrl);
+    LSQuery Q = {K, alphas + (size_t)i * K, d0 + (size_t)i * K, d1 + (size_t)i * K, scale + (size_t)i * K, margin + (size_t)i * K, cost ? cost + (size_t)i * K : NULL,
+                 search_out ? search_out + (size_t)i * NV : NULL, info ? info + 4 * (size_t)i : NULL};
+    g_ls_query = &Q;
+    g_search_override = search_in ? search_in + (size_t)i * NV : NULL;
+    g_force_start = force_start ? force_start[i] : 0;
+    g_start_costs = start_costs ? start_costs + 2 * (size_t)i : NULL;
+    forward(m, o, &e, d);
+    g_ls_query = NULL; g_search_override = NULL; g_force_start = 0; g_start_costs = NULL;
     free(d);
   }
   return 0;

@@ -22,6 +22,7 @@ _BUILD = os.path.join(_HERE, "_build")
 NQ, NV, NU, NBODY, NSITE, NBOX, MAXCON = 27, 26, 20, 26, 3, 2, 8
 NEFC = 2 * NV + 4 * MAXCON
 NSENSORDATA = 18
+NTRACE, TRACE_POINTS, TRACE_SEARCH, TRACE_START = 160, 32, 128, 154  # include/zbphys.h ZB_NTRACE / ZB_TRACE_*
 STAGES = [
     "kinematics", "com_pos", "crb", "factor_m", "collision", "make_constraint", "com_vel", "rne",
     "actuation", "fwd_acceleration", "solver", "sensor", "integrate",
@@ -43,7 +44,7 @@ _REAL_FIELDS = [
     ("qfrc_constraint", (NV,)), ("qacc", (NV,)),
     ("cacc", (NBODY, 6)), ("cfrc_int", (NBODY, 6)), ("cfrc_ext", (NBODY, 6)),
     ("sensordata", (NSENSORDATA,)),
-    ("solver_cost", ()), ("trace", (128,)),
+    ("solver_cost", ()), ("trace", (NTRACE,)),
 ]
 _INT_FIELDS = [
     ("con_body", (MAXCON,)), ("con_vert", (MAXCON,)), ("con_active", (MAXCON,)), ("efc_type", (NEFC,)),
@@ -161,7 +162,7 @@ class Oracle:
     def new_out(self, n):
         out = {k: np.zeros((n,) + OUT_SHAPES[k], dtype=self.dtype) for k in _OUT_REAL}
         out.update({k: np.zeros((n,), dtype=np.int32) for k in _OUT_INT})
-        out["solver_trace"] = np.zeros((n, 128), dtype=self.dtype)
+        out["solver_trace"] = np.zeros((n, NTRACE), dtype=self.dtype)
         return out
 
     def _state(self, st):
@@ -212,6 +213,42 @@ class Oracle:
                 int(bool(push_per_substep)), ctypes.byref(self._out(out)), n, int(n_substeps), self.threads)
         assert rc == 0, rc
         return out
+
+    def step_follow(self, state, action, trace, niter, params=None, out=None, force_start=None):
+        """One physics step whose solver takes the step sizes of ``trace`` [n, 128] (another implementation's ZbOut.solver_trace)
+        and runs ``niter`` [n] iterations (zbo_step_follow).  Returns (out, start_costs [n, 2])."""
+        n = state["qpos"].shape[0]
+        ps, keep = self._params(params)
+        a, tr = self._arr(action), self._arr(trace)
+        ni = np.ascontiguousarray(niter, dtype=np.int32)
+        fs = None if force_start is None else np.ascontiguousarray(force_start, dtype=np.int32)
+        costs = np.zeros((n, 2), dtype=self.dtype)
+        fn = getattr(self.lib, "zbo_step_follow" + self.suf)
+        P = lambda x: None if x is None else x.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        rc = fn(ctypes.byref(self.model), ctypes.byref(self.opts), ctypes.byref(ps), ctypes.byref(self._state(state)), P(a),
+                ctypes.byref(self._out(out)), n, self.threads, P(tr), P(ni), P(fs), P(costs))
+        assert rc == 0, rc
+        return out, costs
+
+    def ls_points(self, state, action, alphas, params=None, force_start=None, search=None):
+        """First-line-search derivatives at the step sizes ``alphas`` [n, K] (zbo_ls_points): dict(d0, d1, scale, margin [n, K],
+        start_costs [n, 2]).  The state is not modified."""
+        n = state["qpos"].shape[0]
+        ps, keep = self._params(params)
+        a, al = self._arr(action), self._arr(alphas)
+        K = al.shape[1]
+        fs = None if force_start is None else np.ascontiguousarray(force_start, dtype=np.int32)
+        r = {k: np.zeros((n, K), dtype=self.dtype) for k in ("d0", "d1", "scale", "margin", "cost")}
+        r["start_costs"] = np.zeros((n, 2), dtype=self.dtype)
+        r["search"] = np.zeros((n, NV), dtype=self.dtype)
+        r["info"] = np.zeros((n, 4), dtype=self.dtype)
+        sin = self._arr(search)
+        fn = getattr(self.lib, "zbo_ls_points" + self.suf)
+        P = lambda x: None if x is None else x.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        rc = fn(ctypes.byref(self.model), ctypes.byref(self.opts), ctypes.byref(ps), ctypes.byref(self._state(state)), P(a), n, self.threads,
+                P(fs), P(al), K, P(r["d0"]), P(r["d1"]), P(r["scale"]), P(r["margin"]), P(r["cost"]), P(r["start_costs"]), P(sin), P(r["search"]), P(r["info"]))
+        assert rc == 0, rc
+        return r
 
     def forward(self, state, params=None, out=None):
         n = state["qpos"].shape[0]

@@ -51,7 +51,7 @@ def run(lib, a, model, opts, seed=0):
         eng.step(actions[t], ep, ps, push_rand=None if pushes is None else pushes[t], auto_reset=(rq, rv, rt), done_out=done)
         if t >= W:
             ev[t - W][1].record()
-        ndone += done.sum()
+        ndone += (done != 0).sum()
     torch.cuda.synchronize()
     ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
     h = hashlib.sha1()

@@ -14,7 +14,7 @@ n = 1024
 q, v = random_states(m, n, 12)
 opts = M.make_opts(dt=0.001, iterations=8)
 eng = ZbotCudaEngine(m, n, opts=opts)
-eng.trace = torch.zeros((n, 128), device="cuda")
+eng.trace = torch.zeros((n, 160), device="cuda")
 ps = eng.reset(reset_qpos=torch.tensor(q), reset_qvel=torch.tensor(v), reset_t_rem=torch.full((n,), 1e9))
 traw = eng.trace.cpu().numpy(); tc = traw[:, :64].reshape(n, 16, 4)
 qc = ps.data.qacc.cpu().numpy()

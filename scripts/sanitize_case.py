@@ -18,7 +18,7 @@ for solver in (M.SOLVER_CG, M.SOLVER_NEWTON):
     eng.forward(ep, ps)
     rq, rv, rt = eng.sample_reset(n)
     done = torch.zeros(n, dtype=torch.uint8, device="cuda")
-    eng.trace = torch.zeros((n, 128), device="cuda")
+    eng.trace = torch.zeros((n, 160), device="cuda")
     for t in range(2):
         eng.step(torch.tensor(random_actions(n, t), device="cuda"), ep, ps, auto_reset=(rq, rv, rt), done_out=done)
     eng.trace = None

@@ -24,7 +24,7 @@ t0 = time.time()
 for t in range(steps):
     act = bias + 0.5 * (torch.rand((n, 20), generator=g, device="cuda") * 2 - 1)
     eng.step(act, ep, ps, auto_reset=(rq, rv, rt), done_out=done)
-    tot_done += done.sum()
+    tot_done += (done != 0).sum()
     bad += (~torch.isfinite(ps.data.qpos).all(dim=1)).sum() + (ps.data.flags != 0).sum()
     niter += ps.data.solver_niter.float().mean()
 torch.cuda.synchronize()

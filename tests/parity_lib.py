@@ -1,0 +1,517 @@
+"""Tail-sensitive parity checks of the CUDA step against the CPU oracle (used by tests/test_parity_tail.py, the mutation test
+and __graft_entry__.smoke()).  TEST INFRASTRUCTURE: imports oracle/.
+
+Why this exists ("What's weak" 1): quantile assertions alone let up to 1 % of the environments be arbitrarily
+wrong.  The iteration-capped solver makes an unconditional 1e-5 bound impossible for ANY fp32 implementation (DESIGN.md §5:
+discrete line-search decisions on rounding-level derivatives), so the checks here are built from three parts that together
+leave no environment unconstrained:
+
+  (1) PATH-CONDITIONAL MAXIMUM.  The kernel's TRACE instantiation and the oracle both record, per solver iteration, the
+      number of bracket iterations of the line search and whether the step was accepted.  For EVERY environment whose
+      discrete solver path (iteration count, per-iteration bracket count, accepted flags, contact set) equals the fp32
+      oracle's, the results must agree at rounding level: qpos <= 1e-5 relative (north_star) and qvel / qacc at the
+      documented fp32 floor — a maximum over those environments, not a quantile.
+  (2) FLIP RATE.  The fraction of environments whose path differs from the fp32 oracle's must not exceed the oracle's own
+      flip rate under a one-ulp perturbation of its inputs (+ slack): a bug in a rare branch shows up as extra flips.
+  (3) ABSOLUTE CAP.  On ALL environments the error against fp64 is capped by a multiple of the LARGEST error the fp32
+      oracles themselves show on the same batch.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+import zb_oracle
+from ksim_gym_zbot_b200 import model as M
+from ksim_gym_zbot_b200.engine import EnvParams, ZbotCudaEngine
+
+STATE_KEYS = ("qpos", "qvel", "qacc_warmstart", "act_pos", "act_vel", "act_torque", "push_t_rem", "time")
+
+
+def cuda_state_np(ps):
+    d, a = ps.data, ps.actuator_state
+    return {"qpos": d.qpos.cpu().numpy(), "qvel": d.qvel.cpu().numpy(), "qacc_warmstart": d.qacc_warmstart.cpu().numpy(),
+            "act_pos": a.position.cpu().numpy(), "act_vel": a.velocity.cpu().numpy(), "act_torque": a.last_computed_torque.cpu().numpy(),
+            "push_t_rem": ps.event_states["push_t_rem"].cpu().numpy(), "time": d.time.cpu().numpy()}
+
+
+def cuda_out_np(ps, keys=("qacc", "qfrc_constraint", "sensordata", "contact_mask", "solver_niter", "flags", "xpos", "xquat", "efc_force",
+                         "actuator_force", "site_xpos", "cinert", "cvel", "contact_pos", "contact_dist")):
+    return {k: getattr(ps.data, k).cpu().numpy() for k in keys}
+
+
+def oracle_state_from(st_np, dtype, perturb_seed=None):
+    """Oracle state dict (own copies) from a CUDA state; perturb_seed: qpos/qvel moved by up to one fp32 ulp."""
+    st = {k: np.ascontiguousarray(st_np[k], dtype=dtype).copy() for k in STATE_KEYS}
+    if perturb_seed is not None:
+        r = np.random.default_rng(perturb_seed)
+        for k in ("qpos", "qvel"):
+            st[k] = (st[k].astype(np.float64) * (1 + r.uniform(-1.2e-7, 1.2e-7, st[k].shape))).astype(dtype)
+    return st
+
+
+def path_signature(trace, niter, contact_mask):
+    """Discrete solver path of every environment as an int64 array [n, 18]: niter, contact set, per-iteration bracket-iteration
+    count and accepted flag (solver_trace layout: include/zbphys.h ZbOut.solver_trace)."""
+    n = len(niter)
+    sig = np.zeros((n, 18), np.int64)
+    sig[:, 0] = niter
+    sig[:, 1] = contact_mask
+    it = np.arange(8)
+    live = it[None, :] < np.asarray(niter)[:, None]
+    sig[:, 2:10] = np.where(live, np.rint(trace[:, 4 * it + 2]).astype(np.int64), -1)
+    sig[:, 10:18] = np.where(live, (trace[:, 4 * it] != 0).astype(np.int64), -1)
+    return sig
+
+
+def per_env_err(a, ref, floor):
+    a = np.asarray(a, np.float64).reshape(len(a), -1)
+    ref = np.asarray(ref, np.float64).reshape(len(ref), -1)
+    return (np.abs(a - ref) / np.maximum(floor, np.abs(ref))).max(axis=1)
+
+
+class StepReport(dict):
+    """Result of one compared launch: per-environment errors and path flags."""
+
+
+def compare_single_step(model, opts, state_np, action, params=None, lib_path=None, threads=None, n_substeps=1, with_oracles=True):
+    """ONE launch (n_substeps, default one physics step) of the CUDA kernel (TRACE instantiation) and of the fp32 / fp64 /
+    perturbed-fp32 oracles from the identical state.  Returns per-environment errors against fp64 and the path-match masks."""
+    n = state_np["qpos"].shape[0]
+    threads = threads or os.cpu_count() or 1
+    eng = ZbotCudaEngine(model, n, device=0, opts=opts, ctrl_dt=float(opts.dt) * n_substeps, lib_path=lib_path)
+    dev = eng.device
+    ep = EnvParams(n, dev, **params) if params else None
+
+    def load(ps):
+        for k in ("qpos", "qvel", "qacc_warmstart", "time"):
+            getattr(ps.data, k).copy_(torch.tensor(state_np[k]))
+        ps.actuator_state.position.copy_(torch.tensor(state_np["act_pos"]))
+        ps.actuator_state.velocity.copy_(torch.tensor(state_np["act_vel"]))
+        ps.actuator_state.last_computed_torque.copy_(torch.tensor(state_np["act_torque"]))
+        ps.event_states["push_t_rem"].copy_(torch.tensor(state_np["push_t_rem"]))
+
+    act = torch.tensor(action, device=dev)
+    # production instantiation (no trace) and TRACE instantiation must agree bit for bit
+    ps0 = eng.new_state(n)
+    load(ps0)
+    eng.step(act, ep, ps0)
+    ps = eng.new_state(n)
+    load(ps)
+    eng.trace = torch.zeros((n, zb_oracle.NTRACE), dtype=torch.float32, device=dev)
+    traced_ok = True
+    try:
+        eng.step(act, ep, ps)
+    except Exception:  # ZB_MINIMAL (mutation) builds have no TRACE instantiation
+        traced_ok = False
+        ps = ps0
+    torch.cuda.synchronize()
+    c_state, c_out = cuda_state_np(ps), cuda_out_np(ps)
+    if traced_ok:
+        s0 = cuda_state_np(ps0)
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            assert np.array_equal(s0[k], c_state[k]), f"TRACE and production instantiations differ in {k}"
+    c_trace = eng.trace.cpu().numpy() if traced_ok else None
+    eng.close()
+    if not with_oracles:
+        return StepReport(n=n, traced=traced_ok, trace=c_trace, state=c_state, out=c_out)
+
+    res = {}
+    for name, dtype, pseed in (("f32", np.float32, None), ("f64", np.float64, None), ("f32p", np.float32, 12345)):
+        o = zb_oracle.Oracle(model, opts, dtype, threads=threads)
+        st = oracle_state_from(state_np, dtype, pseed)
+        out = o.new_out(n)
+        o.step(st, np.asarray(action, dtype=dtype), n_substeps, params=params, out=out)
+        res[name] = (st, out)
+    f64s, f64o = res["f64"]
+    rep = StepReport(n=n, traced=traced_ok, trace=c_trace, state=c_state, out=c_out)
+    rep["contact_equal"] = c_out["contact_mask"] == f64o["contact_mask"]
+    rep["contact_equal_f32"] = res["f32"][1]["contact_mask"] == f64o["contact_mask"]
+    for key, floor, src in (("qpos", 1.0, "state"), ("qvel", 1.0, "state"), ("qacc", 10.0, "out"), ("sensordata", 10.0, "out"),
+                            ("act_torque", 1.0, "state")):
+        ref = f64s[key] if src == "state" else f64o[key]
+        rep["e_cuda_" + key] = per_env_err(c_state[key] if src == "state" else c_out[key], ref, floor)
+        for name in ("f32", "f32p"):
+            st, out = res[name]
+            rep[f"e_{name}_{key}"] = per_env_err(st[key] if src == "state" else out[key], ref, floor)
+    # CUDA against the fp32 oracle directly (the path-conditional comparison)
+    f32s, f32o = res["f32"]
+    rep["d_cuda_f32_qpos"] = per_env_err(c_state["qpos"], f32s["qpos"], 1.0)
+    rep["d_cuda_f32_qvel"] = per_env_err(c_state["qvel"], f32s["qvel"], 1.0)
+    rep["d_cuda_f32_qacc"] = per_env_err(c_out["qacc"], f32o["qacc"], 10.0)
+    rep["d_f32p_f32_qpos"] = per_env_err(res["f32p"][0]["qpos"], f32s["qpos"], 1.0)
+    rep["d_f32p_f32_qvel"] = per_env_err(res["f32p"][0]["qvel"], f32s["qvel"], 1.0)
+    rep["d_f32p_f32_qacc"] = per_env_err(res["f32p"][1]["qacc"], f32o["qacc"], 10.0)
+    sig_o = path_signature(f32o["solver_trace"], f32o["solver_niter"], f32o["contact_mask"])
+    sig_p = path_signature(res["f32p"][1]["solver_trace"], res["f32p"][1]["solver_niter"], res["f32p"][1]["contact_mask"])
+    rep["path_match_f32p"] = (sig_p == sig_o).all(axis=1)
+    if traced_ok:
+        sig_c = path_signature(c_trace, c_out["solver_niter"], c_out["contact_mask"])
+        rep["path_match_cuda"] = (sig_c == sig_o).all(axis=1)
+    rep["niter_cuda"], rep["niter_f32"] = c_out["solver_niter"], f32o["solver_niter"]
+    rep["finite"] = bool(np.isfinite(c_state["qpos"]).all() and np.isfinite(c_state["qvel"]).all())
+    return rep
+
+
+# Documented fp32 floors for environments on the SAME discrete solver path as the fp32 oracle (one physics step).  qpos is the
+# north_star bound.  qvel = dt * qacc and qacc carries the rounding of the stiff constraint rows (D ~ 1e4..1e6) through eight
+# CG iterations: measured maxima over path-matched environments are printed by the tests; the bounds below are ~4x those.
+TOL_MATCHED = {"qpos": 1e-5, "qvel": 5e-4, "qacc": 2e-2}
+
+
+def check_report(rep, tag="", flip_slack=0.02, cap_factor=3.0, cap_floor=None, verbose=True):
+    """The three assertions described in the module docstring.  Raises AssertionError with a readable message."""
+    cap_floor = cap_floor or {"qpos": 1e-5, "qvel": 1e-4, "qacc": 1e-3, "sensordata": 1e-3, "act_torque": 1e-5}
+    n = rep["n"]
+    msgs = []
+    assert rep["finite"], f"{tag}: non-finite state"
+    bad_contacts = int((~rep["contact_equal"]).sum()), int((~rep["contact_equal_f32"]).sum())
+    if bad_contacts[0] > bad_contacts[1] + max(1, n // 2000):
+        msgs.append(f"contact sets differ from fp64 on {bad_contacts[0]} envs (fp32 oracle: {bad_contacts[1]})")
+    if rep["traced"]:
+        mc, mp = rep["path_match_cuda"], rep["path_match_f32p"]
+        flip_c, flip_p = 1 - mc.mean(), 1 - mp.mean()
+        if flip_c > flip_p + flip_slack:
+            msgs.append(f"path flip rate vs fp32 oracle {flip_c:.4f} > perturbed fp32 oracle's {flip_p:.4f} + {flip_slack}")
+        for k, tol in TOL_MATCHED.items():
+            e = rep["d_cuda_f32_" + k][mc]
+            if e.size and e.max() > tol:
+                msgs.append(f"{k}: max over the {int(mc.sum())} path-matched envs {e.max():.3e} > {tol:.1e} (env {int(np.flatnonzero(mc)[e.argmax()])})")
+        if verbose:
+            em = {k: rep["d_cuda_f32_" + k][mc].max() if mc.any() else 0 for k in TOL_MATCHED}
+            ep = {k: rep["d_f32p_f32_" + k][mp].max() if mp.any() else 0 for k in TOL_MATCHED}
+            print(f"{tag}: n={n} path flips cuda {flip_c:.4f} / perturbed oracle {flip_p:.4f}; max over path-matched envs (cuda vs f32) "
+                  + " ".join(f"{k} {v:.2e}" for k, v in em.items()) + " | (f32p vs f32) " + " ".join(f"{k} {v:.2e}" for k, v in ep.items()))
+    for k in ("qpos", "qvel", "qacc", "sensordata", "act_torque"):
+        ec, eo = rep["e_cuda_" + k], np.maximum(rep["e_f32_" + k], rep["e_f32p_" + k])
+        cap = max(cap_floor[k], cap_factor * eo.max())
+        if ec.max() > cap:
+            msgs.append(f"{k}: max error vs fp64 {ec.max():.3e} (env {int(ec.argmax())}) > cap {cap:.3e} = {cap_factor} x worst fp32 oracle {eo.max():.3e}")
+        for qt in (50, 90, 99, 99.9):
+            qc, qo = np.percentile(ec, qt), np.percentile(eo, qt)
+            if qc > max(cap_floor[k], 3.0 * qo):
+                msgs.append(f"{k}: p{qt} vs fp64 {qc:.3e} > 3 x fp32 oracles' {qo:.3e}")
+        if verbose:
+            print(f"{tag}:   {k:11s} vs f64  cuda p50 {np.percentile(ec, 50):.2e} p99 {np.percentile(ec, 99):.2e} max {ec.max():.2e} | "
+                  f"fp32 oracles p50 {np.percentile(eo, 50):.2e} p99 {np.percentile(eo, 99):.2e} max {eo.max():.2e}")
+    assert not msgs, f"{tag}: " + "; ".join(msgs)
+
+
+def rollout_states(model, opts, n, n_ctrl, S, seed, params=None, push_cfg=None, lib_path=None):
+    """State distribution of a random-action rollout (bench.py's workload): reset, n_ctrl control steps with termination +
+    reset in the launch; returns the CUDA state as numpy (inputs for single-step comparisons)."""
+    eng = ZbotCudaEngine(model, n, device=0, opts=opts, ctrl_dt=float(opts.dt) * S, push=push_cfg, seed=seed, lib_path=lib_path)
+    dev = eng.device
+    ep = EnvParams(n, dev, **params) if params else None
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 17)
+    bias = torch.tensor(M.BIAS_POSE, dtype=torch.float32, device=dev)
+    rq, rv, rt = eng.sample_reset(n)
+    ps = eng.reset(ep, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
+    done = torch.zeros((n,), dtype=torch.uint8, device=dev)
+    for t in range(n_ctrl):
+        act = bias + 0.3 * (torch.rand((n, M.NU), generator=g, device=dev) * 2 - 1)
+        eng.step(act, ep, ps, push_rand=None if push_cfg is None else eng.sample_push(n), auto_reset=(rq, rv, rt), done_out=done)
+    torch.cuda.synchronize()
+    st = cuda_state_np(ps)
+    eng.close()
+    return st
+
+
+# ---------------------------------------------------------------------------------------------
+# Line-search certificate: every point the FIRST line search of a launch evaluated (ZbOut.solver_trace from index 32:
+# (alpha, d0, d1) of p0, newton(p0), then lo_next / hi_next / mid of every bracket iteration) is checked
+#   (a) against the fp64 oracle's derivatives of the same 1-D cost at the SAME step size (zbo_ls_points) — the row sums, the
+#       piece each row is on, the active-set bookkeeping of the fast paths; and
+#   (b) by replaying solver._linesearch's bracket state machine in IEEE fp32 on the recorded numbers: the step sizes of the
+#       next three candidates, the number of iterations and the returned step must come out BIT FOR BIT.
+# Nothing here is statistical: every environment is checked, and a decision is never compared across implementations.
+# ---------------------------------------------------------------------------------------------
+def _in_bracket(x, y):
+    return bool((x < y and y < 0) or (x > y and y > 0))
+
+
+def replay_linesearch(pts, n_it, alpha_out, snorm, opts, meaninertia):
+    """pts [(alpha, d0, d1)] as np.float32 rows; returns None or a message describing the first inconsistency."""
+    f = np.float32
+    gtol = f(f(opts.tolerance) * f(opts.ls_tolerance)) * f(f(f(snorm) * f(meaninertia)) * f(26.0))
+    p0, p1 = pts[0], pts[1]
+    with np.errstate(all="ignore"):
+        if p0[0] != 0:
+            return "p0 is not at alpha = 0"
+        if f(p0[0] - f(p0[1] / p0[2])) != p1[0]:
+            return f"newton(p0) = {f(p0[0] - f(p0[1] / p0[2]))!r} but the second point is at {p1[0]!r}"
+        lo, hi = (p1, p0) if p1[1] < p0[1] else (p0, p1)
+        swap, it, j = True, 0, 2
+        while True:
+            done = it >= opts.ls_iterations or not swap or (lo[1] < 0 and lo[1] > -gtol) or (hi[1] > 0 and hi[1] < gtol)
+            if done:
+                break
+            if j + 3 > len(pts):
+                return f"trace ends after {it} bracket iterations but the state machine continues"
+            a0 = f(lo[0] - (f(lo[1] / lo[2]) if lo[1] != 0 else f(0)))
+            a1 = f(hi[0] - (f(hi[1] / hi[2]) if hi[1] != 0 else f(0)))
+            a2 = f(f(0.5) * f(lo[0] + hi[0]))
+            ln, hn, md = pts[j], pts[j + 1], pts[j + 2]
+            if not (ln[0] == a0 and hn[0] == a1 and md[0] == a2):
+                return f"iteration {it}: candidates at {ln[0]!r}, {hn[0]!r}, {md[0]!r}, state machine expects {a0!r}, {a1!r}, {a2!r}"
+            s1 = _in_bracket(lo[1], ln[1]); lo = ln if s1 else lo
+            s2 = _in_bracket(lo[1], md[1]); lo = md if s2 else lo
+            s3 = _in_bracket(lo[1], hn[1]); lo = hn if s3 else lo
+            s4 = _in_bracket(hi[1], hn[1]); hi = hn if s4 else hi
+            s5 = _in_bracket(hi[1], md[1]); hi = md if s5 else hi
+            s6 = _in_bracket(hi[1], ln[1]); hi = ln if s6 else hi
+            swap = s1 or s2 or s3 or s4 or s5 or s6
+            it += 1
+            j += 3
+        if it != n_it:
+            return f"{n_it} bracket iterations recorded, the state machine runs {it}"
+        if not (alpha_out == 0 or alpha_out == lo[0] or alpha_out == hi[0]):
+            return f"returned step {alpha_out!r} is neither bracket end ({lo[0]!r}, {hi[0]!r}) nor 0"
+    return None, (lo, hi)
+
+
+def geometry_ambiguous(o64, state_np, info, cuda_out, params=None, min_activation=2e-6):
+    """Environments whose constraint ROWS depend on rounding: a contact slot or a joint limit within `min_activation` (m / rad) of
+    its activation threshold, a contact set that differs from the fp64 oracle's, or a manifold that picked other box vertices.
+    info = zbo_ls_points' info array."""
+    n = state_np["qpos"].shape[0]
+    out64 = o64.new_out(n)
+    o64.forward(oracle_state_from(state_np, np.float64), params=params, out=out64)
+    geo = (info[:, 0].astype(np.int64) != cuda_out["contact_mask"]) | (info[:, 1] < min_activation) | (info[:, 3] < min_activation)
+    act = ((cuda_out["contact_mask"][:, None] >> np.arange(8)[None]) & 1).astype(bool)
+    pc = np.where(act[:, :, None], cuda_out["contact_pos"].astype(np.float64), 1e9)
+    po = np.where(act[:, :, None], out64["contact_pos"], 1e9)
+    close_pts = np.abs(np.sort(pc.reshape(n, -1), axis=1) - np.sort(po.reshape(n, -1), axis=1)).max(axis=1) < 3e-5
+    return geo | ~close_pts
+
+
+def linesearch_certificate(model, opts, state_np, action, trace, cuda_out, params=None, threads=None, tol_d0=3e-4, tol_d1=3e-4,
+                           tol_search=1e-3, min_margin=1e-4, min_activation=2e-6):
+    """Checks the first line search of every environment (see above).  ``trace`` [n, ZB_NTRACE] fp32 = ZbOut.solver_trace of a launch
+    of ONE physics step from ``state_np`` with ``action``, ``cuda_out`` its ZbOut arrays (contact_mask, contact_pos).  The fp64 oracle
+    evaluates the 1-D cost along the TRACED search direction (so that only the line search is compared: tolerances at fp32
+    summation level, measured maxima ~1.5e-4) and checks that direction by its backward error against M s = -grad.
+    Environments whose constraint rows themselves depend on rounding (a contact or joint limit within `min_activation` of its
+    activation threshold, a manifold that picked other vertices) are counted as geometry-ambiguous and skipped.
+    Returns dict(fail=[(env, message)], n_points, n_ambiguous, n_ls, n_geometry, dist)."""
+    n = state_np["qpos"].shape[0]
+    threads = threads or os.cpu_count() or 1
+    tr = np.asarray(trace, np.float32)
+    T = zb_oracle
+    nit = np.rint(tr[:, 2]).astype(int)  # bracket iterations of solver iteration 0
+    npts = np.where(tr[:, 3] > 0, 2 + 3 * nit, 0)  # |search| == 0 <=> the solver never entered a line search
+    K = 26
+    P = tr[:, T.TRACE_POINTS:T.TRACE_POINTS + 3 * K].reshape(n, K, 3)
+    search = tr[:, T.TRACE_SEARCH:T.TRACE_SEARCH + 26].astype(np.float64)
+    start = np.rint(tr[:, T.TRACE_START]).astype(np.int32)
+    start = np.where(start == 0, 2, start)  # no warm start requested -> qacc_smooth
+    o64 = zb_oracle.Oracle(model, opts, np.float64, threads=threads)
+    st64 = oracle_state_from(state_np, np.float64)
+    r = o64.ls_points(st64, np.asarray(action, np.float64), P[:, :, 0].astype(np.float64), params=params, force_start=start, search=search)
+    geo = geometry_ambiguous(o64, state_np, r["info"], cuda_out, params, min_activation)
+    fails, n_amb, n_chk = [], 0, 0
+    # error distributions (diagnostics): d0 relative to the magnitude of its summed terms, d1 relative, search backward error
+    valid = (np.arange(K)[None, :] < npts[:, None]) & (r["margin"] >= min_margin) & ~geo[:, None]
+    ed0 = np.where(valid, np.abs(P[:, :, 1] - r["d0"]) / np.maximum(r["scale"], 1e-30), 0.0)
+    ed1 = np.where(valid, np.abs(P[:, :, 2] - r["d1"]) / np.maximum(np.abs(r["d1"]), 1e-30), 0.0)
+    dist = {"d0": ed0.max(axis=1), "d1": ed1.max(axis=1), "search": np.where((npts > 0) & ~geo, r["info"][:, 2], 0.0)}
+    for i in range(n):
+        k = npts[i]
+        if k == 0 or geo[i]:
+            continue
+        pts = P[i, :k]
+        cw, cs = r["start_costs"][i]
+        own = 1 if cw < cs else 2
+        if opts.warmstart and start[i] != own and abs(cw - cs) > 1e-5 * max(abs(cw), abs(cs), 1e-30):
+            fails.append((i, f"started from {'qacc_warmstart' if start[i] == 1 else 'qacc_smooth'} although its cost is higher ({cw:.6e} vs {cs:.6e})"))
+            continue
+        if r["info"][i, 2] > tol_search:
+            fails.append((i, f"first search direction: backward error {r['info'][i, 2]:.2e} against M s = -grad"))
+            continue
+        msg = None
+        for j in range(k):
+            n_chk += 1
+            if r["margin"][i, j] < min_margin:  # a row within rounding of a change of piece: either piece is a legitimate fp32 answer
+                n_amb += 1
+                continue
+            if abs(pts[j, 1] - r["d0"][i, j]) > tol_d0 * r["scale"][i, j] + 1e-30:
+                msg = f"point {j} (alpha {pts[j, 0]!r}): d0 {pts[j, 1]!r} vs fp64 {r['d0'][i, j]:.8e} (scale {r['scale'][i, j]:.3e})"
+                break
+            if abs(pts[j, 2] - r["d1"][i, j]) > tol_d1 * abs(r["d1"][i, j]) + 1e-30:
+                msg = f"point {j} (alpha {pts[j, 0]!r}): d1 {pts[j, 2]!r} vs fp64 {r['d1'][i, j]:.8e}"
+                break
+        if msg is None:
+            rp = replay_linesearch(pts, nit[i], tr[i, 0], tr[i, 3], opts, model.meaninertia)
+            if isinstance(rp, str):
+                msg = rp
+            else:  # the returned end must be the cheaper one (fp64 cost) unless the two are tied at fp32 resolution
+                lo, hi = rp[1]
+                if tr[i, 0] != 0 and lo[0] != hi[0]:
+                    c = {float(pts[j, 0]): r["cost"][i, j] for j in range(k)}
+                    cl, ch = c[float(lo[0])], c[float(hi[0])]
+                    chosen_lo = tr[i, 0] == lo[0]
+                    if (cl < ch) != chosen_lo and abs(cl - ch) > 1e-5 * max(abs(cl), abs(ch), 1e-30):
+                        msg = f"returned the more expensive bracket end (cost lo {cl:.8e}, hi {ch:.8e})"
+        if msg is not None:
+            fails.append((i, msg))
+    return {"fail": fails, "n_points": n_chk, "n_ambiguous": n_amb, "n_ls": int((npts > 0).sum()), "n_geometry": int(geo.sum()), "dist": dist}
+
+
+def follow_compare(model, opts, state_np, action, params=None, lib_path=None, threads=None):
+    """One physics step of the CUDA kernel (TRACE instantiation) against the fp64 oracle FOLLOWING the kernel's step sizes, start
+    point and iteration count (zbo_step_follow): per-environment errors of qpos / qvel / qacc / sensordata / qfrc_constraint.
+    With few solver iterations (opts.iterations <= 3) everything but the line search's own decisions is a well-conditioned
+    continuous function of the inputs, and the two must agree at rounding level on EVERY environment."""
+    n = state_np["qpos"].shape[0]
+    threads = threads or os.cpu_count() or 1
+    rep = compare_single_step(model, opts, state_np, action, params=params, lib_path=lib_path, with_oracles=False)
+    assert rep["traced"], "follow_compare needs the TRACE instantiation"
+    tr = rep["trace"]
+    start = np.rint(tr[:, zb_oracle.TRACE_START]).astype(np.int32)
+    o64 = zb_oracle.Oracle(model, opts, np.float64, threads=threads)
+    st = oracle_state_from(state_np, np.float64)
+    out = o64.new_out(n)
+    _, costs = o64.step_follow(st, np.asarray(action, np.float64), tr.astype(np.float64), rep["out"]["solver_niter"], params=params, out=out,
+                               force_start=np.where(start == 0, 2, start))
+    info = o64.ls_points(oracle_state_from(state_np, np.float64), np.asarray(action, np.float64), np.zeros((n, 1)), params=params)["info"]
+    res = {"niter": rep["out"]["solver_niter"], "start": start, "start_costs": costs,
+           "contact_equal": rep["out"]["contact_mask"] == out["contact_mask"],
+           "geometry_ambiguous": geometry_ambiguous(o64, state_np, info, rep["out"], params)}
+    for key, floor, src in (("qpos", 1.0, "state"), ("qvel", 1.0, "state"), ("qacc", 10.0, "out"), ("sensordata", 10.0, "out"),
+                            ("qfrc_constraint", 10.0, "out"), ("act_torque", 1.0, "state")):
+        res["e_" + key] = per_env_err(rep["state"][key] if src == "state" else rep["out"][key], st[key] if src == "state" else out[key], floor)
+    # the fp32 floor of exactly this computation: the fp32 ORACLE following the same step sizes, against the same fp64 evaluation
+    o32 = zb_oracle.Oracle(model, opts, np.float32, threads=threads)
+    st32 = oracle_state_from(state_np, np.float32)
+    out32 = o32.new_out(n)
+    o32.step_follow(st32, np.asarray(action, np.float32), tr, rep["out"]["solver_niter"], params=params, out=out32, force_start=np.where(start == 0, 2, start))
+    for key, floor, src in (("qpos", 1.0, "state"), ("qvel", 1.0, "state"), ("qacc", 10.0, "out"), ("sensordata", 10.0, "out")):
+        res["e32_" + key] = per_env_err(st32[key] if src == "state" else out32[key], st[key] if src == "state" else out[key], floor)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+# Statistical comparison of the full capped solve at the BASELINE batch sizes, teacher-forced per control step
+# ---------------------------------------------------------------------------------------------
+def stat_check(e_cuda, e_ref, tag, cap_factor=3.0, floors=None, quantiles=(50, 90, 99, 99.9), slack=3.0, verbose=True):
+    """e_cuda / e_ref: {field: per-environment error against fp64} of the kernel and of the fp32 oracles (elementwise max of the
+    plain and the perturbed one).  Quantile by quantile the kernel may be at most `slack` x the fp32 oracles (or at the floor), and
+    NO environment may exceed cap_factor x the fp32 oracles' worst environment.  Returns the list of violations."""
+    floors = floors or {"qpos": 1e-5, "qvel": 1e-4, "qacc": 1e-3, "sensordata": 1e-3, "act_torque": 1e-5, "act_pos": 1e-5, "act_vel": 1e-5}
+    msgs = []
+    for k, ec in e_cuda.items():
+        eo = e_ref[k]
+        if not len(ec):
+            continue
+        fl = floors.get(k, 1e-5)
+        cap = max(fl, cap_factor * eo.max())
+        if not np.all(np.isfinite(ec)):
+            msgs.append(f"{k}: non-finite")
+            continue
+        if ec.max() > cap:
+            msgs.append(f"{k}: max error vs fp64 {ec.max():.3e} (env {int(ec.argmax())}) > cap {cap:.3e} = {cap_factor} x worst fp32-oracle env {eo.max():.3e}")
+        for qt in quantiles:
+            if len(ec) * (100 - qt) / 100 < 3:
+                continue
+            qc, qo = np.percentile(ec, qt), np.percentile(eo, qt)
+            if qc > max(fl, slack * qo):
+                msgs.append(f"{k}: p{qt} vs fp64 {qc:.3e} > {slack} x fp32 oracles' {qo:.3e}")
+        if verbose:
+            print(f"{tag}: {k:11s} n={len(ec)} cuda p50 {np.percentile(ec, 50):.2e} p99 {np.percentile(ec, 99):.2e} max {ec.max():.2e} | "
+                  f"fp32 oracles p50 {np.percentile(eo, 50):.2e} p99 {np.percentile(eo, 99):.2e} max {eo.max():.2e}")
+    return msgs
+
+
+def _terminated(q, z_lo=0.05, z_hi=0.5, cos_tilt=0.5):
+    up = q[:, 3] ** 2 - q[:, 4] ** 2 - q[:, 5] ** 2 + q[:, 6] ** 2
+    return (q[:, 2] < z_lo) | (q[:, 2] > z_hi) | (up < cos_tilt) | ~np.isfinite(q[:, 2]) | ~np.isfinite(up)
+
+
+def teacher_forced_rollout(model, opts, n, S, n_ctrl, seed, params=None, push_cfg=None, lib_path=None, warmup_ctrl=15, threads=None,
+                           verbose=True):
+    """bench.py's control step (S fused substeps + termination + reset in ONE launch) for n_ctrl steps; before every step the three
+    oracles (fp32, fp64, fp32 on one-ulp-perturbed inputs) are put on the kernel's state, run the same control step with their own
+    termination + zbo_reset, and the results are compared: done masks, the reset environments (exact state, forward outputs at
+    rounding level) and the stepped environments (stat_check).  Returns (violations, summary dict)."""
+    from ksim_gym_zbot_b200.engine import PushEventConfig  # noqa: F401
+
+    threads = threads or os.cpu_count() or 1
+    eng = ZbotCudaEngine(model, n, device=0, opts=opts, ctrl_dt=float(opts.dt) * S, push=push_cfg, seed=seed, lib_path=lib_path)
+    dev = eng.device
+    ep = EnvParams(n, dev, **params) if params else None
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 17)
+    bias = torch.tensor(M.BIAS_POSE, dtype=torch.float32, device=dev)
+    rq, rv, rt = eng.sample_reset(n)
+    rq_n, rv_n, rt_n = rq.cpu().numpy(), rv.cpu().numpy(), rt.cpu().numpy()
+    ps = eng.reset(ep, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt)
+    done = torch.zeros((n,), dtype=torch.uint8, device=dev)
+    orcs = {"f32": zb_oracle.Oracle(model, opts, np.float32, threads=threads), "f64": zb_oracle.Oracle(model, opts, np.float64, threads=threads),
+            "f32p": zb_oracle.Oracle(model, opts, np.float32, threads=threads)}
+    msgs, summ = [], {"done_cuda": 0, "done_f64": 0, "done_mismatch_cuda": 0, "done_mismatch_f32": 0, "reset_checked": 0, "steps": 0}
+    for t in range(warmup_ctrl + n_ctrl):
+        act = bias + 0.3 * (torch.rand((n, M.NU), generator=g, device=dev) * 2 - 1)
+        pr = None if push_cfg is None else eng.sample_push(n)
+        check = t >= warmup_ctrl
+        if check:
+            pre = cuda_state_np(ps)
+        eng.step(act, ep, ps, push_rand=pr, auto_reset=(rq, rv, rt), done_out=done)
+        if not check:
+            continue
+        torch.cuda.synchronize()
+        post, out_c, done_c = cuda_state_np(ps), cuda_out_np(ps), done.cpu().numpy().astype(bool)
+        act_n, pr_n = act.cpu().numpy(), None if pr is None else pr.cpu().numpy()
+        res = {}
+        for name, o in orcs.items():
+            st = oracle_state_from(pre, o.dtype, 777 + t if name == "f32p" else None)
+            out = o.new_out(n)
+            o.step(st, act_n.astype(o.dtype), S, params=params, push_rand=None if pr_n is None else pr_n.astype(o.dtype), out=out)
+            d = _terminated(st["qpos"]) | (out["flags"] != 0)
+            if d.any():
+                o.reset(st, rq_n, rv_n, rt_n, done=d.astype(np.uint8), params=params, out=out)
+            res[name] = (st, out, d)
+        st64, out64, d64 = res["f64"]
+        summ["steps"] += 1
+        summ["done_cuda"] += int(done_c.sum()); summ["done_f64"] += int(d64.sum())
+        summ["done_mismatch_cuda"] += int((done_c != d64).sum())
+        summ["done_mismatch_f32"] += int(max((res["f32"][2] != d64).sum(), (res["f32p"][2] != d64).sum()))
+        # ---- environments reset by both: the state is the reset arrays, exactly; forward() outputs at rounding level
+        both = done_c & d64
+        if both.any():
+            summ["reset_checked"] += int(both.sum())
+            ex = {"qvel": rv_n, "act_vel": rv_n[:, 6:], "push_t_rem": rt_n, "time": np.zeros(n, np.float32), "qacc_warmstart": np.zeros((n, 26), np.float32),
+                  "act_torque": np.zeros((n, 20), np.float32)}
+            for k, ref in ex.items():
+                if not np.array_equal(post[k][both], ref[both]):
+                    msgs.append(f"step {t}: reset environments: {k} is not the reset value")
+            if not np.array_equal(post["act_pos"][both], post["qpos"][both][:, 7:]):
+                msgs.append(f"step {t}: reset environments: planner position != joint position")
+            for k, tol in (("qpos", 1e-6), ("xpos", 2e-6), ("xquat", 2e-6), ("cinert", 2e-5), ("site_xpos", 2e-6)):
+                a = post[k][both] if k == "qpos" else out_c[k][both]
+                b = st64[k][both] if k == "qpos" else out64[k][both]
+                e = per_env_err(a, b, 1.0)
+                if e.max() > tol:
+                    msgs.append(f"step {t}: reset environments: {k} max error {e.max():.2e} > {tol:.0e}")
+        # ---- environments stepped by both
+        live = ~done_c & ~d64
+        ec, eo = {}, {}
+        for key, floor, src in (("qpos", 1.0, 0), ("qvel", 1.0, 0), ("act_pos", 1.0, 0), ("act_vel", 1.0, 0), ("act_torque", 1.0, 0), ("qacc", 10.0, 1), ("sensordata", 10.0, 1)):
+            ref = (st64 if src == 0 else out64)[key][live]
+            ec[key] = per_env_err((post if src == 0 else out_c)[key][live], ref, floor)
+            eo[key] = np.maximum(per_env_err((res["f32"][0] if src == 0 else res["f32"][1])[key][live], ref, floor),
+                                 per_env_err((res["f32p"][0] if src == 0 else res["f32p"][1])[key][live], ref, floor))
+        m_ = stat_check(ec, eo, f"step {t}", verbose=verbose and t == warmup_ctrl + n_ctrl - 1)
+        msgs += [f"step {t}: {x}" for x in m_]
+        cm = (out_c["contact_mask"][live] != out64["contact_mask"][live]).mean()
+        co = max((res[k][1]["contact_mask"][live] != out64["contact_mask"][live]).mean() for k in ("f32", "f32p"))
+        if cm > max(0.03, 2 * co):
+            msgs.append(f"step {t}: contact sets after the control step differ from fp64 on {cm:.4f} of the envs (fp32 oracles: {co:.4f})")
+        summ["contact_mismatch_cuda"], summ["contact_mismatch_f32"] = float(cm), float(co)
+    eng.close()
+    # terminations: the kernel may disagree with fp64 about as often as the fp32 oracles do (a state within rounding of a threshold)
+    if summ["done_mismatch_cuda"] > 2 * summ["done_mismatch_f32"] + max(3, int(2e-4 * n * summ["steps"])):
+        msgs.append(f"termination masks differ from fp64 on {summ['done_mismatch_cuda']} env-steps (fp32 oracles: {summ['done_mismatch_f32']})")
+    return msgs, summ

@@ -1,0 +1,168 @@
+"""Tail-sensitive GPU parity tests: checks that constrain EVERY environment, at the BASELINE.json batch sizes,
+and a mutation test proving that they turn red on bugs planted in rarely taken paths.
+
+The iteration-capped solver (iterations = 8, ls_iterations = 8, train.py:1779-1780) is chaotic at the bit level — two fp64
+evaluations that differ only in summation order disagree at the 1e-2 level on qacc for a few percent of the states (DESIGN.md §5;
+scripts/parity_probe.py shows that even environments with identical per-iteration bracket counts do) — so "max error over all
+environments <= 1e-5 after a full step" is not a property ANY fp32 implementation has.  What IS deterministic, and what these
+tests therefore pin on every environment without statistics:
+
+  * the line search, point by point (parity_lib.linesearch_certificate): every (alpha, d0, d1) the kernel evaluated against the
+    fp64 derivatives of the same 1-D cost at the same alpha, and the bracket state machine replayed bit-exactly in IEEE fp32;
+  * the rest of the step given the step sizes (parity_lib.follow_compare): the fp64 oracle following the kernel's alphas for
+    1..3 solver iterations must land on the kernel's qpos within 1e-5 (north_star) and qvel / qacc at the fp32 floor — max over
+    all environments;
+  * the full capped solve, statistically: quantiles up to p99.9 and an absolute cap against fp64, both relative to what the fp32
+    oracle (plain and on one-ulp-perturbed inputs) shows on the same batch — at 4096 and 16 384 environments, teacher-forced over
+    10 control steps with randomisation, pushes and the in-launch termination + reset (compared against zbo_reset).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity_lib as P
+from helpers import random_actions, random_states
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _limit_states(zmodel, n, seed):
+    q, v = random_states(zmodel, n, seed)
+    rng = np.random.default_rng(seed + 1)
+    lo, hi = zmodel.field("jnt_range")[6:, 0], zmodel.field("jnt_range")[6:, 1]
+    for i in range(n):
+        for j in rng.choice(20, size=3, replace=False):
+            q[i, 7 + j] = (lo[j] - rng.uniform(0.01, 0.1)) if rng.random() < 0.5 else (hi[j] + rng.uniform(0.01, 0.1))
+    return {"qpos": q, "qvel": v, "qacc_warmstart": np.zeros((n, 26), np.float32), "act_pos": q[:, 7:].copy(), "act_vel": v[:, 6:].copy(),
+            "act_torque": np.zeros((n, 20), np.float32), "push_t_rem": np.full(n, 1e9, np.float32), "time": np.zeros(n, np.float32)}
+
+
+def _populations(zmodel, n, lib_path=None):
+    """(name, opts, state, action, params): rollout states of the bench workload at both substep settings, states with joints
+    beyond their range, states with both feet flat on the floor (4-point manifolds), rollout states with a scrambled warm start (first line searches that cross many row pieces) and a
+    randomised-model batch."""
+    from ksim_gym_zbot_b200 import model as M
+
+    out = []
+    for name, dt, S in (("rollout dt=0.005", 0.005, 4), ("rollout dt=0.001", 0.001, 20)):
+        opts = M.make_opts(dt=dt)
+        out.append((name, opts, P.rollout_states(zmodel, opts, n, 25, S, seed=3, lib_path=lib_path), random_actions(n, 5), None))
+    opts = M.make_opts(dt=0.002)
+    out.append(("joint limits", opts, _limit_states(zmodel, n, 101), random_actions(n, 6), None))
+    opts = M.make_opts(dt=0.005)
+    st = {k: v.copy() for k, v in out[0][2].items()}
+    st["qacc_warmstart"] = (st["qacc_warmstart"] + np.random.default_rng(5).uniform(-20, 20, (n, 26))).astype(np.float32)
+    out.append(("scrambled warm start", opts, st, random_actions(n, 7), None))
+    q, v = random_states(zmodel, n, 103, joint_noise=2e-3, z_jitter=1.5e-3, tilt=2e-3, vel=0.3)  # both feet flat on the floor: 4-point manifolds
+    flat = _limit_states(zmodel, n, 104)
+    flat.update(qpos=q, qvel=v, act_pos=q[:, 7:].copy(), act_vel=v[:, 6:].copy())
+    out.append(("flat feet", opts, flat, random_actions(n, 9), None))
+    prm = M.randomize_env_params(zmodel, n, 7)
+    out.append(("randomised model", opts, P.rollout_states(zmodel, opts, n, 25, 4, seed=4, params=prm, lib_path=lib_path), random_actions(n, 8), prm))
+    return out
+
+
+def _certify(zmodel, pops, lib_path=None):
+    """Runs the certificate on every population; returns the list of (population, env, message) failures."""
+    fails, stats = [], []
+    for name, opts, st, act, prm in pops:
+        rep = P.compare_single_step(zmodel, opts, st, act, params=prm, lib_path=lib_path, with_oracles=False)
+        assert rep["traced"]
+        r = P.linesearch_certificate(zmodel, opts, st, act, rep["trace"], rep["out"], params=prm)
+        stats.append((name, r["n_ls"], r["n_points"], r["n_ambiguous"], r["n_geometry"], len(r["fail"])))
+        fails += [(name, i, msg) for i, msg in r["fail"]]
+    return fails, stats
+
+
+def test_linesearch_certificate_every_environment(zmodel):
+    """Every point of every environment's first line search against fp64 + bit-exact replay of the bracket state machine."""
+    n = 4096
+    fails, stats = _certify(zmodel, _populations(zmodel, n))
+    for s in stats:
+        print("certificate: %-22s line searches %d, points %d (ambiguous piece: %d), geometry-ambiguous envs %d, failures %d" % s)
+    assert sum(s[1] for s in stats) > 4 * n  # the populations really run line searches
+    assert not fails, fails[:5]
+
+
+@pytest.mark.parametrize("iters", [0, 1, 2, 3])
+def test_step_follows_fp64_given_step_sizes(zmodel, iters):
+    """The rest of the step given the line search's step sizes (those are certified separately): CUDA step with `iters` solver
+    iterations vs the fp64 oracle FOLLOWING the kernel's alphas / start point / iteration count.  MAX over all environments:
+    qpos within north_star's 1e-5 relative, qvel / qacc at the fp32 floor — or, where the batch's own fp32 floor is higher (stiff
+    randomised models), within 3x of what the fp32 ORACLE following the same step sizes shows against the same fp64 evaluation."""
+    from ksim_gym_zbot_b200 import model as M
+
+    n = 4096
+    bad = []
+    for name, opts, st, act, prm in _populations(zmodel, n):
+        o = M.make_opts(dt=float(opts.dt), iterations=iters)
+        r = P.follow_compare(zmodel, o, st, act, params=prm)
+        ok = ~r["geometry_ambiguous"]  # (rows that exist or not depending on rounding: a contact / limit within 2e-6 of activation)
+        assert ok.mean() > 0.985, (name, ok.mean())
+        line = []
+        for k, t in {"qpos": 1e-5, "qvel": 4e-3, "qacc": 1e-2, "sensordata": 3e-2}.items():
+            ec, eo = r["e_" + k][ok].max(), r["e32_" + k][ok].max()
+            line.append(f"{k} {ec:.2e} (fp32 oracle {eo:.2e})")
+            if ec > max(t, min(3 * eo, 50 * t)):  # (the fp32 oracle following foreign step sizes can blow up on stiff randomised models: capped)
+                bad.append(f"{name}, {iters} iterations: {k} max over all {int(ok.sum())} envs {ec:.3e} > max({t:.0e}, 3 x fp32 oracle's {eo:.3e})")
+        assert r["e_act_torque"][ok].max() < 1e-5
+        print(f"follow, {iters} iterations, {name}: max over {int(ok.sum())} envs " + " ".join(line))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("mutant", ["mut1", "mut2", "mut3", "mut4"])
+def test_planted_bugs_are_caught(zmodel, mutant):
+    """Mutation test: libraries with ONE planted bug each in a rarely taken path (build.py MUTANTS: a lost friction-pyramid facet on
+    manifold slot 2, a wrong active set after one particular bracket swap, limit rows invisible to the line search, the
+    production-only one-sided loop writing its result to the wrong bracket end).  The checks above must turn red on each of them."""
+    from ksim_gym_zbot_b200 import build as B
+
+    lib = B.variant_path(mutant)
+    if not os.path.exists(lib):
+        B.build_mutants()
+    n = 4096
+    caught = []
+    pops = _populations(zmodel, n)  # states from the healthy library: identical inputs for every mutant
+    try:
+        fails, stats = _certify(zmodel, pops, lib_path=lib)
+        if fails:
+            caught.append(f"certificate: {len(fails)} environments, e.g. {fails[0]}")
+    except AssertionError as e:  # production and TRACE instantiations disagree
+        caught.append(f"bitwise TRACE/production check: {e}")
+    print(f"{mutant}: " + ("; ".join(caught) if caught else "NOT caught"))
+    assert caught, f"{mutant} went unnoticed"
+
+
+def test_c2_4096_envs_teacher_forced(zmodel):
+    """BASELINE.json configs[1] at its own size: 4096 envs, S = 4, random actions, in-launch termination + reset; 10 control steps,
+    each compared with the oracles from the kernel's state (quantiles to p99.9 + absolute cap on every environment)."""
+    from ksim_gym_zbot_b200 import model as M
+
+    msgs, summ = P.teacher_forced_rollout(zmodel, M.make_opts(dt=0.005), 4096, 4, 10, seed=0)
+    print("c2 4096:", summ)
+    assert summ["steps"] == 10 and not msgs, msgs[:6]
+
+
+def test_c3_16384_envs_randomised_pushes_autoreset(zmodel):
+    """BASELINE.json configs[2] at its own size: 16 384 envs, per-env randomisation, PushEvent, in-launch termination + reset
+    (compared against zbo_reset), 10 control steps teacher-forced."""
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import PushEventConfig
+
+    n = 16384
+    # pushes ten times the reference's magnitude and frequent, so that terminations + resets happen inside the 10 compared steps
+    push = PushEventConfig(x_linvel=1.0, y_linvel=1.0, z_linvel=0.5, interval_range=(0.1, 0.3))
+    msgs, summ = P.teacher_forced_rollout(zmodel, M.make_opts(dt=0.005), n, 4, 10, seed=1, params=M.randomize_env_params(zmodel, n, 101), push_cfg=push)
+    print("c3 16384:", summ)
+    assert summ["steps"] == 10 and summ["reset_checked"] > 20 and not msgs, msgs[:6]
+
+
+def test_s20_4096_envs_teacher_forced(zmodel):
+    """The reference's launch config (dt = 0.001, 20 substeps per control step, train.py:1777-1778) at 4096 envs, 5 control steps."""
+    from ksim_gym_zbot_b200 import model as M
+
+    msgs, summ = P.teacher_forced_rollout(zmodel, M.make_opts(dt=0.001), 4096, 20, 5, seed=2, warmup_ctrl=10)
+    print("S=20 4096:", summ)
+    assert summ["steps"] == 5 and not msgs, msgs[:6]
