@@ -898,7 +898,7 @@ struct WarpEnv {
   //   phase 0/1: cost of the two warm-start candidates (qacc_smooth, qacc_warmstart)
   //   phase 2  : Context.create at the chosen start + first gradient/search direction
   //   phase 3  : one solver iteration (line search, constraint update, gradient, Polak-Ribiere)
-  //   phase 99 : implicit integration solve (M + dt D)^-1 (qfrc_smooth + qfrc_constraint)
+  //   after the loop: implicit integration solve (M + dt D)^-1 (qfrc_smooth + qfrc_constraint)
   // ------------------------------------------------------------------------------------------
   // forces and cost of the rows at the current Jaref; returns this lane's partial constraint cost
   ZB_DI float row_update(float& fr_force, float& lm_force, float& c_force) const {
@@ -1272,18 +1272,33 @@ struct WarpEnv {
   }
 
   // The whole constrained solve + (optionally) the implicit-integration solve.  Returns the integration acceleration.
+  // (The solver loop exists twice in the instruction stream, once per solver type, selected by a warp-uniform branch: the CG loop
+  //  then carries no Hessian assembly / factorisation and, with the integration solve moved behind the loop, is 1.6 k instructions
+  //  = 26 KB instead of 3.1 k = 50 KB.  It is executed ~12 times per substep by every warp of the CTA and now fits the 32 KB
+  //  instruction cache level below L0: +2.7 % at S = 4, +4 % at S = 20, bit-identical results.)
   ZB_DI float solve_all(bool implicit_damp) {
+    if (o.solver == ZB_SOLVER_NEWTON) solver_loop<true>();
+    else solver_loop<false>();
+    // implicit integration: (M + dt D)^-1 (qfrc_smooth + qfrc_constraint).  M + dt D is factored only here, when the solve has
+    // finished: an up-front factor would sit in 19 registers per lane through the whole solve.  F0 (factor of M / of the last
+    // Newton Hessian) is dead from here on.
+    if (!implicit_damp) return qacc;
+    float Hb[6], Hc[CHD];
+    load_m(Hb, Hc);
+    factor(Hb, Hc, o.dt * damp);
+    return solve(qfrc_smooth + qfrc_c);
+  }
+  template <bool newton>
+  ZB_DI void solver_loop() {
     const float scale = 1.f / (meaninertia * (float)NV);
-    const bool newton = o.solver == ZB_SOLVER_NEWTON;
     int phase = -1;
-    float v = 0.f, cost_s = 0.f, qa_int = 0.f, pg = 0.f, pMg = 0.f;
+    float v = 0.f, cost_s = 0.f, pg = 0.f, pMg = 0.f;
     cost = 0.f; prev_cost = 0.f; niter = 0; lscount = 0;
     qacc = 0.f; Ma = 0.f; fr_ja = lm_ja = c_ja = 0.f; qfrc_c = 0.f; grad = 0.f; Mgrad = 0.f; search = 0.f; mv = 0.f; gauss = 0.f;
-    bool finished = false;
 #pragma unroll 1
-    while (!finished) {
+    while (true) {
       float fr_force = 0.f, lm_force = 0.f, c_force = 0.f;  // row forces of THIS pass
-      if (phase >= 0 && phase < 99) {
+      if (phase >= 0) {
         // ---- operator application: mv = M v, contact rows J v ----
         float vb[6];
         mv = mul_m(v, vb);
@@ -1308,28 +1323,19 @@ struct WarpEnv {
       }
       float x = 0.f;
       if (phase == -1 || phase >= 2) {
-        if (phase >= 2 && phase < 99) {
+        if (phase >= 2) {
           const float jt = contact_jtf(c_force);
           qfrc_c = hasdof ? jt + (fr_on ? fr_force : 0.f) + (lm_on ? lm_sign * lm_force : 0.f) : 0.f;
           pg = grad; pMg = Mgrad;
           grad = hasdof ? Ma - qfrc_smooth - qfrc_c : 0.f;
         }
-        // ONE more call site of the factorisation serves the Newton Hessian of every iteration and the implicit-integration
-        // matrix M + dt D (phase 99).  The latter is factored only here, when it is needed: an up-front factor would sit in 19
-        // registers per lane through the whole solve.  F0 (factor of M) is dead once qacc_smooth exists (Newton) / once the
-        // solver has finished (phase 99).
-        const bool fac_newton = newton && phase >= 2 && phase < 99;
-        if (fac_newton || phase == 99) {
+        // Newton: F0 (factor of M) is dead once qacc_smooth exists and is overwritten by the factor of every iteration's Hessian
+        if (newton && phase >= 2) {
           float Hb[6], Hc[CHD];
-          float extra = 0.f;
-          if (fac_newton) newton_hessian(Hb, Hc);
-          else {
-            load_m(Hb, Hc);
-            extra = o.dt * damp;
-          }
-          factor(Hb, Hc, extra);
+          newton_hessian(Hb, Hc);
+          factor(Hb, Hc, 0.f);
         }
-        const float rhs = phase == -1 ? qfrc_smooth : (phase == 99 ? qfrc_smooth + qfrc_c : grad);
+        const float rhs = phase == -1 ? qfrc_smooth : grad;
         x = solve(rhs);
       }
       // ---- transitions ----
@@ -1339,7 +1345,6 @@ struct WarpEnv {
         const bool pick_warm = __all_sync(ZB_FULL, cost < cost_s);
         if (TRACE && trace && L == 0) trace[ZB_TRACE_START] = pick_warm ? 1.f : 2.f;
         v = pick_warm ? warm : qacc_smooth; warm = 0.f; /* dead from here on: frees its register for the iterations */ phase = 2; continue; }
-      if (phase == 99) { qa_int = x; finished = true; continue; }
       Mgrad = x;
       float gnorm2;
       if (phase == 2 || newton) {
@@ -1360,15 +1365,10 @@ struct WarpEnv {
       bool done = niter >= o.iterations;
       done |= improvement < o.tolerance;
       done |= gradient < o.tolerance;
-      if (__all_sync(ZB_FULL, done)) {
-        if (!implicit_damp) { qa_int = qacc; finished = true; continue; }
-        phase = 99;
-        continue;
-      }
+      if (__all_sync(ZB_FULL, done)) break;
       phase = 3;
       v = search;
     }
-    return qa_int;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1377,9 +1377,13 @@ struct WarpEnv {
   // ------------------------------------------------------------------------------------------
   // keep: shared [16] (or nullptr) that receives framequat (4), accelerometer (3), gyro (3), touch l / r (2) for the observation epilogue —
   // shared memory, not registers: the values would otherwise stay live across the substep loop and the solver
-  ZB_DI void sensors(float* sd /* global [18] or nullptr */, float* keep) {
-    if (!sd && !keep) return;
-    if (keep) {  // touch values default to 0 (a foot box without a touch site)
+  // (has_sd / has_keep: the same facts as `sd != nullptr` / `keep != nullptr`, but derived from kernel parameters only.  The pointers
+  //  themselves depend on the warp index, and a branch on them is not PROVABLY warp-uniform: ptxas then treats everything behind it
+  //  as potentially diverged, wraps every shuffle of the kernel in WARPSYNC and duplicates the solver — the observation
+  //  instantiation was 18.6 k instructions instead of 9.6 k and 10 % slower because of exactly that.)
+  ZB_DI void sensors(float* sd /* global [18] or nullptr */, float* keep, bool has_sd, bool has_keep) {
+    if (!has_sd && !has_keep) return;
+    if (has_keep) {  // touch values default to 0 (a foot box without a touch site)
       if (L == 0) { keep[10] = 0.f; keep[11] = 0.f; }
       __syncwarp();
     }
@@ -1433,18 +1437,18 @@ struct WarpEnv {
       matT_vec(acc, sxmat, uu);
       cross3(corr, ang, lin);
       simu[4] = acc[0] + corr[0]; simu[5] = acc[1] + corr[1]; simu[6] = acc[2] + corr[2];
-      if (keep) {
+      if (has_keep) {
 #pragma unroll
         for (int k = 0; k < 10; k++) keep[k] = simu[k];
       }
-      if (sd) {
+      if (has_sd) {
 #pragma unroll
         for (int k = 0; k < 4; k++) sd[ZB_SENS_IMU_QUAT + k] = simu[k];
 #pragma unroll
         for (int k = 0; k < 3; k++) { sd[ZB_SENS_IMU_ACC + k] = simu[4 + k]; sd[ZB_SENS_IMU_GYRO + k] = simu[7 + k]; }
       }
     }
-    if (sd && (s == 1 || s == 2)) {  // foot force sensors
+    if (has_sd && (s == 1 || s == 2)) {  // foot force sensors
       float fo[3];
       matT_vec(fo, sxmat, cf + 3);
       const int o = s == 1 ? ZB_SENS_FORCE_L : ZB_SENS_FORCE_R;
@@ -1469,8 +1473,8 @@ struct WarpEnv {
       }
       val += shx(val, 8); val += shx(val, 4); val += shx(val, 2); val += shx(val, 1);
       if ((L & 15) == 0 && ts >= 0) {
-        if (sd) sd[ts == 1 ? ZB_SENS_TOUCH_L : ZB_SENS_TOUCH_R] = val;
-        if (keep) keep[ts == 1 ? 10 : 11] = val;
+        if (has_sd) sd[ts == 1 ? ZB_SENS_TOUCH_L : ZB_SENS_TOUCH_R] = val;
+        if (has_keep) keep[ts == 1 ? 10 : 11] = val;
       }
     }
   }

@@ -100,9 +100,14 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   // lockstep exists for instruction-fetch sharing, but every barrier also waits for the slowest environment of its group; two
   // groups measured +1 % over one (4096 and 16 384 envs), four no better (scripts/sweep_variants.sh).
   const int nwarp = blockDim.x >> 5;
+#ifdef ZB_BAR_INTERLEAVE
+  const int bar_g = wib % ZB_BAR_GROUPS;
+  const int bar_cnt = (bar_g < nwarp ? (nwarp - 1 - bar_g) / ZB_BAR_GROUPS + 1 : 0) * 32;
+#else
   const int bar_g = (ZB_BAR_GROUPS > 1) ? (wib * ZB_BAR_GROUPS) / nwarp : 0;
   const int bar_lo = (bar_g * nwarp + ZB_BAR_GROUPS - 1) / ZB_BAR_GROUPS, bar_hi = ((bar_g + 1) * nwarp + ZB_BAR_GROUPS - 1) / ZB_BAR_GROUPS;
   const int bar_cnt = (bar_hi - bar_lo) * 32;
+#endif
 #define ZB_LOCKSTEP_BARRIER() do { if (ZB_BAR_GROUPS > 1) asm volatile("bar.sync %0, %1;" ::"r"(bar_g + 1), "r"(bar_cnt) : "memory"); else __syncthreads(); } while (0)
   const int env = blockIdx.x * (blockDim.x >> 5) + wib;  // warps per CTA is a launch-time choice (<= ZB_WPB, see pick_wpb)
   // (vote: makes the flag provably warp-uniform for ptxas; a divergent-looking exit around barriers would wrap every
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
     E.qfrc_smooth = E.hasdof ? qfrc_passive - E.qfrc_bias + qfrc_act : 0.f;
     const float qa = E.solve_all(implicit_damp && stepping);
     if (last || extra) E.final_rows();
-    if (last || extra) E.sensors(sd, (OBS && want_obs) ? imu_keep[OBS ? wib : 0] : nullptr);
+    if (last || extra) E.sensors(sd, imu_keep[OBS ? wib : 0], O.sensordata != nullptr, OBS && want_obs);
     if (extra) E.warm = 0.f;
     if (stepping) {
       // ---- euler / implicitfast + _advance ----
@@ -594,7 +599,7 @@ int zb_engine_create(const ZbModel* model, const ZbOpts* opts, int device, ZbEng
   {  // the throughput-profile kernels keep 31 floats per lane in dynamic shared memory: 28 warps x 3968 B = 108.5 KB > the 48 KB default
     const int bytes = ZB_WPB_WIDE * ZB_FSM_BYTES_PER_WARP;
     cudaError_t a1 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, false, ZB_WPB_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-#ifdef ZB_MINIMAL
+#if defined(ZB_MINIMAL) && !defined(ZB_MINIMAL_OBS)
     cudaError_t a2 = cudaSuccess;
 #else
     cudaError_t a2 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, true, ZB_WPB_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -668,6 +673,10 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
 #define ZB_LAUNCH_STEP(TR, OBSV, W) zb_kernel<ZB_MODE_STEP, TR, OBSV, W><<<grid, wpb * 32, (W > ZB_WPB) ? (size_t)wpb * ZB_FSM_BYTES_PER_WARP : 0, (cudaStream_t)stream>>>( \
     e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR, OB)
 #ifdef ZB_MINIMAL  // development / mutation builds: only the plain step (both register profiles, + trace) and the plain reset are compiled
+#ifdef ZB_MINIMAL_OBS  // ... + the observation epilogue in the throughput profile
+  if (with_obs && !cs.wide) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL_OBS) has the observation epilogue in the throughput profile only%s");
+  if (with_obs && !O.solver_trace) { ZB_LAUNCH_STEP(false, true, ZB_WPB_WIDE); return after_launch("zb_step_f32 launch: %s"); }
+#endif
   if (with_obs) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no observation instantiations%s");
   if (O.solver_trace) ZB_LAUNCH_STEP(true, false, ZB_WPB);
   else if (cs.wide) ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB);

@@ -115,15 +115,44 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
 
 
+def _host_key() -> str:
+    """Identifies the CPU this process runs on (model name + ISA flags): -march=native objects are only valid there."""
+    import hashlib
+
+    txt = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith(("model name", "flags")):
+                txt += ln
+                if ln.startswith("flags"):
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(txt.encode()).hexdigest()[:10]
+
+
+def build_fast() -> str:
+    """Timing build of the same source (``-O3 -march=native -ffp-contract=fast``) for bench.py's CPU arm, compiled
+    on the host that runs it into ``_build/fast_<cpu key>/``.  Parity tests never load it."""
+    out = os.path.join(_BUILD, "fast_" + _host_key())
+    path = os.path.join(out, "libzb_oracle_fast.so")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "zb_oracle.c")):
+        subprocess.run(["make", "-C", _HERE, "-s", "fast", "FASTOUT=" + out], check=True)
+    return path
+
+
 _libs: dict[str, ctypes.CDLL] = {}
 
 
-def lib(count: bool = False) -> ctypes.CDLL:
-    key = "cnt" if count else "std"
+def lib(count: bool = False, fast: bool = False) -> ctypes.CDLL:
+    key = "cnt" if count else ("fast" if fast else "std")
     if key not in _libs:
-        path = os.path.join(_BUILD, "libzb_oracle_cnt.so" if count else "libzb_oracle.so")
-        if not os.path.exists(path):
-            build()
+        if fast:
+            path = build_fast()
+        else:
+            path = os.path.join(_BUILD, "libzb_oracle_cnt.so" if count else "libzb_oracle.so")
+            if not os.path.exists(path):
+                build()
         _libs[key] = ctypes.CDLL(path)
     return _libs[key]
 
@@ -131,11 +160,11 @@ def lib(count: bool = False) -> ctypes.CDLL:
 class Oracle:
     """Batched CPU oracle in one precision (``np.float32`` — JAX's dtype — or ``np.float64``)."""
 
-    def __init__(self, model, opts, dtype=np.float32, count: bool = False, threads: int = 1):
+    def __init__(self, model, opts, dtype=np.float32, count: bool = False, threads: int = 1, fast: bool = False):
         self.model, self.opts = model, opts
         self.dtype = np.dtype(dtype)
         self.suf = "_f64" if self.dtype == np.float64 else "_f32"
-        self.lib = lib(count)
+        self.lib = lib(count, fast)  # fast: the -O3 -march=native timing build (bench.py only)
         self.count = count
         self.threads = threads
         self.Data = ZboDataF64 if self.dtype == np.float64 else ZboDataF32

@@ -507,25 +507,7 @@ def test_rollout_50_terminations(zmodel):
     agree_o = min((np.abs(first["f32"] - first["f64"]) <= 1).mean(), (np.abs(first["f32p"] - first["f64"]) <= 1).mean())
     print(f"rollout: {fell:.2f} of envs terminate; termination step agrees (+-1) cuda/f64 {agree_c:.3f}, f32/f64 {agree_o:.3f}")
     assert agree_c >= min(0.97, agree_o - 0.02)
-    # reward proxies built from the fields the reference's rewards read (train.py:1546-1586): StayAliveReward, UprightReward,
-    # NaiveForwardReward(scale 5, clip_max 0.2), SimpleSingleFootContactReward (touch sensors > 0.1, train.py:516-517)
-    def returns(name):
-        tot = np.zeros(n)
-        for t, tr in enumerate(r["traj"][name]):
-            alive = t < first[name]
-            q, qd, sd = tr["qpos"], tr["qvel"], tr["sensordata"]
-            up = 1 - 2 * (q[:, 4] ** 2 + q[:, 5] ** 2)
-            single = ((sd[:, 10] > 0.1) ^ (sd[:, 11] > 0.1)).astype(np.float64)
-            tot += alive * (1.0 + up + 5.0 * np.minimum(qd[:, 0], 0.2) + 0.3 * single)
-        return tot
-
-    ret = {k: returns(k) for k in ("cuda", "f32", "f64", "f32p")}
-    gap_c = np.abs(ret["cuda"] - ret["f64"]).mean() / np.abs(ret["f64"]).mean()
-    gap_o = max(np.abs(ret[k] - ret["f64"]).mean() / np.abs(ret["f64"]).mean() for k in ("f32", "f32p"))
-    print(f"rollout: mean |return - return_f64| / mean |return_f64|: cuda {gap_c:.4f}, fp32 oracles {gap_o:.4f}; "
-          f"mean return cuda {ret['cuda'].mean():.3f} f64 {ret['f64'].mean():.3f}")
-    assert gap_c <= max(0.02, 2.0 * gap_o)
-    assert abs(ret["cuda"].mean() - ret["f64"].mean()) <= max(0.01 * abs(ret["f64"].mean()), 3 * abs(ret["f32"].mean() - ret["f64"].mean()))
+    # (the reference's real reward list and terminations over 50 steps: tests/test_rollout_rewards.py)
     # before anything falls the trajectories agree tightly (step 5)
     r5 = {k: r["traj"][k][4] for k in ("cuda", "f32", "f64", "f32p")}
     _assert_close("qpos@5", r5, "qpos", 1e-4)
