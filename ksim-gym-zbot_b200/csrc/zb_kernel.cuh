@@ -44,6 +44,9 @@
 #ifndef ZB_MUTANT
 #define ZB_MUTANT 0 /* mutation builds (build.py MUTANTS): one planted bug each, the parity tests must catch every one */
 #endif
+#ifndef ZB_EXPLICIT_J
+#define ZB_EXPLICIT_J 1 /* contact rows as explicit 12-column Jacobian rows (chain dofs + base dofs) instead of matrix-free wrench directions */
+#endif
 #ifndef ZB_LS_SAME
 #define ZB_LS_SAME 2 /* line search: 1 = no zone evaluation while both bracket ends share one active set, 2 = + the one-sided loop (see linesearch) */
 #endif
@@ -147,6 +150,12 @@ struct WarpEnv {
   // constraint rows
   bool fr_on, lm_on, c_on, any_limit;
   float fr_D, fr_rf, fr_f, fr_aref, lm_sign, lm_D, lm_aref, c_D, c_aref, w[6];
+  // Explicit Jacobian row of this lane's contact row.  Tree sparsity: the row of a foot contact touches only the (<= 6) dofs of its
+  // leg chain and the 6 base dofs, J[r, d] = w_r . cdof_d.  cj[0..5]: chain dofs of the box (lanes jsrc + k, zero for non-ancestors),
+  // cj[6..11]: base dofs.  With it J v is 6 shuffles + 12 FMAs (instead of a 6-vector chain prefix scan + the base motion) and
+  // neither cdof, w nor the base pose are read inside the solver loop.
+  float cj[12];
+  int jsrc;
   float cdist, cpos[3];
   // solver
   float qacc, Ma, grad, Mgrad, search, mv, qfrc_c;
@@ -578,8 +587,16 @@ struct WarpEnv {
     return hasdof ? y : 0.f;
   }
 
-  // contact rows: jv[r] = w_r . V_box(v), V_box = spatial velocity of the box body under v
+  // contact rows: jv[r] = sum_d J[r, d] v_d over the chain dofs of the box and the base dofs (vb = broadcast base part of v)
   ZB_DI float contact_jv(float v, const float (&vb)[6]) {
+#if ZB_EXPLICIT_J
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CHD; k++) s = fmaf(cj[k], shf(v, jsrc + k), s);
+#pragma unroll
+    for (int a = 0; a < 6; a++) s = fmaf(cj[6 + a], vb[a], s);
+    return s;
+#else
     float pre[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) pre[k] = hinge ? cdof[k] * v : 0.f;
@@ -589,6 +606,42 @@ struct WarpEnv {
 #pragma unroll
     for (int k = 0; k < 6; k++) Vf[k] = shf(pre[k], boxlane) + Vb[k];
     return dot6(w, Vf);
+#endif
+  }
+
+  // J[r, :] of this lane's contact row (once per substep, after make_constraint): for a hinge with axis a through the anchor p,
+  // J = dir . (a x (pos - p)) — the lever arm taken from the joint anchor itself, not as the difference of two arms about the tree
+  // COM (w . cdof = dir . (a x (pos - c0)) + dir . (a x (c0 - p)) loses three bits to cancellation at the ankle, 3 cm from the
+  // contact and 25 cm from the COM).  Base dofs: translations J = dir, rotations (body-frame axes through the base origin) likewise.
+  ZB_DI void contact_rows_jacobian() {
+    jsrc = D->cs[boxlane];
+    const int g = L >> 4;
+    float anc[3] = {0.f, 0.f, 0.f};
+    if (hinge) {
+      const float jp[3] = {D->m.jnt_pos[L][0], D->m.jnt_pos[L][1], D->m.jnt_pos[L][2]};
+      float a[3];
+      mat_vec(a, xmat, jp);
+      anc[0] = xpos[0] + a[0]; anc[1] = xpos[1] + a[1]; anc[2] = xpos[2] + a[2];
+    }
+    const float dir[3] = {w[3], w[4], w[5]};
+#pragma unroll
+    for (int k = 0; k < CHD; k++) {
+      float ax[3], rel[3], c[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) { ax[j] = shf(cdof[j], jsrc + k); rel[j] = cpos[j] - shf(anc[j], jsrc + k); }
+      const int lb = __shfl_sync(ZB_FULL, lbox, jsrc + k);  // the dof of lane jsrc + k moves my box iff its lane_box is mine
+      cross3(c, ax, rel);
+      cj[k] = (lb == g) ? dot3(dir, c) : 0.f;
+    }
+    const float rel[3] = {cpos[0] - xb[0], cpos[1] - xb[1], cpos[2] - xb[2]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float col[3] = {Rb[a], Rb[3 + a], Rb[6 + a]};
+      float c[3];
+      cross3(c, col, rel);
+      cj[6 + a] = dir[a];
+      cj[9 + a] = dot3(dir, c);
+    }
   }
 
   // Total contact wrench of the foot box of my half-warp, sum_r f_r w_r over its 16 row lanes, as a transpose-reduce inside the
@@ -612,8 +665,31 @@ struct WarpEnv {
     return v[0] + shx(v[0], 1);
   }
 
-  // J^T f for the contact rows: per-box total wrench, projected on the dofs
+  // J^T f for the contact rows
   ZB_DI float contact_jtf(float f) {
+#if ZB_EXPLICIT_J
+    // sum_r J[r, d] f_r over the 16 row lanes of each box as a transpose-reduce inside the half-warp: total t lands in lane 16 g + t
+    float p[16];
+#pragma unroll
+    for (int k = 0; k < 12; k++) p[k] = c_on ? f * cj[k] : 0.f;
+    p[12] = p[13] = p[14] = p[15] = 0.f;
+    int m = 8;
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1, m >>= 1) {
+      const bool up = (L & m) != 0;
+#pragma unroll
+      for (int j = 0; j < half; j++) {
+        const float send = up ? p[j] : p[j + half], keep = up ? p[j + half] : p[j];
+        p[j] = keep + __shfl_xor_sync(ZB_FULL, send, m);
+      }
+    }
+    // chain dof at position gp of box lbox reads lane 16 lbox + gp; base dof a reads the sum over both boxes from lane 6 + a
+    const float both = p[0] + shx(p[0], 16);  // (executed by all lanes)
+    const float pub = ((L & 15) >= 6) ? both : p[0];
+    const bool leg = hinge && lbox >= 0;
+    const float r = shf(pub, leg ? 16 * lbox + gp : (bdof ? 6 + (L - BL0) : 0));
+    return (leg || bdof) ? r : 0.f;
+#else
     const float tot = contact_wrench(f);
     // even lanes keep the wrench of their own box, odd lanes the sum over both boxes: a leg dof pulls component k from lane
     // 16 box + 2k, a base dof from lane 2k + 1 — one shuffle per component for either kind of lane
@@ -628,6 +704,7 @@ struct WarpEnv {
       if (leg || bdof) r += cdof[k] * wk;
     }
     return r;
+#endif
   }
 
   // ------------------------------------------------------------------------------------------
@@ -830,6 +907,27 @@ struct WarpEnv {
     return x > 1.f ? s.dmax : imp;
   }
 
+  // friction coefficient of this lane's contact (geom-priority mixing done on the host: con_mu_mode)
+  ZB_DI float contact_mu() const {
+    const int g = L >> 4;
+    const float bf = D->m.box_friction[g][0];
+    return D->con_mu_mode[g] == 0 ? mu : (D->con_mu_mode[g] == 1 ? bf : fmaxf(mu, bf));
+  }
+  // w = [(pos - c0) x dir ; dir], dir = n +- mu t: the wrench (about the tree COM) a unit force along this lane's pyramid edge exerts
+  ZB_DI void row_wrench() {
+    const float cmu = contact_mu();
+    const int e = L & 3;
+    float sgn = (e & 1) ? -1.f : 1.f;
+    if (ZB_MUTANT == 1 && ((L >> 2) & 3) == 2 && e == 3) sgn = 1.f;  // (mutant 1: manifold slot 2 loses a facet of its friction pyramid)
+    const float* fr = D->frame;
+    const float* tt = fr + 3 * (1 + (e >> 1));
+    const float dir[3] = {fr[0] + sgn * cmu * tt[0], fr[1] + sgn * cmu * tt[1], fr[2] + sgn * cmu * tt[2]};
+    const float off[3] = {cpos[0] - c0[0], cpos[1] - c0[1], cpos[2] - c0[2]};
+    float tq[3];
+    cross3(tq, off, dir);
+    w[0] = tq[0]; w[1] = tq[1]; w[2] = tq[2]; w[3] = dir[0]; w[4] = dir[1]; w[5] = dir[2];
+  }
+
   ZB_DI void make_constraint() {
     const ZbModel& m = D->m;
     const int d = hasdof ? dof : 0;
@@ -863,19 +961,10 @@ struct WarpEnv {
     {
       const int g = L >> 4;
       const ZbSolPrm& sp = D->con[g];
-      const float cmu = D->con_mu_mode[g] == 0 ? mu : (D->con_mu_mode[g] == 1 ? m.box_friction[g][0] : fmaxf(mu, m.box_friction[g][0]));
+      const float cmu = contact_mu();
       const float dist = cdist - D->con_includemargin[g];
       c_on = dist < 0.f;
-      const int e = L & 3;
-      float sgn = (e & 1) ? -1.f : 1.f;
-      if (ZB_MUTANT == 1 && ((L >> 2) & 3) == 2 && e == 3) sgn = 1.f;  // (mutant 1: manifold slot 2 loses a facet of its friction pyramid)
-      const float* fr = D->frame;
-      const float* tt = fr + 3 * (1 + (e >> 1));
-      const float dir[3] = {fr[0] + sgn * cmu * tt[0], fr[1] + sgn * cmu * tt[1], fr[2] + sgn * cmu * tt[2]};
-      const float off[3] = {cpos[0] - c0[0], cpos[1] - c0[1], cpos[2] - c0[2]};
-      float tq[3];
-      cross3(tq, off, dir);
-      w[0] = tq[0]; w[1] = tq[1]; w[2] = tq[2]; w[3] = dir[0]; w[4] = dir[1]; w[5] = dir[2];
+      row_wrench();
       // velocity of the box body (needs velocity() first)
       float vf[6];
 #pragma unroll
@@ -1409,6 +1498,9 @@ struct WarpEnv {
     inert_mul(t, cinert, cvel);
     motion_cross_force(u, cvel, t);
     const int mybox = isbody ? D->body_box[L] : -1;
+#if ZB_EXPLICIT_J
+    row_wrench();  // recomputed here (20 instructions, last substep only) instead of living in 6 registers across the solve
+#endif
     const float Wtot = contact_wrench(c_force);  // cfrc_ext of a foot = the solver's total contact wrench of its box
 #pragma unroll
     for (int k = 0; k < 6; k++) {

@@ -244,6 +244,9 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
     float qfrc_passive;
     E.velocity(qfrc_passive);
     E.make_constraint();
+#if ZB_EXPLICIT_J
+    E.contact_rows_jacobian();
+#endif
     E.bias_forces();
     const float qfrc_act = E.actuation();
     E.qfrc_smooth = E.hasdof ? qfrc_passive - E.qfrc_bias + qfrc_act : 0.f;
