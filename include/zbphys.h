@@ -274,6 +274,14 @@ typedef struct ZbAutoResetArgs {
   uint8_t* done_out;        /* [N] or NULL: 0 = running, 1 = terminated (bad z / not upright / non-finite), 2 = episode length reached */
   float z_lo, z_hi, max_tilt_rad;
   float max_episode_sec;    /* ksim.EpisodeLengthTermination(max_length_sec), train.py:1592: time > max ends the episode; <= 0 disables */
+  /* Trajectory record: what ksim's rollout stores in its Trajectory for this control step —
+   * qpos / qvel / xpos / xquat of `next_physics_state` BEFORE the done -> reset select, i.e. the terminal state of an environment
+   * that ends here (train.py:297, 476, 681 read exactly these four).  Written for EVERY environment just before the termination
+   * test; pointing them at slice t of time-major [T, N, ...] arrays makes the step launch the trajectory writer.  Each may be NULL. */
+  float* term_qpos;         /* [N, ZB_NQ]        */
+  float* term_qvel;         /* [N, ZB_NV]        */
+  float* term_xpos;         /* [N, ZB_NBODY, 3]  */
+  float* term_xquat;        /* [N, ZB_NBODY, 4]  */
 } ZbAutoResetArgs;
 
 typedef struct ZbEngine ZbEngine; /* opaque: device copy of ZbModel + ZbOpts */

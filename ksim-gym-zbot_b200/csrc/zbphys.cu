@@ -15,7 +15,7 @@
 #include "../../include/zbphys.h"
 #include "zb_kernel.cuh"
 
-#define ZB_ABI_VERSION 4
+#define ZB_ABI_VERSION 5
 #define ZB_FSM_BYTES_PER_WARP (31 * 32 * 4) /* WarpEnv::F_N floats per lane */
 
 // auto-reset pass of the step kernel (zb_step_autoreset_f32)
@@ -24,6 +24,7 @@ struct ZbAutoReset {
   float z_lo, z_hi, cos_tilt, max_time;
   const float *reset_qpos, *reset_qvel, *reset_t_rem;
   uint8_t* done_out;
+  float *term_qpos, *term_qvel, *term_xpos, *term_xquat;  // Trajectory record (ZbAutoResetArgs)
 };
 
 struct ZbEngine {
@@ -196,6 +197,20 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
 #endif
     if (extra) {
       if (!(MODE == ZB_MODE_STEP && AR.enabled)) break;
+      // Trajectory record of this control step: the integrated state + the poses forward() of the last substep left, before the
+      // termination test can replace them (what ksim's rollout stores from next_physics_state)
+      if (AR.term_qpos) {
+        float v = E.bq[0];
+#pragma unroll
+        for (int k = 1; k < 7; k++) v = (L == k) ? E.bq[k] : v;
+        if (L < 7) AR.term_qpos[(size_t)env * NQ + L] = v;
+        if (E.hinge) AR.term_qpos[(size_t)env * NQ + d + 1] = E.q;
+      }
+      if (AR.term_qvel && E.hasdof) AR.term_qvel[(size_t)env * NV + d] = E.qv;
+      if (E.isbody) {
+        if (AR.term_xpos) { float* p = AR.term_xpos + ((size_t)env * NB + L) * 3; p[0] = E.xpos[0]; p[1] = E.xpos[1]; p[2] = E.xpos[2]; }
+        if (AR.term_xquat) { float* p = AR.term_xquat + ((size_t)env * NB + L) * 4; p[0] = E.xquat[0]; p[1] = E.xquat[1]; p[2] = E.xquat[2]; p[3] = E.xquat[3]; }
+      }
       const float up = E.bq[3] * E.bq[3] - E.bq[4] * E.bq[4] - E.bq[5] * E.bq[5] + E.bq[6] * E.bq[6];
       const bool nonfinite = !(isfinite(E.q) && isfinite(E.qv) && isfinite(E.bq[0]) && isfinite(E.bq[1]) && isfinite(E.bq[2]) && isfinite(E.bq[3]));
       bool bad = (E.bq[2] < AR.z_lo) || (E.bq[2] > AR.z_hi) || (up < AR.cos_tilt) || !isfinite(E.bq[2]) || !isfinite(up);
@@ -706,6 +721,7 @@ int zb_step_autoreset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, 
   if (!reset_qpos || !reset_qvel) return fail(ZB_EINVAL, "zb_step_autoreset_f32: null reset_qpos/reset_qvel%s");
   if (max_episode_sec > 0 && state && !state->time) return fail(ZB_EINVAL, "zb_step_autoreset_f32: max_episode_sec needs ZbState.time%s");
   ZbAutoReset AR;
+  memset(&AR, 0, sizeof(AR));
   AR.enabled = 1; AR.z_lo = z_lo; AR.z_hi = z_hi; AR.cos_tilt = cosf(max_tilt_rad); AR.max_time = max_episode_sec;
   AR.reset_qpos = reset_qpos; AR.reset_qvel = reset_qvel; AR.reset_t_rem = reset_t_rem; AR.done_out = done_out;
   return step_impl(e, stream, params, state, action, push_rand, push_per_substep, out, n_envs, n_substeps, AR);
@@ -791,6 +807,7 @@ int zb_step_obs_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const 
     if (ar->max_episode_sec > 0 && state && !state->time) return fail(ZB_EINVAL, "zb_step_obs_f32: max_episode_sec needs ZbState.time%s");
     AR.enabled = 1; AR.z_lo = ar->z_lo; AR.z_hi = ar->z_hi; AR.cos_tilt = cosf(ar->max_tilt_rad); AR.max_time = ar->max_episode_sec;
     AR.reset_qpos = ar->reset_qpos; AR.reset_qvel = ar->reset_qvel; AR.reset_t_rem = ar->reset_t_rem; AR.done_out = ar->done_out;
+    AR.term_qpos = ar->term_qpos; AR.term_qvel = ar->term_qvel; AR.term_xpos = ar->term_xpos; AR.term_xquat = ar->term_xquat;
   }
   return step_impl(e, stream, params, state, action, push_rand, push_per_substep, out, n_envs, n_substeps, AR, obs);
 }

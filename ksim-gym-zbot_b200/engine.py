@@ -64,7 +64,8 @@ NUM_ACTOR_INPUTS, NUM_CRITIC_INPUTS, NUM_COMMANDS = 50, 484, 7  # train.py:53-54
 class ZbAutoResetArgs(ctypes.Structure):
     _fields_ = [("reset_qpos", ctypes.c_void_p), ("reset_qvel", ctypes.c_void_p), ("reset_t_rem", ctypes.c_void_p),
                 ("done_out", ctypes.c_void_p), ("z_lo", ctypes.c_float), ("z_hi", ctypes.c_float), ("max_tilt_rad", ctypes.c_float),
-                ("max_episode_sec", ctypes.c_float)]
+                ("max_episode_sec", ctypes.c_float), ("term_qpos", ctypes.c_void_p), ("term_qvel", ctypes.c_void_p),
+                ("term_xpos", ctypes.c_void_p), ("term_xquat", ctypes.c_void_p)]
 
 
 MAX_EPISODE_SEC = 80.0  # ksim.EpisodeLengthTermination(max_length_sec=80), train.py:1592
@@ -74,6 +75,18 @@ ZB_OK, ZB_EINVAL, ZB_ENODEV, ZB_ECUDA, ZB_EUNSUP = 0, -1, -2, -3, -4
 EXPORTS = ["zb_engine_create", "zb_engine_destroy", "zb_engine_set_opts", "zb_step_f32", "zb_forward_f32", "zb_reset_f32",
            "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count", "zb_bench_ffma", "zb_terminations_f32", "zb_step_autoreset_f32",
            "zb_step_obs_f32", "zb_reset_obs_f32", "zb_feet_airtime_f32", "zb_cta_shape"]
+
+
+def _term_ptrs(terminal):
+    """(qpos, qvel, xpos, xquat) tensors or None -> the four ZbAutoResetArgs.term_* pointers."""
+    if terminal is None:
+        return (None, None, None, None)
+    out = []
+    for t in terminal:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        out.append(None if t is None else t.data_ptr())
+    return tuple(out)
 
 
 class ZbError(RuntimeError):
@@ -444,8 +457,11 @@ class ZbotCudaEngine:
              n_substeps: int | None = None, auto_reset: tuple | None = None, done_out: torch.Tensor | None = None,
              z_lo: float = 0.05, z_hi: float = 0.5, max_tilt: float = math.radians(60), obs: Observations | None = None,
              command: torch.Tensor | None = None, reset_imu_lag: torch.Tensor | None = None,
-             obs_noise: tuple | None = None, max_episode_sec: float = MAX_EPISODE_SEC) -> PhysicsState:
+             obs_noise: tuple | None = None, max_episode_sec: float = MAX_EPISODE_SEC, terminal: tuple | None = None) -> PhysicsState:
         """MjxEngine.step: one control step = ``phys_steps_per_ctrl_steps`` fused physics substeps (in place).
+
+        ``terminal=(qpos, qvel, xpos, xquat)`` (with ``auto_reset`` and ``obs``; each may be None): receives the Trajectory record of
+        the step — the state BEFORE the done -> reset select (ZbAutoResetArgs.term_*).
 
         ``auto_reset=(reset_qpos, reset_qvel, reset_t_rem)`` folds the rollout's termination check + partial reset
         (train.py:1588-1593, 1471-1476) into the same launch; ``done_out`` (uint8 [N]) receives the mask.
@@ -484,7 +500,8 @@ class ZbotCudaEngine:
                 for t in (rq, rv) + ((rt,) if rt is not None else ()):
                     assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
                 ar = ZbAutoResetArgs(rq.data_ptr(), rv.data_ptr(), None if rt is None else rt.data_ptr(),
-                                     None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt, max_episode_sec)
+                                     None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt, max_episode_sec,
+                                     *_term_ptrs(terminal))
                 if reset_imu_lag is None:
                     reset_imu_lag = self.sample_imu_lag(n, obs.lag_range)
             nq, na = obs_noise if obs_noise is not None else (None, None)
@@ -492,6 +509,8 @@ class ZbotCudaEngine:
             rc = self.lib.zb_step_obs_f32(self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st),
                                           ctypes.c_void_p(action.data_ptr()), pr, per_substep, ctypes.byref(out), ctypes.byref(ob), n, S,
                                           None if ar is None else ctypes.byref(ar))
+        elif terminal is not None:
+            raise ValueError("terminal= (Trajectory record) needs the zb_step_obs_f32 path: pass obs=")
         elif auto_reset is None:
             rc = self.lib.zb_step_f32(self._h, self._stream(), self._c_params(physics_model), ctypes.byref(st),
                                       ctypes.c_void_p(action.data_ptr()), pr, per_substep, ctypes.byref(out), n, S)
@@ -518,7 +537,7 @@ class ZbotCudaEngine:
                   auto_reset: tuple | None = None, done_out: torch.Tensor | None = None, z_lo: float = 0.05, z_hi: float = 0.5,
                   max_tilt: float = math.radians(60), obs: Observations | None = None, command: torch.Tensor | None = None,
                   reset_imu_lag: torch.Tensor | None = None, obs_noise: tuple | None = None, push_per_substep: bool = False,
-                  max_episode_sec: float = MAX_EPISODE_SEC, track_action: bool = True):
+                  max_episode_sec: float = MAX_EPISODE_SEC, track_action: bool = True, terminal: tuple | None = None):
         """Pre-bind one control step: all argument structs of the C call are built once, the returned function
         ``run(action, push_rand=None)`` only passes the two pointers that change per step and enqueues the launch on the
         current stream (what an XLA custom call does with its operand buffers; ~10x less host time per step than ``step``).
@@ -539,8 +558,11 @@ class ZbotCudaEngine:
         if auto_reset is not None:
             rq, rv, rt = auto_reset
             ar = ZbAutoResetArgs(rq.data_ptr(), rv.data_ptr(), None if rt is None else rt.data_ptr(),
-                                 None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt, max_episode_sec)
-            keep.append(ar)
+                                 None if done_out is None else done_out.data_ptr(), z_lo, z_hi, max_tilt, max_episode_sec,
+                                 *_term_ptrs(terminal))
+            keep += [ar, terminal]
+            if terminal is not None and obs is None:
+                raise ValueError("terminal= (Trajectory record) needs the zb_step_obs_f32 path: pass obs=")
         if obs is not None:
             if auto_reset is not None and reset_imu_lag is None:
                 reset_imu_lag = self.sample_imu_lag(n, obs.lag_range)

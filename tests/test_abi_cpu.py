@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_struct_layouts_match_header(lib):
-    assert lib.zb_abi_version() == 4
+    assert lib.zb_abi_version() == 5
     assert lib.zb_sizeof_model() == ctypes.sizeof(M.ZbModel)
     assert lib.zb_sizeof_opts() == ctypes.sizeof(M.ZbOpts)
 

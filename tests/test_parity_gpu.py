@@ -130,7 +130,7 @@ def test_library_exports_and_errors(zmodel):
     lib = load_library()
     for name in EXPORTS:
         assert hasattr(lib, name)
-    assert lib.zb_abi_version() == 4
+    assert lib.zb_abi_version() == 5
     h = ctypes.c_void_p()
     assert lib.zb_engine_create(None, None, 0, ctypes.byref(h)) == ZB_EINVAL
     bad = M.make_opts(dt=-1.0)

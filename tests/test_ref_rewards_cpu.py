@@ -47,3 +47,33 @@ def test_airtime_and_tables():
     assert [x[0] for x in RR.JOINT_BIASES] == M.JOINT_NAMES and np.allclose([x[1] for x in RR.JOINT_BIASES], M.BIAS_POSE)
     assert set(RR.SCALES) == {"stay_alive", "upright", "naive_forward", "naive_forward_orientation", "linvel_y_penalty", "single_foot_contact",
                               "feet_airtime", "feet_orientation", "feet_too_close", "straight_leg", "ankle_knee", "arm_pose"}  # train.py:1548-1585
+
+
+def test_product_rewards_equal_transcription_on_cpu_tensors(zmodel):
+    """ksim-gym-zbot_b200/rewards.py (torch ops, the product's reward list) against tests/ref_rewards.py on random trajectories."""
+    import types
+
+    import torch
+    from ksim_gym_zbot_b200 import rewards as PR
+
+    r = np.random.default_rng(9)
+    T, n = 7, 64
+    q = r.normal(size=(T, n, 27)).astype(np.float32) * 0.3
+    q[..., 3:7] = r.normal(size=(T, n, 4)) * r.uniform(0.6, 1.4, (T, n, 1))
+    v = r.normal(size=(T, n, 26)).astype(np.float32)
+    xq = r.normal(size=(T, n, 26, 4)).astype(np.float32)
+    rt = (r.random((T + 1, n, 6)) < 0.5).astype(np.float32)
+    dn = r.random((T, n)) < 0.1
+    air = r.normal(size=(T, n)).astype(np.float32)
+    traj = types.SimpleNamespace(qpos=torch.tensor(q), qvel=torch.tensor(v), xquat=torch.tensor(xq), reward_terms=torch.tensor(rt),
+                                 done=torch.tensor(dn.astype(np.uint8)))
+    lb, rb = int(zmodel.site_body[1]), int(zmodel.site_body[2])
+    terms = PR.reward_terms(traj, torch.tensor(air), lb, rb)
+    assert set(terms) == set(RR.SCALES) and {k: s for k, (s, _) in RR.SCALES.items()} == PR.SCALES
+    for t in range(T):
+        f = {"qpos": q[t], "qvel": v[t], "xquat": xq[t], "site_xpos": np.zeros((n, 3, 3), np.float32), "sensordata": np.zeros((n, 18), np.float32), "done": dn[t]}
+        ref = RR.step_terms(f, lb, rb)
+        for k in ("stay_alive", "upright", "naive_forward", "naive_forward_orientation", "linvel_y_penalty", "feet_orientation", "straight_leg",
+                  "ankle_knee", "arm_pose"):
+            np.testing.assert_allclose(terms[k][t].numpy(), ref[k], rtol=0, atol=5e-6, err_msg=k)
+    assert torch.equal(terms["single_foot_contact"], traj.reward_terms[:T, :, 0]) and torch.equal(terms["feet_too_close"], traj.reward_terms[:T, :, 2])
