@@ -46,6 +46,7 @@ extern "C" {
 #define ZB_NREWARD_TERMS 6 /* see ZbObs.reward_terms                          */
 
 enum { ZB_SOLVER_CG = 0, ZB_SOLVER_NEWTON = 1 };
+enum { ZB_GEOM_BOX = 0, ZB_GEOM_SPHERE = 1, ZB_GEOM_CAPSULE = 2 }; /* ZbModel.box_type / pair_type (0 = box keeps zero-filled models valid) */
 enum { ZB_INT_EULER = 0, ZB_INT_IMPLICITFAST = 1 };
 enum { ZB_ORDER_EVENT_ACT_STEP = 0, ZB_ORDER_ACT_EVENT_STEP = 1 };
 
@@ -145,7 +146,12 @@ typedef struct ZbModel {
   int32_t floor_priority;
   float floor_margin;
   float floor_gap;
-  /* foot collision boxes */
+  /* Collision groups (mjx.collision_driver's static candidate list).  Group g collides geom 2 = the box_*
+   * fields (on body box_body[g], shape box_type[g]) with geom 1 = the floor plane (pair_body[g] == 0) or a second geom on body
+   * pair_body[g] (self-collision; pair_* fields).  MJX orders a pair by geom type (plane < sphere < capsule < box) and the
+   * contact normal points from geom 1 to geom 2; primitives and contacts per group [R: mjx collision_primitive / collision_convex]:
+   *   plane-box 4 (plane_convex + _manifold_points) | plane-capsule 2 | plane-sphere 1 | sphere-sphere, sphere-capsule,
+   *   capsule-capsule 1.   zbot_syn: two foot boxes against the floor. */
   int32_t box_body[ZB_NBOX];
   float box_pos[ZB_NBOX][3];
   float box_quat[ZB_NBOX][4];
@@ -156,6 +162,18 @@ typedef struct ZbModel {
   int32_t box_priority[ZB_NBOX];
   float box_margin[ZB_NBOX];
   float box_gap[ZB_NBOX];
+  int32_t box_type[ZB_NBOX];      /* ZB_GEOM_*: box (size = half extents) | sphere (size[0] = radius) | capsule (radius, half length) */
+  int32_t pair_body[ZB_NBOX];     /* 0: geom 1 is the floor plane; else the body of geom 1                                        */
+  int32_t pair_type[ZB_NBOX];     /* ZB_GEOM_SPHERE / ZB_GEOM_CAPSULE (unused for the plane)                                      */
+  float pair_pos[ZB_NBOX][3];
+  float pair_quat[ZB_NBOX][4];
+  float pair_size[ZB_NBOX][3];
+  float pair_friction[ZB_NBOX][3];
+  float pair_solref[ZB_NBOX][2];
+  float pair_solimp[ZB_NBOX][5];
+  int32_t pair_priority[ZB_NBOX];
+  float pair_margin[ZB_NBOX];
+  float pair_gap[ZB_NBOX];
   /* sites: 0 = imu_site, 1 = left_foot, 2 = right_foot (box-shaped touch volumes) */
   int32_t site_body[ZB_NSITE];
   float site_pos[ZB_NSITE][3];

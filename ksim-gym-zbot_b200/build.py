@@ -40,15 +40,34 @@ def _nvcc_cmd(out: str, defines=(), verbose: bool = False) -> list[str]:
     return [nvcc, *NVCC_FLAGS, *defines, *(["-Xptxas", "-v"] if verbose else []), "-o", out, *[os.path.join(_CSRC, s) for s in SOURCES]]
 
 
+def _build_two_units(out: str, defines=(), verbose: bool = False) -> None:
+    """The full library = two translation units of zbphys.cu compiled in parallel (ZB_TU = 0: host code + the kernels of plane-box-only
+    models, ZB_TU = 1: the kernels of the general collision groups), then linked."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = os.path.join(_CSRC, SOURCES[0])
+    objs, procs = [], []
+    for tu in (0, 1):
+        obj = out[:-3] + f".tu{tu}.o"
+        objs.append(obj)
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], "-c", f"-DZB_TU={tu}", *defines, *(["-Xptxas", "-v"] if verbose else []), "-o", obj, src]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate()[0] for p in procs]
+    if any(p.returncode != 0 for p in procs):
+        raise RuntimeError("nvcc failed:\n" + "\n".join(logs))
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *objs], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
+    for o in objs:
+        os.remove(o)
+    if verbose:
+        print("\n".join(logs))
+
+
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu -> csrc/libzbphys.so (nvcc cross-compiles without a GPU)."""
     if not force and _newer_than_sources(LIB):
         return LIB
-    r = subprocess.run(_nvcc_cmd(LIB, (), verbose), capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    _build_two_units(LIB, (), verbose)
     return LIB
 
 
@@ -65,7 +84,10 @@ def build_variants(variants: dict[str, list[str]], force: bool = False, minimal:
         out[name] = path
         if not force and _newer_than_sources(path):
             continue
-        d = list(defines) + (["-DZB_MINIMAL"] if minimal else [])
+        if not minimal:  # a full two-unit build (sequential across variants, parallel inside)
+            _build_two_units(path, tuple(defines))
+            continue
+        d = list(defines) + ["-DZB_MINIMAL"]
         procs.append((name, subprocess.Popen(_nvcc_cmd(path, d), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for name, p in procs:
         log, _ = p.communicate()

@@ -47,6 +47,9 @@
 #ifndef ZB_EXPLICIT_J
 #define ZB_EXPLICIT_J 1 /* contact rows as explicit 12-column Jacobian rows (chain dofs + base dofs) instead of matrix-free wrench directions */
 #endif
+#ifndef ZB_RECOLLIDE
+#define ZB_RECOLLIDE 0 /* 1: sensors() re-run collision() instead of keeping contact point + frame live across the solve (more code, no gain measured) */
+#endif
 #ifndef ZB_LS_SAME
 #define ZB_LS_SAME 2 /* line search: 1 = no zone evaluation while both bracket ends share one active set, 2 = + the one-sided loop (see linesearch) */
 #endif
@@ -85,8 +88,16 @@ struct ZbDev {
   ZbSolPrm con[ZB_NBOX];           // contact rows by box (after geom-priority mixing)
   float con_includemargin[ZB_NBOX];
   float con_invweight[ZB_NBOX];    // body_invweight0[world] + body_invweight0[box body]
-  int con_mu_mode[ZB_NBOX];        // 0: floor friction (per-env), 1: box friction, 2: max of both
+  int con_mu_mode[ZB_NBOX];        // 0: floor friction (per-env), 1: con_mu_const, 2: max of both
+  float con_mu_const[ZB_NBOX];     // friction of the group after mixing, where it does not depend on the per-env floor friction
+  // collision groups (ZbModel.box_* / pair_*): primitive of each group and what the model contains at all (uniform branches)
+  int grp_kind[ZB_NBOX];           // ZB_PAIR_*
+  int any_box, any_prim, any_pair; // a plane-box group / a sphere or capsule group / a body-body group exists
+  int body_pair[32];               // group whose geom 1 this body lane carries, -1 none
+  int lane_jt[32][ZB_NBOX];        // dof lanes: index of my entry in group g's transposed J^T f totals (0..5 chain of geom 2,
+                                   // 6..11 chain of geom 1 / base dofs), -1: the group does not touch my dof
 };
+enum { ZB_PAIR_PLANE_BOX = 0, ZB_PAIR_PLANE_SPHERE, ZB_PAIR_PLANE_CAPSULE, ZB_PAIR_SPHERE_SPHERE, ZB_PAIR_SPHERE_CAPSULE, ZB_PAIR_CAPSULE_CAPSULE };
 
 struct Factor {      // block LDL^T of M (or M + dt D); every entry is zero where it does not apply to the lane
   float lc[CHD];  // Lt[gp][k], k < gp: row of the unit lower factor of the lane's group (chain block or base block)
@@ -106,10 +117,15 @@ struct LSSet {          // an active set of the line search: its summed quadrati
 
 // TRACE: compile the solver-trace diagnostics in (scripts/gpu_probe*.py); the production instantiation carries none of it.
 // FSM: the factor and the mass-matrix rows of a lane live in shared memory (throughput profile) instead of registers.
-template <bool TRACE, bool FSM>
+// GEN: general collision groups (sphere / capsule primitives, geom 1 on a body).  GEN = false is the instantiation for models whose
+// groups are all plane-box (zbot_syn): the frame is the constant floor frame and none of the extra per-lane state exists — the
+// general code costs 3.7 % there (measured), so it is compiled separately and chosen per engine.
+template <bool TRACE, bool FSM, bool GEN>
 struct WarpEnv {
   const ZbDev* D;
   ZbOpts o;           // by value from the kernel parameters: uniform-datapath registers, provably warp-uniform control flow
+  bool any_box, any_prim, any_pair;  // ZbDev.any_*, handed in as a kernel parameter for the same reason (a flag LOADED from the model
+                                     // table is not provably uniform: ptxas then wraps every later shuffle in WARPSYNC and clones the solver)
   float meaninertia;
   float* scr;  // per-warp scratch, 32 * ZB_SCR floats
   int L;
@@ -155,7 +171,9 @@ struct WarpEnv {
   // cj[6..11]: base dofs.  With it J v is 6 shuffles + 12 FMAs (instead of a 6-vector chain prefix scan + the base motion) and
   // neither cdof, w nor the base pose are read inside the solver loop.
   float cj[12];
-  int jsrc;
+  int jsrc, jsrc2;      // first lane of the chain of geom 2 / of geom 1 (BL0: the base dofs, geom 1 = the floor)
+  int pairlane;         // body lane of geom 1 of my group (0 = world)
+  float cn[3], ct[3];   // contact normal and the tangent of this lane's pyramid edge (collision())
   float cdist, cpos[3];
   // solver
   float qacc, Ma, grad, Mgrad, search, mv, qfrc_c;
@@ -169,8 +187,9 @@ struct WarpEnv {
   int lscount;
 
   // ------------------------------------------------------------------------------------------
-  ZB_DI void init_topology(const ZbDev* D_, const ZbOpts& o_, float meaninertia_, float* scr_, int lane) {
+  ZB_DI void init_topology(const ZbDev* D_, const ZbOpts& o_, float meaninertia_, float* scr_, int lane, int cflags) {
     D = D_; o = o_; meaninertia = meaninertia_; scr = scr_; L = lane;
+    any_box = GEN ? (cflags & 1) != 0 : true; any_prim = GEN && (cflags & 2) != 0; any_pair = GEN && (cflags & 4) != 0;
     isbody = L < NB;
     const int jt = isbody ? D->m.body_jnttype[L] : 0;
     hinge = jt == 2;
@@ -180,6 +199,7 @@ struct WarpEnv {
     hasdof = dof >= 0;
     chainbody = isbody && L >= 2;
     boxlane = D->m.box_body[L >> 4];
+    pairlane = D->m.pair_body[L >> 4];
   }
 
   // chain-scan helpers (bodies of one chain are contiguous lanes)
@@ -593,8 +613,13 @@ struct WarpEnv {
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < CHD; k++) s = fmaf(cj[k], shf(v, jsrc + k), s);
+    if (any_pair) {  // (kernel-uniform) some group has geom 1 on a body: its second block are that chain's dofs
 #pragma unroll
-    for (int a = 0; a < 6; a++) s = fmaf(cj[6 + a], vb[a], s);
+      for (int k = 0; k < CHD; k++) s = fmaf(cj[6 + k], shf(v, jsrc2 + k), s);
+    } else {
+#pragma unroll
+      for (int a = 0; a < 6; a++) s = fmaf(cj[6 + a], vb[a], s);
+    }
     return s;
 #else
     float pre[6];
@@ -615,7 +640,6 @@ struct WarpEnv {
   // contact and 25 cm from the COM).  Base dofs: translations J = dir, rotations (body-frame axes through the base origin) likewise.
   ZB_DI void contact_rows_jacobian() {
     jsrc = D->cs[boxlane];
-    const int g = L >> 4;
     float anc[3] = {0.f, 0.f, 0.f};
     if (hinge) {
       const float jp[3] = {D->m.jnt_pos[L][0], D->m.jnt_pos[L][1], D->m.jnt_pos[L][2]};
@@ -624,15 +648,17 @@ struct WarpEnv {
       anc[0] = xpos[0] + a[0]; anc[1] = xpos[1] + a[1]; anc[2] = xpos[2] + a[2];
     }
     const float dir[3] = {w[3], w[4], w[5]};
+    // chain of geom 2: the hinge of lane jsrc + k moves the geom iff it lies on the path base -> body of the geom
 #pragma unroll
     for (int k = 0; k < CHD; k++) {
       float ax[3], rel[3], c[3];
 #pragma unroll
       for (int j = 0; j < 3; j++) { ax[j] = shf(cdof[j], jsrc + k); rel[j] = cpos[j] - shf(anc[j], jsrc + k); }
-      const int lb = __shfl_sync(ZB_FULL, lbox, jsrc + k);  // the dof of lane jsrc + k moves my box iff its lane_box is mine
+      const int hk = __shfl_sync(ZB_FULL, (int)hinge, jsrc + k);
       cross3(c, ax, rel);
-      cj[k] = (lb == g) ? dot3(dir, c) : 0.f;
+      cj[k] = (hk && jsrc + k <= boxlane) ? dot3(dir, c) : 0.f;
     }
+    // second block: base dofs (geom 1 = the floor plane: translations J = dir, rotations about the body-frame axes through the base origin)
     const float rel[3] = {cpos[0] - xb[0], cpos[1] - xb[1], cpos[2] - xb[2]};
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -641,6 +667,27 @@ struct WarpEnv {
       cross3(c, col, rel);
       cj[6 + a] = dir[a];
       cj[9 + a] = dot3(dir, c);
+    }
+    jsrc2 = BL0;
+    if (any_pair) {
+      // ... or the chain of geom 1 with the opposite sign (support.jac_dif_pair; the base dofs move both geoms alike and cancel).
+      // The shuffles are executed by every lane; lanes of floor groups keep their base block.
+      const bool pair = pairlane != 0;
+      const int j2 = pair ? D->cs[pairlane] : BL0;
+#pragma unroll
+      for (int k = 0; k < CHD; k++) {
+        float ax[3], rl[3], c[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) { ax[j] = shf(cdof[j], (j2 + k) & 31); rl[j] = cpos[j] - shf(anc[j], (j2 + k) & 31); }
+        const int hk = __shfl_sync(ZB_FULL, (int)hinge, (j2 + k) & 31);
+        cross3(c, ax, rl);
+        const float v = (hk && j2 + k <= pairlane) ? -dot3(dir, c) : 0.f;
+        if (pair) {
+          if (j2 == jsrc) { cj[k] += v; cj[6 + k] = 0.f; }  // both geoms hang on the same chain
+          else cj[6 + k] = v;
+        }
+      }
+      jsrc2 = j2;
     }
   }
 
@@ -683,7 +730,17 @@ struct WarpEnv {
         p[j] = keep + __shfl_xor_sync(ZB_FULL, send, m);
       }
     }
-    // chain dof at position gp of box lbox reads lane 16 lbox + gp; base dof a reads the sum over both boxes from lane 6 + a
+    if (any_pair) {  // (kernel-uniform) general candidate list: every dof lane picks its entry of each group's totals (ZbDev.lane_jt)
+      float r = 0.f;
+#pragma unroll
+      for (int g = 0; g < ZB_NBOX; g++) {
+        const int idx = D->lane_jt[L][g];
+        const float t = shf(p[0], 16 * g + (idx < 0 ? 0 : idx));
+        r += idx < 0 ? 0.f : t;
+      }
+      return r;
+    }
+    // floor groups only: chain dof at position gp of box lbox reads lane 16 lbox + gp; base dof a reads the sum over both boxes from lane 6 + a
     const float both = p[0] + shx(p[0], 16);  // (executed by all lanes)
     const float pub = ((L & 15) >= 6) ? both : p[0];
     const bool leg = hinge && lbox >= 0;
@@ -833,6 +890,7 @@ struct WarpEnv {
   ZB_DI void collision() {
     const ZbModel& m = D->m;
     const int g = L >> 4;
+    // world pose of the geoms: the body lanes compute theirs, the row lanes fetch the two of their group
     float gpos[3] = {0.f, 0.f, 0.f}, gmat[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     if (isbody && D->body_box[L] >= 0) {
       const int gb = D->body_box[L];
@@ -849,6 +907,152 @@ struct WarpEnv {
     for (int k = 0; k < 3; k++) bp[k] = shf(gpos[k], boxlane);
 #pragma unroll
     for (int k = 0; k < 9; k++) bm[k] = shf(gmat[k], boxlane);
+    const float pn[3] = {m.floor_normal[0], m.floor_normal[1], m.floor_normal[2]};
+    // defaults: inert slot, floor frame (D->frame = make_frame(floor normal): rows n, t1, t2)
+    const int e = L & 3, s = (L >> 2) & 3;
+    if (GEN) {
+      const float* fr = D->frame;
+      cdist = 1.f; cpos[0] = cpos[1] = cpos[2] = 0.f;
+      cn[0] = fr[0]; cn[1] = fr[1]; cn[2] = fr[2];
+      ct[0] = fr[3 * (1 + (e >> 1))]; ct[1] = fr[3 * (1 + (e >> 1)) + 1]; ct[2] = fr[3 * (1 + (e >> 1)) + 2];
+    }
+    if (any_box) collide_plane_box(bp, bm);
+    if (GEN && (any_prim || any_pair)) {
+      // sphere / capsule primitives (mjx collision_primitive [R]): plain per-lane arithmetic, every row lane evaluates its own slot
+      const int kind = D->grp_kind[g];
+      const float r2 = m.box_size[g][0], h2 = m.box_size[g][1];
+      const float ax2[3] = {bm[2], bm[5], bm[8]};
+      const float ppl[3] = {m.floor_pos[0], m.floor_pos[1], m.floor_pos[2]};
+      if (kind == ZB_PAIR_PLANE_SPHERE || kind == ZB_PAIR_PLANE_CAPSULE) {
+        // plane_sphere / plane_capsule: capsule = two spheres at the segment ends (slots 0, 1), frame aligned with the capsule axis
+        const float sg = (kind == ZB_PAIR_PLANE_CAPSULE) ? (s == 0 ? 1.f : -1.f) * h2 : 0.f;
+        const float c[3] = {bp[0] + sg * ax2[0], bp[1] + sg * ax2[1], bp[2] + sg * ax2[2]};
+        const float rel[3] = {c[0] - ppl[0], c[1] - ppl[1], c[2] - ppl[2]};
+        const float dist = dot3(rel, pn) - r2;
+        const bool live = s < (kind == ZB_PAIR_PLANE_CAPSULE ? 2 : 1);
+        cdist = live ? dist : 1.f;
+        const float back = r2 + 0.5f * dist;
+        cpos[0] = c[0] - pn[0] * back; cpos[1] = c[1] - pn[1] * back; cpos[2] = c[2] - pn[2] * back;
+        if (kind == ZB_PAIR_PLANE_CAPSULE) {
+          const float na = dot3(pn, ax2);
+          float b[3] = {ax2[0] - pn[0] * na, ax2[1] - pn[1] * na, ax2[2] - pn[2] * na};
+          const float bn = sqrtf(dot3(b, b));
+          const float sc = 1.f / (bn + 1e-6f * (bn == 0.f));
+          b[0] *= sc; b[1] *= sc; b[2] *= sc;
+          if (bn < 0.5f) { const bool yy = -0.5f < pn[1] && pn[1] < 0.5f; b[0] = 0.f; b[1] = yy ? 1.f : 0.f; b[2] = yy ? 0.f : 1.f; }
+          float t2[3];
+          cross3(t2, pn, b);
+          cn[0] = pn[0]; cn[1] = pn[1]; cn[2] = pn[2];
+#pragma unroll
+          for (int k = 0; k < 3; k++) ct[k] = (e >> 1) ? t2[k] : b[k];
+        }
+      }
+      if (any_pair) {
+        // geom 1 on a body (self-collision): sphere_sphere / sphere_capsule / capsule_capsule, one contact, normal from geom 1 to geom 2
+        float qpos_[3] = {0.f, 0.f, 0.f}, qax[3] = {0.f, 0.f, 1.f};
+        if (isbody && D->body_pair[L] >= 0) {
+          const int gb = D->body_pair[L];
+          const float pp_[3] = {m.pair_pos[gb][0], m.pair_pos[gb][1], m.pair_pos[gb][2]};
+          const float pq_[4] = {m.pair_quat[gb][0], m.pair_quat[gb][1], m.pair_quat[gb][2], m.pair_quat[gb][3]};
+          float r[3], qq[4], R[9];
+          mat_vec(r, xmat, pp_);
+          qpos_[0] = xpos[0] + r[0]; qpos_[1] = xpos[1] + r[1]; qpos_[2] = xpos[2] + r[2];
+          quat_mul(qq, xquat, pq_);
+          quat_to_mat(R, qq);
+          qax[0] = R[2]; qax[1] = R[5]; qax[2] = R[8];
+        }
+        float p1[3], ax1[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { p1[k] = shf(qpos_[k], pairlane); ax1[k] = shf(qax[k], pairlane); }
+        if (kind >= ZB_PAIR_SPHERE_SPHERE) {
+          const float r1 = m.pair_size[g][0], h1 = m.pair_size[g][1];
+          float q1[3] = {p1[0], p1[1], p1[2]}, q2[3] = {bp[0], bp[1], bp[2]};
+          if (kind == ZB_PAIR_SPHERE_CAPSULE) {
+            const float a[3] = {bp[0] - ax2[0] * h2, bp[1] - ax2[1] * h2, bp[2] - ax2[2] * h2};
+            const float b[3] = {bp[0] + ax2[0] * h2, bp[1] + ax2[1] * h2, bp[2] + ax2[2] * h2};
+            closest_segment_point(q2, a, b, p1);
+          } else if (kind == ZB_PAIR_CAPSULE_CAPSULE) {
+            const float a0[3] = {p1[0] - ax1[0] * h1, p1[1] - ax1[1] * h1, p1[2] - ax1[2] * h1};
+            const float a1[3] = {p1[0] + ax1[0] * h1, p1[1] + ax1[1] * h1, p1[2] + ax1[2] * h1};
+            const float b0[3] = {bp[0] - ax2[0] * h2, bp[1] - ax2[1] * h2, bp[2] - ax2[2] * h2};
+            const float b1[3] = {bp[0] + ax2[0] * h2, bp[1] + ax2[1] * h2, bp[2] + ax2[2] * h2};
+            closest_segment_to_segment(q1, q2, a0, a1, b0, b1);
+          }
+          // _sphere_sphere
+          const float dl[3] = {q2[0] - q1[0], q2[1] - q1[1], q2[2] - q1[2]};
+          const float len = sqrtf(dot3(dl, dl));
+          const float sc = 1.f / (len + 1e-6f * (len == 0.f));
+          float n[3] = {dl[0] * sc, dl[1] * sc, dl[2] * sc};
+          if (len == 0.f) { n[0] = 1.f; n[1] = 0.f; n[2] = 0.f; }
+          const float dist = len - (r1 + r2);
+          cdist = s == 0 ? dist : 1.f;
+          const float fwd = r1 + 0.5f * dist;
+          cpos[0] = q1[0] + n[0] * fwd; cpos[1] = q1[1] + n[1] * fwd; cpos[2] = q1[2] + n[2] * fwd;
+          float t1[3], t2[3];
+          make_frame_tangents(n, t1, t2);
+          cn[0] = n[0]; cn[1] = n[1]; cn[2] = n[2];
+#pragma unroll
+          for (int k = 0; k < 3; k++) ct[k] = (e >> 1) ? t2[k] : t1[k];
+        }
+      }
+    }
+  }
+
+  // math.make_frame(n) [R]: n normalised, b = y (or z when n is close to y), Gram-Schmidt, t2 = n x b
+  static ZB_DI void make_frame_tangents(float (&a)[3], float (&b)[3], float (&c)[3]) {
+    float nn = sqrtf(dot3(a, a));
+    float sc = 1.f / (nn + 1e-6f * (nn == 0.f));
+    a[0] *= sc; a[1] *= sc; a[2] *= sc;
+    const bool yy = -0.5f < a[1] && a[1] < 0.5f;
+    b[0] = 0.f; b[1] = yy ? 1.f : 0.f; b[2] = yy ? 0.f : 1.f;
+    const float ab = dot3(a, b);
+    b[0] -= a[0] * ab; b[1] -= a[1] * ab; b[2] -= a[2] * ab;
+    nn = sqrtf(dot3(b, b));
+    sc = 1.f / (nn + 1e-6f * (nn == 0.f));
+    b[0] *= sc; b[1] *= sc; b[2] *= sc;
+    cross3(c, a, b);
+  }
+  // math.closest_segment_point [R]
+  static ZB_DI void closest_segment_point(float (&out)[3], const float (&a)[3], const float (&b)[3], const float (&pt)[3]) {
+    const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ap[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+    float t = dot3(ap, ab) / (dot3(ab, ab) + 1e-6f);
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    out[0] = a[0] + t * ab[0]; out[1] = a[1] + t * ab[1]; out[2] = a[2] + t * ab[2];
+  }
+  // math.closest_segment_to_segment_points [R]
+  static ZB_DI void closest_segment_to_segment(float (&best_a)[3], float (&best_b)[3], const float (&a0)[3], const float (&a1)[3],
+                                               const float (&b0)[3], const float (&b1)[3]) {
+    float da[3] = {a1[0] - a0[0], a1[1] - a0[1], a1[2] - a0[2]}, db[3] = {b1[0] - b0[0], b1[1] - b0[1], b1[2] - b0[2]};
+    const float la = sqrtf(dot3(da, da)), lb = sqrtf(dot3(db, db));
+    const float sa = 1.f / (la + 1e-6f * (la == 0.f)), sb = 1.f / (lb + 1e-6f * (lb == 0.f));
+    da[0] *= sa; da[1] *= sa; da[2] *= sa; db[0] *= sb; db[1] *= sb; db[2] *= sb;
+    const float ha = la * 0.5f, hb = lb * 0.5f;
+    float am[3], bmid[3], tr[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { am[k] = a0[k] + da[k] * ha; bmid[k] = b0[k] + db[k] * hb; tr[k] = am[k] - bmid[k]; }
+    const float dd = dot3(da, db), dat = dot3(da, tr), dbt = dot3(db, tr);
+    const float denom = 1.f - dd * dd;
+    float ta = (-dat + dd * dbt) / (denom + 1e-6f);
+    float tb = dbt + ta * dd;
+    ta = fminf(fmaxf(ta, -ha), ha);
+    tb = fminf(fmaxf(tb, -hb), hb);
+    float ba[3], bb[3], na[3], nb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { ba[k] = am[k] + da[k] * ta; bb[k] = bmid[k] + db[k] * tb; }
+    closest_segment_point(na, a0, a1, bb);
+    closest_segment_point(nb, b0, b1, ba);
+    const float e1[3] = {na[0] - bb[0], na[1] - bb[1], na[2] - bb[2]}, e2[3] = {ba[0] - nb[0], ba[1] - nb[1], ba[2] - nb[2]};
+    const bool first = dot3(e1, e1) < dot3(e2, e2);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { best_a[k] = first ? na[k] : ba[k]; best_b[k] = first ? bb[k] : nb[k]; }
+  }
+
+  // collision_convex.plane_convex + _manifold_points for the box groups: every lane evaluates vertex (L & 7) of the box of its
+  // half-warp; 8-lane groups pick the manifold; lane r then becomes row r.  (Shuffles inside: executed by ALL lanes; lanes of
+  // other primitives discard the result.)
+  ZB_DI void collide_plane_box(const float (&bp)[3], const float (&bm)[9]) {
+    const ZbModel& m = D->m;
+    const int g = L >> 4;
     const float pn[3] = {m.floor_normal[0], m.floor_normal[1], m.floor_normal[2]};
     const float rel[3] = {m.floor_pos[0] - bp[0], m.floor_pos[1] - bp[1], m.floor_pos[2] - bp[2]};
     float ppl[3], nl[3];
@@ -888,10 +1092,12 @@ struct WarpEnv {
     const float dist = uniq ? -ZB_SUPPORT(mvv) : 1.f;
     float vw[3];
     mat_vec(vw, bm, mvv);
-    cdist = dist;
-    cpos[0] = bp[0] + vw[0] - 0.5f * dist * pn[0];
-    cpos[1] = bp[1] + vw[1] - 0.5f * dist * pn[1];
-    cpos[2] = bp[2] + vw[2] - 0.5f * dist * pn[2];
+    if (!GEN || D->grp_kind[g] == ZB_PAIR_PLANE_BOX) {
+      cdist = dist;
+      cpos[0] = bp[0] + vw[0] - 0.5f * dist * pn[0];
+      cpos[1] = bp[1] + vw[1] - 0.5f * dist * pn[1];
+      cpos[2] = bp[2] + vw[2] - 0.5f * dist * pn[2];
+    }
 #undef ZB_VERT
 #undef ZB_SUPPORT
   }
@@ -910,8 +1116,8 @@ struct WarpEnv {
   // friction coefficient of this lane's contact (geom-priority mixing done on the host: con_mu_mode)
   ZB_DI float contact_mu() const {
     const int g = L >> 4;
-    const float bf = D->m.box_friction[g][0];
-    return D->con_mu_mode[g] == 0 ? mu : (D->con_mu_mode[g] == 1 ? bf : fmaxf(mu, bf));
+    const float cf = D->con_mu_const[g];
+    return D->con_mu_mode[g] == 0 ? mu : (D->con_mu_mode[g] == 1 ? cf : fmaxf(mu, cf));
   }
   // w = [(pos - c0) x dir ; dir], dir = n +- mu t: the wrench (about the tree COM) a unit force along this lane's pyramid edge exerts
   ZB_DI void row_wrench() {
@@ -919,9 +1125,14 @@ struct WarpEnv {
     const int e = L & 3;
     float sgn = (e & 1) ? -1.f : 1.f;
     if (ZB_MUTANT == 1 && ((L >> 2) & 3) == 2 && e == 3) sgn = 1.f;  // (mutant 1: manifold slot 2 loses a facet of its friction pyramid)
-    const float* fr = D->frame;
-    const float* tt = fr + 3 * (1 + (e >> 1));
-    const float dir[3] = {fr[0] + sgn * cmu * tt[0], fr[1] + sgn * cmu * tt[1], fr[2] + sgn * cmu * tt[2]};
+    float dir[3];
+    if (GEN) {
+      dir[0] = cn[0] + sgn * cmu * ct[0]; dir[1] = cn[1] + sgn * cmu * ct[1]; dir[2] = cn[2] + sgn * cmu * ct[2];
+    } else {  // the floor frame, a model constant
+      const float* fr = D->frame;
+      const float* tt = fr + 3 * (1 + (e >> 1));
+      dir[0] = fr[0] + sgn * cmu * tt[0]; dir[1] = fr[1] + sgn * cmu * tt[1]; dir[2] = fr[2] + sgn * cmu * tt[2];
+    }
     const float off[3] = {cpos[0] - c0[0], cpos[1] - c0[1], cpos[2] - c0[2]};
     float tq[3];
     cross3(tq, off, dir);
@@ -969,6 +1180,10 @@ struct WarpEnv {
       float vf[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) vf[k] = shf(cvel[k], boxlane);
+      if (any_pair) {  // (kernel-uniform) geom 1 on a body: relative velocity (cvel of the world lane is zero)
+#pragma unroll
+        for (int k = 0; k < 6; k++) vf[k] -= shf(cvel[k], pairlane);
+      }
       c_D = 0.f; c_aref = 0.f;
       if (c_on) {
         const float imp = impedance(sp, dist);
@@ -1499,13 +1714,21 @@ struct WarpEnv {
     motion_cross_force(u, cvel, t);
     const int mybox = isbody ? D->body_box[L] : -1;
 #if ZB_EXPLICIT_J
+#if ZB_RECOLLIDE
+    collision();   // contact point and frame recomputed from the (still live) body poses instead of living in registers across the solve
+#endif
     row_wrench();  // recomputed here (20 instructions, last substep only) instead of living in 6 registers across the solve
 #endif
-    const float Wtot = contact_wrench(c_force);  // cfrc_ext of a foot = the solver's total contact wrench of its box
+    const float Wtot = contact_wrench(c_force);  // cfrc_ext of a foot = the solver's total contact wrench of its group
+    const int mypair = (any_pair && isbody) ? D->body_pair[L] : -1;  // ... and the body of geom 1 feels the reaction
 #pragma unroll
     for (int k = 0; k < 6; k++) {
       const float ext = shf(Wtot, (mybox >= 0 ? 16 * mybox : 0) + 2 * k);
       cf[k] = isbody ? cf[k] + u[k] - (mybox >= 0 ? ext : 0.f) : 0.f;
+      if (any_pair) {
+        const float rea = shf(Wtot, (mypair >= 0 ? 16 * mypair : 0) + 2 * k);
+        cf[k] += mypair >= 0 ? rea : 0.f;
+      }
     }
     chain_suffix<6>(cf);
     const int s = isbody ? D->body_site[L] : -1;

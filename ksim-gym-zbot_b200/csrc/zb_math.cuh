@@ -107,4 +107,4 @@ ZB_DI float signf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
 
 // general x^p for the solimp power (default power == 2 never gets here); out of line so that the libdevice powf body
 // exists once and stays out of the hot instruction stream
-__device__ __noinline__ float zb_pow(float x, float p) { return powf(x, p); }
+static __device__ __noinline__ float zb_pow(float x, float p) { return powf(x, p); }

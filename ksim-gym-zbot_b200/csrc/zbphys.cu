@@ -58,6 +58,8 @@ static CtaShape shape_policy(int n_envs, int sms, int force_wpb, bool wide_avail
   if (w > ZB_WPB_WIDE) w = ZB_WPB_WIDE;
   return {true, w};
 }
+static bool uses_gen(const ZbEngine* e) { return e->host.any_prim || e->host.any_pair; }  // general collision instantiations (TU 1)
+static int cflags_of(const ZbEngine* e) { return (e->host.any_box ? 1 : 0) | (e->host.any_prim ? 2 : 0) | (e->host.any_pair ? 4 : 0); }
 static CtaShape pick_shape(const ZbEngine* e, int n_envs, bool wide_available) { return shape_policy(n_envs, e->num_sms, e->force_wpb, wide_available); }
 
 // Launches go to the engine's device whatever the caller's current device is (an engine on device k used from a thread whose
@@ -85,8 +87,8 @@ static int fail(int code, const char* fmt, const char* a = "") {
 // the kernel
 // ---------------------------------------------------------------------------------------------
 // OBS: the observation epilogue is a separate instantiation so that the plain step keeps its register allocation
-template <int MODE, bool TRACE, bool OBS, int WPB>
-__global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict__ D, ZbOpts o, float meaninertia, ZbEnvParams P, ZbState S,
+template <int MODE, bool TRACE, bool OBS, int WPB, bool GEN>
+__global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict__ D, ZbOpts o, float meaninertia, int cflags, ZbEnvParams P, ZbState S,
                                                        const float* __restrict__ action, const float* __restrict__ push_rand,
                                                        int push_per_substep, ZbOut O, int n_envs, int n_substeps,
                                                        const uint8_t* __restrict__ done, const float* __restrict__ rq,
@@ -127,8 +129,8 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   // throughput profile: factor + mass-matrix rows of every lane in (dynamic) shared memory, 31 x 128 B per warp
   constexpr bool FSM = WPB > ZB_WPB;
   extern __shared__ float dyn_smem[];
-  WarpEnv<TRACE, FSM> E;
-  E.init_topology(D, o, meaninertia, scratch[wib], L);
+  WarpEnv<TRACE, FSM, GEN> E;
+  E.init_topology(D, o, meaninertia, scratch[wib], L, cflags);
   E.fsm = FSM ? dyn_smem + (size_t)wib * (32 * 31) + L : nullptr;
   const int b = E.isbody ? L : 0;
   const int d = E.hasdof ? E.dof : 0;
@@ -371,6 +373,79 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// launch dispatch.  The library is built from TWO translation units of this one source (build.py compiles them in parallel):
+//   ZB_TU == 0: host code + the kernels for models whose collision groups are all plane-box (GEN = false: zbot_syn);
+//   ZB_TU == 1: the kernels of the general collision groups (GEN = true), reached through zb_gen_launch / zb_gen_init.
+// ZB_MINIMAL builds (variants, mutants) are TU 0 alone: plain step (both profiles, + trace) and plain reset, GEN = false only.
+// ---------------------------------------------------------------------------------------------
+struct KArgs {
+  const ZbDev* D; ZbOpts o; float meaninertia; int cflags; ZbEnvParams P; ZbState S; const float* action; const float* push_rand;
+  int push_per_substep; ZbOut O; int n_envs, n_substeps; const uint8_t* done; const float *rq, *rv, *rt; ZbAutoReset AR; ZbObs OB;
+};
+#define ZB_KLAUNCH(MODE, TR, OBSV, W, GENV)                                                                                        \
+  zb_kernel<MODE, TR, OBSV, W, GENV><<<grid, threads, smem, st>>>(a.D, a.o, a.meaninertia, a.cflags, a.P, a.S, a.action, a.push_rand, \
+                                                                 a.push_per_substep, a.O, a.n_envs, a.n_substeps, a.done, a.rq, a.rv, a.rt, a.AR, a.OB)
+// returns false when the requested instantiation is not part of this build
+template <bool GENV>
+static bool launch_kernel(int mode, bool trace, bool obs, bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KArgs& a) {
+  if (mode == ZB_MODE_STEP) {
+    if (!trace && !obs) { if (wide) ZB_KLAUNCH(ZB_MODE_STEP, false, false, ZB_WPB_WIDE, GENV); else ZB_KLAUNCH(ZB_MODE_STEP, false, false, ZB_WPB, GENV); return true; }
+    if (trace && !obs && !wide) { ZB_KLAUNCH(ZB_MODE_STEP, true, false, ZB_WPB, GENV); return true; }
+#if !defined(ZB_MINIMAL) || defined(ZB_MINIMAL_OBS)
+    if (!trace && obs && wide) { ZB_KLAUNCH(ZB_MODE_STEP, false, true, ZB_WPB_WIDE, GENV); return true; }
+#endif
+#ifndef ZB_MINIMAL
+    if (!trace && obs && !wide) { ZB_KLAUNCH(ZB_MODE_STEP, false, true, ZB_WPB, GENV); return true; }
+    if constexpr (!GENV) { if (trace && obs && !wide) { ZB_KLAUNCH(ZB_MODE_STEP, true, true, ZB_WPB, false); return true; } }
+#endif
+    return false;
+  }
+  if (wide) return false;
+  if (mode == ZB_MODE_RESET) {
+    if (!trace && !obs) { ZB_KLAUNCH(ZB_MODE_RESET, false, false, ZB_WPB, GENV); return true; }
+#ifndef ZB_MINIMAL
+    if (!trace && obs) { ZB_KLAUNCH(ZB_MODE_RESET, false, true, ZB_WPB, GENV); return true; }
+    if constexpr (!GENV) { if (trace) { if (obs) ZB_KLAUNCH(ZB_MODE_RESET, true, true, ZB_WPB, false); else ZB_KLAUNCH(ZB_MODE_RESET, true, false, ZB_WPB, false); return true; } }
+#endif
+    return false;
+  }
+#ifndef ZB_MINIMAL
+  if (mode == ZB_MODE_FORWARD && !obs) {
+    if (!trace) { ZB_KLAUNCH(ZB_MODE_FORWARD, false, false, ZB_WPB, GENV); return true; }
+    if constexpr (!GENV) { ZB_KLAUNCH(ZB_MODE_FORWARD, true, false, ZB_WPB, false); return true; }
+  }
+#endif
+  return false;
+}
+template <bool GENV>
+static cudaError_t init_kernels() {  // the throughput-profile kernels keep 31 floats per lane in dynamic shared memory: 28 warps x 3968 B = 108.5 KB > the 48 KB default
+  const int bytes = ZB_WPB_WIDE * ZB_FSM_BYTES_PER_WARP;
+  cudaError_t a1 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, false, ZB_WPB_WIDE, GENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#if !defined(ZB_MINIMAL) || defined(ZB_MINIMAL_OBS)
+  cudaError_t a2 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, true, ZB_WPB_WIDE, GENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#else
+  cudaError_t a2 = cudaSuccess;
+#endif
+  return a1 != cudaSuccess ? a1 : a2;
+}
+#ifndef ZB_TU
+#define ZB_TU 0
+#endif
+#if ZB_TU == 1
+bool zb_gen_launch(int mode, bool trace, bool obs, bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KArgs& a) {
+  return launch_kernel<true>(mode, trace, obs, wide, grid, threads, smem, st, a);
+}
+cudaError_t zb_gen_init() { return init_kernels<true>(); }
+#else
+#ifdef ZB_MINIMAL
+static bool zb_gen_launch(int, bool, bool, bool, int, int, size_t, cudaStream_t, const KArgs&) { return false; }
+static cudaError_t zb_gen_init() { return cudaSuccess; }
+#else
+bool zb_gen_launch(int mode, bool trace, bool obs, bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KArgs& a);  // TU 1
+cudaError_t zb_gen_init();
+#endif
+
 // ksim BadZTermination + NotUprightTermination + EpisodeLengthTermination as configured at train.py:1588-1593 (+ non-finite guard),
 // one thread per env.
 __global__ void zb_term_kernel(const float* __restrict__ qpos, const int32_t* __restrict__ flags, const float* __restrict__ time,
@@ -466,11 +541,21 @@ static void derive_solprm(ZbDev* D) {
     D->lim[L] = h_solprm(D->o, m.jnt_solref[d], m.jnt_solimp[d]);
   }
   for (int g = 0; g < ZB_NBOX; g++) {
-    const bool floor_wins = m.floor_priority >= m.box_priority[g];
-    D->con[g] = h_solprm(D->o, floor_wins ? m.floor_solref : m.box_solref[g], floor_wins ? m.floor_solimp : m.box_solimp[g]);
-    D->con_mu_mode[g] = m.floor_priority > m.box_priority[g] ? 0 : (m.floor_priority < m.box_priority[g] ? 1 : 2);
-    D->con_includemargin[g] = fmaxf(m.floor_margin, m.box_margin[g]) - fmaxf(m.floor_gap, m.box_gap[g]);
-    D->con_invweight[g] = m.body_invweight0[0][0] + m.body_invweight0[m.box_body[g]][0];
+    // contact parameter mixing (collision_driver): the higher geom_priority wins, a tie takes the larger friction and geom 1's solref / solimp
+    const bool world = m.pair_body[g] == 0;
+    const int p1 = world ? m.floor_priority : m.pair_priority[g], p2 = m.box_priority[g];
+    const float* sr1 = world ? m.floor_solref : m.pair_solref[g];
+    const float* si1 = world ? m.floor_solimp : m.pair_solimp[g];
+    D->con[g] = h_solprm(D->o, p1 >= p2 ? sr1 : m.box_solref[g], p1 >= p2 ? si1 : m.box_solimp[g]);
+    if (world) {  // the floor friction is a per-environment field (train.py:1446-1448)
+      D->con_mu_mode[g] = p1 > p2 ? 0 : (p1 < p2 ? 1 : 2);
+      D->con_mu_const[g] = m.box_friction[g][0];
+    } else {
+      D->con_mu_mode[g] = 1;
+      D->con_mu_const[g] = p1 > p2 ? m.pair_friction[g][0] : (p1 < p2 ? m.box_friction[g][0] : fmaxf(m.pair_friction[g][0], m.box_friction[g][0]));
+    }
+    D->con_includemargin[g] = fmaxf(world ? m.floor_margin : m.pair_margin[g], m.box_margin[g]) - fmaxf(world ? m.floor_gap : m.pair_gap[g], m.box_gap[g]);
+    D->con_invweight[g] = m.body_invweight0[m.pair_body[g]][0] + m.body_invweight0[m.box_body[g]][0];
   }
 }
 
@@ -521,10 +606,30 @@ static int derive(ZbDev* D) {
     if (dof < 6 || dof >= NV) return fail(ZB_EINVAL, "model: act_dof out of range%s");
     D->lane_act[m.dof_body[dof]] = j;
   }
+  D->any_box = D->any_prim = D->any_pair = 0;
+  for (int L = 0; L < 32; L++) {
+    D->body_pair[L] = -1;
+    for (int g = 0; g < ZB_NBOX; g++) D->lane_jt[L][g] = -1;
+  }
   for (int g = 0; g < ZB_NBOX; g++) {
-    const int bb = m.box_body[g];
-    if (bb < 2 || bb >= NB) return fail(ZB_EUNSUP, "model: foot box must sit on a chain body%s");
+    const int bb = m.box_body[g], b1 = m.pair_body[g], t2 = m.box_type[g], t1 = m.pair_type[g];
+    if (bb < 2 || bb >= NB) return fail(ZB_EUNSUP, "model: the geom of a collision group must sit on a chain body%s");
     if (D->body_box[bb] >= 0) return fail(ZB_EUNSUP, "model: one box per body%s");
+    if (t2 != ZB_GEOM_BOX && t2 != ZB_GEOM_SPHERE && t2 != ZB_GEOM_CAPSULE) return fail(ZB_EINVAL, "model: unknown box_type%s");
+    if (b1 == 0) {
+      D->grp_kind[g] = t2 == ZB_GEOM_BOX ? ZB_PAIR_PLANE_BOX : (t2 == ZB_GEOM_SPHERE ? ZB_PAIR_PLANE_SPHERE : ZB_PAIR_PLANE_CAPSULE);
+      if (t2 == ZB_GEOM_BOX) D->any_box = 1; else D->any_prim = 1;
+    } else {
+      // mjx orders a pair by geom type (sphere < capsule): geom 1 = pair_*, geom 2 = box_*
+      if (b1 < 2 || b1 >= NB || b1 == bb) return fail(ZB_EUNSUP, "model: pair_body must be another chain body (or 0 = the floor)%s");
+      if (t1 == ZB_GEOM_SPHERE && t2 == ZB_GEOM_SPHERE) D->grp_kind[g] = ZB_PAIR_SPHERE_SPHERE;
+      else if (t1 == ZB_GEOM_SPHERE && t2 == ZB_GEOM_CAPSULE) D->grp_kind[g] = ZB_PAIR_SPHERE_CAPSULE;
+      else if (t1 == ZB_GEOM_CAPSULE && t2 == ZB_GEOM_CAPSULE) D->grp_kind[g] = ZB_PAIR_CAPSULE_CAPSULE;
+      else return fail(ZB_EUNSUP, "model: body-body groups: sphere-sphere, sphere-capsule (sphere = geom 1), capsule-capsule%s");
+      if (D->body_pair[b1] >= 0) return fail(ZB_EUNSUP, "model: one geom 1 per body%s");
+      D->body_pair[b1] = g;
+      D->any_pair = 1;
+    }
     D->body_box[bb] = g;
     for (int c = D->cs[bb]; c <= bb; c++)
       if (m.body_jnttype[c] == 2) {
@@ -538,6 +643,19 @@ static int derive(ZbDev* D) {
     if (sb < 1 || sb >= NB || D->body_site[sb] >= 0) return fail(ZB_EUNSUP, "model: one site per (non-world) body%s");
     D->body_site[sb] = s;
     if (s > 0 && D->body_box[sb] >= 0) D->box_site[D->body_box[sb]] = s;
+  }
+  // lane_jt: which entry of group g's transposed J^T f totals belongs to the dof of lane L (contact_jtf, contact_rows_jacobian)
+  for (int g = 0; g < ZB_NBOX; g++) {
+    const int bb = m.box_body[g], b1 = m.pair_body[g];
+    for (int c = D->cs[bb]; c <= bb; c++)
+      if (m.body_jnttype[c] == 2) D->lane_jt[c][g] = D->gp[c];
+    if (b1 == 0) {
+      for (int a = 0; a < 6; a++) D->lane_jt[BL0 + a][g] = 6 + a;
+    } else {
+      const bool same_chain = D->cs[b1] == D->cs[bb];
+      for (int c = D->cs[b1]; c <= b1; c++)
+        if (m.body_jnttype[c] == 2) D->lane_jt[c][g] = same_chain ? D->gp[c] : 6 + D->gp[c];  // (same chain: the two blocks are merged into the first)
+    }
   }
   {  // math.make_frame(floor_normal)
     float a[3] = {m.floor_normal[0], m.floor_normal[1], m.floor_normal[2]};
@@ -559,6 +677,11 @@ static int derive(ZbDev* D) {
   return ZB_OK;
 }
 
+static int check_model_opts(const ZbDev* D, const ZbOpts* o) {
+  if (D->any_pair && o->solver == ZB_SOLVER_NEWTON)
+    return fail(ZB_EUNSUP, "Newton solver with body-body collision groups: the Hessian loses its block-arrow structure (use CG)%s");
+  return ZB_OK;
+}
 static int check_opts(const ZbOpts* o) {
   if (!(o->dt > 0) || o->iterations < 0 || o->ls_iterations < 0 || !(o->impratio > 0)) return fail(ZB_EINVAL, "opts: dt/iterations/impratio invalid%s");
   if (o->solver != ZB_SOLVER_CG && o->solver != ZB_SOLVER_NEWTON) return fail(ZB_EINVAL, "opts: unknown solver%s");
@@ -610,22 +733,18 @@ int zb_engine_create(const ZbModel* model, const ZbOpts* opts, int device, ZbEng
     if (v >= 1 && v <= ZB_WPB_WIDE) e->force_wpb = v;  // > ZB_WPB selects the throughput profile
   }
   rc = derive(&e->host);
+  if (!rc) rc = check_model_opts(&e->host, opts);
   if (rc) { delete e; return rc; }
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(device);
-  {  // the throughput-profile kernels keep 31 floats per lane in dynamic shared memory: 28 warps x 3968 B = 108.5 KB > the 48 KB default
-    const int bytes = ZB_WPB_WIDE * ZB_FSM_BYTES_PER_WARP;
-    cudaError_t a1 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, false, ZB_WPB_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-#if defined(ZB_MINIMAL) && !defined(ZB_MINIMAL_OBS)
-    cudaError_t a2 = cudaSuccess;
-#else
-    cudaError_t a2 = cudaFuncSetAttribute(zb_kernel<ZB_MODE_STEP, false, true, ZB_WPB_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-#endif
-    if (a1 != cudaSuccess || a2 != cudaSuccess) {
+  {
+    cudaError_t a1 = init_kernels<false>();
+    if (a1 == cudaSuccess && uses_gen(e)) a1 = zb_gen_init();
+    if (a1 != cudaSuccess) {
       cudaSetDevice(prev);
       delete e;
-      return fail(ZB_ECUDA, "zb_engine_create: cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(a1 != cudaSuccess ? a1 : a2));
+      return fail(ZB_ECUDA, "zb_engine_create: cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(a1));
     }
   }
   cudaError_t ce = cudaMalloc(&e->dev, sizeof(ZbDev));
@@ -650,6 +769,7 @@ int zb_engine_destroy(ZbEngine* e) {
 int zb_engine_set_opts(ZbEngine* e, const ZbOpts* opts) {
   if (!e || !opts) return fail(ZB_EINVAL, "zb_engine_set_opts: null argument%s");
   int rc = check_opts(opts);
+  if (!rc) rc = check_model_opts(&e->host, opts);
   if (rc) return rc;
   e->host.o = *opts;
   derive_solprm(&e->host);
@@ -673,6 +793,14 @@ static int after_launch(const char* what) {
   return ZB_OK;
 }
 
+static int dispatch(const ZbEngine* e, int mode, bool trace, bool obs, bool wide, int grid, int threads, size_t smem, void* stream, const KArgs& a,
+                    const char* what) {
+  const bool ok = uses_gen(e) ? zb_gen_launch(mode, trace, obs, wide, grid, threads, smem, (cudaStream_t)stream, a)
+                              : launch_kernel<false>(mode, trace, obs, wide, grid, threads, smem, (cudaStream_t)stream, a);
+  if (!ok) return fail(ZB_EUNSUP, "this combination (mode / trace / observation epilogue / profile / collision groups) is not instantiated in this build%s");
+  return after_launch(what);
+}
+
 static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
                      const float* push_rand, int push_per_substep, const ZbOut* out, int n_envs, int n_substeps, ZbAutoReset AR,
                      const ZbObs* obs = nullptr) {
@@ -688,23 +816,11 @@ static int step_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, const
   const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x || OB.feet_pos_obs || OB.reward_terms;
   const CtaShape cs = pick_shape(e, n_envs, !O.solver_trace);  // the diagnostics instantiation exists in the latency profile only
   const int wpb = cs.wpb, grid = (n_envs + wpb - 1) / wpb;
-#define ZB_LAUNCH_STEP(TR, OBSV, W) zb_kernel<ZB_MODE_STEP, TR, OBSV, W><<<grid, wpb * 32, (W > ZB_WPB) ? (size_t)wpb * ZB_FSM_BYTES_PER_WARP : 0, (cudaStream_t)stream>>>( \
-    e->dev, e->host.o, e->host.m.meaninertia, P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps, nullptr, nullptr, nullptr, nullptr, AR, OB)
-#ifdef ZB_MINIMAL  // development / mutation builds: only the plain step (both register profiles, + trace) and the plain reset are compiled
-#ifdef ZB_MINIMAL_OBS  // ... + the observation epilogue in the throughput profile
-  if (with_obs && !cs.wide) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL_OBS) has the observation epilogue in the throughput profile only%s");
-  if (with_obs && !O.solver_trace) { ZB_LAUNCH_STEP(false, true, ZB_WPB_WIDE); return after_launch("zb_step_f32 launch: %s"); }
-#endif
-  if (with_obs) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no observation instantiations%s");
-  if (O.solver_trace) ZB_LAUNCH_STEP(true, false, ZB_WPB);
-  else if (cs.wide) ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB);
-#else
-  if (O.solver_trace) { if (with_obs) ZB_LAUNCH_STEP(true, true, ZB_WPB); else ZB_LAUNCH_STEP(true, false, ZB_WPB); }
-  else if (cs.wide) { if (with_obs) ZB_LAUNCH_STEP(false, true, ZB_WPB_WIDE); else ZB_LAUNCH_STEP(false, false, ZB_WPB_WIDE); }
-  else { if (with_obs) ZB_LAUNCH_STEP(false, true, ZB_WPB); else ZB_LAUNCH_STEP(false, false, ZB_WPB); }
-#endif
-#undef ZB_LAUNCH_STEP
-  return after_launch("zb_step_f32 launch: %s");
+  KArgs a = {e->dev, e->host.o, e->host.m.meaninertia, cflags_of(e), P, *state, action, push_rand, push_per_substep, O, n_envs, n_substeps,
+             nullptr, nullptr, nullptr, nullptr, AR, OB};
+  // (the diagnostics instantiation exists in the latency profile only)
+  return dispatch(e, ZB_MODE_STEP, O.solver_trace != nullptr, with_obs, cs.wide && !O.solver_trace, grid, wpb * 32,
+                  (cs.wide && !O.solver_trace) ? (size_t)wpb * ZB_FSM_BYTES_PER_WARP : 0, stream, a, "zb_step_f32 launch: %s");
 }
 
 int zb_step_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const float* action,
@@ -737,16 +853,9 @@ int zb_forward_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const Z
   ZbEnvParams P; memset(&P, 0, sizeof(P)); if (params) P = *params;
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   const int wpb = pick_shape(e, n_envs, false).wpb, grid = (n_envs + wpb - 1) / wpb;
-#ifdef ZB_MINIMAL
-  (void)wpb; (void)grid;
-  return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no forward instantiation%s");
-#else
-  if (O.solver_trace) zb_kernel<ZB_MODE_FORWARD, true, false, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
-                                                                            nullptr, nullptr, nullptr, nullptr, ZbAutoReset{}, ZbObs{});
-  else zb_kernel<ZB_MODE_FORWARD, false, false, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1,
-                                                                            nullptr, nullptr, nullptr, nullptr, ZbAutoReset{}, ZbObs{});
-  return after_launch("zb_forward_f32 launch: %s");
-#endif
+  KArgs a = {e->dev, e->host.o, e->host.m.meaninertia, cflags_of(e), P, *state, nullptr, nullptr, 0, O, n_envs, 1, nullptr, nullptr, nullptr, nullptr,
+             ZbAutoReset{}, ZbObs{}};
+  return dispatch(e, ZB_MODE_FORWARD, O.solver_trace != nullptr, false, false, grid, wpb * 32, 0, stream, a, "zb_forward_f32 launch: %s");
 }
 
 static int check_obs(const ZbObs* obs) {
@@ -768,18 +877,10 @@ static int reset_impl(ZbEngine* e, void* stream, const ZbEnvParams* params, cons
   ZbOut O; memset(&O, 0, sizeof(O)); if (out) O = *out;
   ZbObs OB; memset(&OB, 0, sizeof(OB)); if (obs) OB = *obs;
   const int wpb = pick_shape(e, n_envs, false).wpb, grid = (n_envs + wpb - 1) / wpb;
-#define ZB_LAUNCH_RESET(TR, OBSV) zb_kernel<ZB_MODE_RESET, TR, OBSV, ZB_WPB><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>( \
-    e->dev, e->host.o, e->host.m.meaninertia, P, *state, nullptr, nullptr, 0, O, n_envs, 1, done, reset_qpos, reset_qvel, reset_t_rem, ZbAutoReset{}, OB)
   const bool with_obs = OB.actor_obs || OB.critic_obs || OB.imu_x || OB.feet_pos_obs || OB.reward_terms;
-#ifdef ZB_MINIMAL
-  if (O.solver_trace || with_obs) return fail(ZB_EUNSUP, "this build (ZB_MINIMAL) has no trace / observation instantiations%s");
-  ZB_LAUNCH_RESET(false, false);
-#else
-  if (O.solver_trace) { if (with_obs) ZB_LAUNCH_RESET(true, true); else ZB_LAUNCH_RESET(true, false); }
-  else { if (with_obs) ZB_LAUNCH_RESET(false, true); else ZB_LAUNCH_RESET(false, false); }
-#endif
-#undef ZB_LAUNCH_RESET
-  return after_launch("zb_reset_f32 launch: %s");
+  KArgs a = {e->dev, e->host.o, e->host.m.meaninertia, cflags_of(e), P, *state, nullptr, nullptr, 0, O, n_envs, 1, done, reset_qpos, reset_qvel, reset_t_rem,
+             ZbAutoReset{}, OB};
+  return dispatch(e, ZB_MODE_RESET, O.solver_trace != nullptr, with_obs, false, grid, wpb * 32, 0, stream, a, "zb_reset_f32 launch: %s");
 }
 
 int zb_reset_f32(ZbEngine* e, void* stream, const ZbEnvParams* params, const ZbState* state, const uint8_t* done,
@@ -841,3 +942,4 @@ int zb_bench_ffma(void* stream, float* scratch, int grid, int iters) {
 }
 
 }  // extern "C"
+#endif  // ZB_TU == 0

@@ -372,27 +372,81 @@ def compile_mjcf(xml: str, servo_params: dict | None = None, floor: dict | None 
     m.field("floor_solimp")[:] = _floats(fl.get("solimp"), 5, solimp0)
     m.floor_priority = int(fl.get("priority", 2))  # train.py:1330 sets geom_priority[floor] = 2
     m.floor_margin, m.floor_gap = float(fl.get("margin", 0.0)), float(fl.get("gap", 0.0))
+    # Collision groups (ZbModel.box_* / pair_*).  Explicit <contact><pair geom1 geom2> elements become body-body groups (geom 1 =
+    # pair_*, geom 2 = box_*; MJX orders a pair by geom type: sphere before capsule); every other colliding box / sphere / capsule geom on a
+    # chain body collides with the floor plane.  Anything else (meshes, cylinders, geoms beyond the ZB_NBOX groups) is reported in
+    # `ignored_geoms` — the kernel has no primitive for it.
+    types = {"box": M.GEOM_BOX, "sphere": M.GEOM_SPHERE, "capsule": M.GEOM_CAPSULE}
+    by_name = {}
+    for i, b in enumerate(bodies):
+        for g in b["geoms"]:
+            if g.get("name"):
+                by_name[g["name"]] = (i, g)
+
+    def geom_size(g):
+        t = g.get("type", "sphere")
+        n_ = {"box": 3, "sphere": 1, "capsule": 2}[t]
+        sz = np.zeros(3)
+        sz[:n_] = _floats(g.get("size"), n_)
+        return sz
+
+    def fill_geom2(k, i, g):
+        m.box_body[k], m.box_type[k] = i, types[g.get("type", "sphere")]
+        m.field("box_pos")[k] = _floats(g.get("pos"), 3, (0, 0, 0))
+        m.field("box_quat")[k] = _orientation(g, degree, eulerseq)
+        m.field("box_size")[k] = geom_size(g)
+        m.field("box_friction")[k] = _floats(g.get("friction"), 3, fr0)
+        m.field("box_solref")[k] = _floats(g.get("solref"), 2, solref0)
+        m.field("box_solimp")[k] = _floats(g.get("solimp"), 5, solimp0)
+        m.box_priority[k] = int(g.get("priority", 0))
+        m.box_margin[k], m.box_gap[k] = float(g.get("margin", 0.0)), float(g.get("gap", 0.0))
+        m.pair_body[k] = 0
+        m.field("pair_quat")[k] = (1, 0, 0, 0)
+
+    pairs = []  # (geom-2 slot order is fixed later: floor groups first in body order, like geom ids)
+    contact = root.find("contact")
+    paired = set()
+    if contact is not None:
+        for pe in contact.findall("pair"):
+            n1, n2 = pe.get("geom1"), pe.get("geom2")
+            if n1 not in by_name or n2 not in by_name:
+                raise MjcfError(f"<pair>: unknown geom {n1!r} / {n2!r}")
+            (i1, g1), (i2, g2) = by_name[n1], by_name[n2]
+            order = {"sphere": 0, "capsule": 1}
+            t1, t2 = g1.get("type", "sphere"), g2.get("type", "sphere")
+            if t1 not in order or t2 not in order:
+                raise MjcfError("<pair>: body-body groups support sphere-sphere, sphere-capsule and capsule-capsule")
+            if order[t1] > order[t2]:
+                (i1, g1, n1), (i2, g2, n2) = (i2, g2, n2), (i1, g1, n1)
+            pairs.append((i1, g1, i2, g2))
+            paired |= {n1, n2}
     nbox = 0
     for i, b in enumerate(bodies):
         for g in b["geoms"]:
             collides = int(g.get("contype", 1)) != 0 or int(g.get("conaffinity", 1)) != 0
-            if g.get("type", "sphere") == "box" and collides and i >= 2:
-                if nbox >= M.NBOX:
-                    raise MjcfError(f"more than {M.NBOX} colliding box geoms")
-                m.box_body[nbox] = i
-                m.field("box_pos")[nbox] = _floats(g.get("pos"), 3, (0, 0, 0))
-                m.field("box_quat")[nbox] = _orientation(g, degree, eulerseq)
-                m.field("box_size")[nbox] = _floats(g.get("size"), 3)
-                m.field("box_friction")[nbox] = _floats(g.get("friction"), 3, fr0)
-                m.field("box_solref")[nbox] = _floats(g.get("solref"), 2, solref0)
-                m.field("box_solimp")[nbox] = _floats(g.get("solimp"), 5, solimp0)
-                m.box_priority[nbox] = int(g.get("priority", 0))
-                m.box_margin[nbox], m.box_gap[nbox] = float(g.get("margin", 0.0)), float(g.get("gap", 0.0))
+            if g.get("name") in paired:
+                continue
+            if g.get("type", "sphere") in types and collides and i >= 2 and nbox + len(pairs) < M.NBOX:
+                fill_geom2(nbox, i, g)
                 nbox += 1
             elif collides:
                 out.ignored_geoms.append((b["name"], g.get("name"), g.get("type", "sphere")))
+    for (i1, g1, i2, g2) in pairs:
+        if nbox >= M.NBOX:
+            raise MjcfError(f"more than {M.NBOX} collision groups")
+        fill_geom2(nbox, i2, g2)
+        m.pair_body[nbox], m.pair_type[nbox] = i1, types[g1.get("type", "sphere")]
+        m.field("pair_pos")[nbox] = _floats(g1.get("pos"), 3, (0, 0, 0))
+        m.field("pair_quat")[nbox] = _orientation(g1, degree, eulerseq)
+        m.field("pair_size")[nbox] = geom_size(g1)
+        m.field("pair_friction")[nbox] = _floats(g1.get("friction"), 3, fr0)
+        m.field("pair_solref")[nbox] = _floats(g1.get("solref"), 2, solref0)
+        m.field("pair_solimp")[nbox] = _floats(g1.get("solimp"), 5, solimp0)
+        m.pair_priority[nbox] = int(g1.get("priority", 0))
+        m.pair_margin[nbox], m.pair_gap[nbox] = float(g1.get("margin", 0.0)), float(g1.get("gap", 0.0))
+        nbox += 1
     if nbox != M.NBOX:
-        raise MjcfError(f"expected {M.NBOX} colliding foot boxes, found {nbox}")
+        raise MjcfError(f"expected {M.NBOX} collision groups (colliding box / sphere / capsule geoms on chain bodies, <pair> elements), found {nbox}")
 
     # ---- sites ----
     found = {}
@@ -487,11 +541,18 @@ def to_mjcf(m: M.ZbModel, body_names=None, joint_names=None, opts: M.ZbOpts | No
                      f"armature=\"{_fmt(m.dof_armature[d])}\" damping=\"{_fmt(m.dof_damping[d])}\" frictionloss=\"{_fmt(m.dof_frictionloss[d])}\" "
                      f"ref=\"{_fmt(m.field('qpos0')[d + 1])}\" solreflimit=\"{_fmt(m.field('jnt_solref')[d])}\" solimplimit=\"{_fmt(m.field('jnt_solimp')[d])}\" "
                      f"solreffriction=\"{_fmt(m.field('dof_solref')[d])}\" solimpfriction=\"{_fmt(m.field('dof_solimp')[d])}\"/>")
+        tname, nsz = {M.GEOM_BOX: "box", M.GEOM_SPHERE: "sphere", M.GEOM_CAPSULE: "capsule"}, {M.GEOM_BOX: 3, M.GEOM_SPHERE: 1, M.GEOM_CAPSULE: 2}
         for g in range(M.NBOX):
             if m.box_body[g] == b:
-                L.append(f"{ind}  <geom name=\"{body_names[b]}_box\" type=\"box\" size=\"{_fmt(m.field('box_size')[g])}\" pos=\"{_fmt(m.field('box_pos')[g])}\" "
+                t = int(m.box_type[g])
+                L.append(f"{ind}  <geom name=\"group{g}_geom2\" type=\"{tname[t]}\" size=\"{_fmt(m.field('box_size')[g][:nsz[t]])}\" pos=\"{_fmt(m.field('box_pos')[g])}\" "
                          f"quat=\"{_fmt(m.field('box_quat')[g])}\" friction=\"{_fmt(m.field('box_friction')[g])}\" solref=\"{_fmt(m.field('box_solref')[g])}\" "
                          f"solimp=\"{_fmt(m.field('box_solimp')[g])}\" priority=\"{m.box_priority[g]}\" margin=\"{_fmt(m.box_margin[g])}\" gap=\"{_fmt(m.box_gap[g])}\"/>")
+            if m.pair_body[g] == b and b != 0:
+                t = int(m.pair_type[g])
+                L.append(f"{ind}  <geom name=\"group{g}_geom1\" type=\"{tname[t]}\" size=\"{_fmt(m.field('pair_size')[g][:nsz[t]])}\" pos=\"{_fmt(m.field('pair_pos')[g])}\" "
+                         f"quat=\"{_fmt(m.field('pair_quat')[g])}\" friction=\"{_fmt(m.field('pair_friction')[g])}\" solref=\"{_fmt(m.field('pair_solref')[g])}\" "
+                         f"solimp=\"{_fmt(m.field('pair_solimp')[g])}\" priority=\"{m.pair_priority[g]}\" margin=\"{_fmt(m.pair_margin[g])}\" gap=\"{_fmt(m.pair_gap[g])}\"/>")
         for s in range(M.NSITE):
             if m.site_body[s] == b:
                 L.append(f"{ind}  <site name=\"{site_names[s]}\" type=\"box\" pos=\"{_fmt(m.field('site_pos')[s])}\" quat=\"{_fmt(m.field('site_quat')[s])}\" "
@@ -503,6 +564,10 @@ def to_mjcf(m: M.ZbModel, body_names=None, joint_names=None, opts: M.ZbOpts | No
     for b in children.get(0, []):
         emit(b, "    ")
     L.append("  </worldbody>")
+    if any(m.pair_body[g] != 0 for g in range(M.NBOX)):
+        L.append("  <contact>")
+        L += [f"    <pair geom1=\"group{g}_geom1\" geom2=\"group{g}_geom2\"/>" for g in range(M.NBOX) if m.pair_body[g] != 0]
+        L.append("  </contact>")
     L.append("  <actuator>")
     for j in range(M.NU):
         L.append(f"    <motor name=\"{joint_names[j]}_ctrl\" joint=\"{joint_names[j]}\" gear=\"{_fmt(m.act_gear[j])}\" ctrlrange=\"{_fmt(m.field('act_ctrlrange')[j])}\" "

@@ -76,6 +76,7 @@ class ZbOpts(ctypes.Structure):
 
 
 SOLVER_CG, SOLVER_NEWTON = 0, 1
+GEOM_BOX, GEOM_SPHERE, GEOM_CAPSULE = 0, 1, 2  # ZbModel.box_type / pair_type
 INT_EULER, INT_IMPLICITFAST = 0, 1
 
 
@@ -167,6 +168,18 @@ class ZbModel(ctypes.Structure):
         ("box_priority", _i * NBOX),
         ("box_margin", _f * NBOX),
         ("box_gap", _f * NBOX),
+        ("box_type", _i * NBOX),
+        ("pair_body", _i * NBOX),
+        ("pair_type", _i * NBOX),
+        ("pair_pos", _f * 3 * NBOX),
+        ("pair_quat", _f * 4 * NBOX),
+        ("pair_size", _f * 3 * NBOX),
+        ("pair_friction", _f * 3 * NBOX),
+        ("pair_solref", _f * 2 * NBOX),
+        ("pair_solimp", _f * 5 * NBOX),
+        ("pair_priority", _i * NBOX),
+        ("pair_margin", _f * NBOX),
+        ("pair_gap", _f * NBOX),
         ("site_body", _i * NSITE),
         ("site_pos", _f * 3 * NSITE),
         ("site_quat", _f * 4 * NSITE),
@@ -458,6 +471,8 @@ def build_zbot_syn() -> ZbModel:
         m.field("box_solref")[k] = solref
         m.field("box_solimp")[k] = solimp
         m.box_priority[k], m.box_margin[k], m.box_gap[k] = 0, 0.0, 0.0
+        m.box_type[k], m.pair_body[k] = GEOM_BOX, 0  # geom 1 = the floor plane (the pair_* fields are unused)
+        m.field("pair_quat")[k] = _QI
     # sites: imu_site on imu_link; left_foot/right_foot touch boxes around the foot plates
     m.site_body[0] = BODY_NAMES.index("imu_link")
     m.field("site_pos")[0] = (0.0, 0.0, 0.002)
@@ -471,6 +486,38 @@ def build_zbot_syn() -> ZbModel:
 
     set_const(m)
     return m
+
+
+def set_collision_group(m: ZbModel, g: int, *, body: int | str, geom: str, size, pos=(0.0, 0.0, 0.0), quat=None, friction=None,
+                        other_body: int | str = 0, other_geom: str = "sphere", other_size=(0.0, 0.0, 0.0), other_pos=(0.0, 0.0, 0.0),
+                        other_quat=None, other_friction=None, priority: int = 0, other_priority: int = 0, margin: float = 0.0) -> None:
+    """Configure collision group ``g`` (ZbModel.box_* / pair_*): geom 2 (``geom`` on ``body``) against the floor plane
+    (``other_body=0``) or against geom 1 (``other_geom`` on ``other_body``).  MJX pair order: sphere before capsule before box."""
+    types = {"box": GEOM_BOX, "sphere": GEOM_SPHERE, "capsule": GEOM_CAPSULE}
+    bi = BODY_NAMES.index(body) if isinstance(body, str) else int(body)
+    oi = BODY_NAMES.index(other_body) if isinstance(other_body, str) else int(other_body)
+    m.box_body[g], m.box_type[g] = bi, types[geom]
+    sz = np.zeros(3); sz[:len(np.atleast_1d(size))] = np.atleast_1d(size)
+    m.field("box_size")[g] = sz
+    m.field("box_pos")[g] = pos
+    m.field("box_quat")[g] = _QI if quat is None else quat
+    if friction is not None:
+        m.field("box_friction")[g] = friction
+    m.box_priority[g], m.box_margin[g] = priority, margin
+    m.pair_body[g], m.pair_type[g] = oi, types[other_geom]
+    osz = np.zeros(3); osz[:len(np.atleast_1d(other_size))] = np.atleast_1d(other_size)
+    m.field("pair_size")[g] = osz
+    m.field("pair_pos")[g] = other_pos
+    m.field("pair_quat")[g] = _QI if other_quat is None else other_quat
+    if oi != 0:
+        m.field("pair_friction")[g] = (1.0, 0.005, 0.0001) if other_friction is None else other_friction
+        m.field("pair_solref")[g] = m.field("box_solref")[g]
+        m.field("pair_solimp")[g] = m.field("box_solimp")[g]
+    m.pair_priority[g], m.pair_margin[g] = other_priority, margin
+    if oi != 0:
+        order = {GEOM_SPHERE: 0, GEOM_CAPSULE: 1, GEOM_BOX: 2}
+        if types[geom] == GEOM_BOX or order[types[other_geom]] > order[types[geom]]:
+            raise ValueError("body-body pairs: sphere-sphere, sphere-capsule (sphere = geom 1) and capsule-capsule only")
 
 
 def set_const(m: ZbModel) -> None:

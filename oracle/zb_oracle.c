@@ -278,6 +278,15 @@ static void kinematics(const ZbModel* m, const EnvModel* e, ZboData* d) {
     FL(3);
     quat_mul(q, d->xquat[b], gq);
     quat_to_mat(d->box_xmat[g], q);
+    if (m->pair_body[g] > 0) { /* geom 1 of a body-body pair */
+      int b1 = m->pair_body[g];
+      real pp[3] = {(real)m->pair_pos[g][0], (real)m->pair_pos[g][1], (real)m->pair_pos[g][2]};
+      real pq[4] = {(real)m->pair_quat[g][0], (real)m->pair_quat[g][1], (real)m->pair_quat[g][2], (real)m->pair_quat[g][3]};
+      mat_vec(r, d->xmat[b1], pp);
+      for (int k = 0; k < 3; k++) d->pair_xpos[g][k] = d->xpos[b1][k] + r[k];
+      quat_mul(q, d->xquat[b1], pq);
+      quat_to_mat(d->pair_xmat[g], q);
+    }
   }
 }
 
@@ -447,11 +456,86 @@ static int argmax8(const real* v) { /* jp.argmax: first maximum */
     if (v[i] > v[bi]) bi = i;
   return bi;
 }
-static void collision(const ZbModel* m, const EnvModel* e, ZboData* d) {
-  STAGE(ZBO_ST_COLLISION);
-  real pn[3] = {(real)m->floor_normal[0], (real)m->floor_normal[1], (real)m->floor_normal[2]};
-  real pp[3] = {(real)m->floor_pos[0], (real)m->floor_pos[1], (real)m->floor_pos[2]};
-  for (int g = 0; g < NBOX; g++) {
+/* contact parameter mixing of group g (collision_driver: the higher geom_priority wins — floor = 2, train.py:1330 [V]; equal
+ * priority: max friction, margins / gaps max; solref / solimp of geom 1 on a tie: solmix default 1:1 would average, documented risk) */
+static void mix_params(const ZbModel* m, const EnvModel* e, ZboData* d, int g, int ci) {
+  int world = m->pair_body[g] == 0;
+  real mu1 = world ? e->floor_mu : (real)m->pair_friction[g][0], mu2 = (real)m->box_friction[g][0];
+  int p1 = world ? m->floor_priority : m->pair_priority[g], p2 = m->box_priority[g];
+  const float* sr1 = world ? m->floor_solref : m->pair_solref[g];
+  const float* si1 = world ? m->floor_solimp : m->pair_solimp[g];
+  real margin = R_FMAX(world ? (real)m->floor_margin : (real)m->pair_margin[g], (real)m->box_margin[g]);
+  real gap = R_FMAX(world ? (real)m->floor_gap : (real)m->pair_gap[g], (real)m->box_gap[g]);
+  d->con_includemargin[ci] = margin - gap;
+  const float *sr, *si;
+  if (p1 > p2) { d->con_mu[ci] = mu1; sr = sr1; si = si1; }
+  else if (p1 < p2) { d->con_mu[ci] = mu2; sr = m->box_solref[g]; si = m->box_solimp[g]; }
+  else { d->con_mu[ci] = R_FMAX(mu1, mu2); sr = sr1; si = si1; }
+  for (int k = 0; k < 2; k++) d->con_solref[ci][k] = (real)sr[k];
+  for (int k = 0; k < 5; k++) d->con_solimp[ci][k] = (real)si[k];
+}
+static void set_contact(const ZbModel* m, const EnvModel* e, ZboData* d, int g, int s, real dist, const real* pos, const real* frame, int vert) {
+  int ci = g * 4 + s;
+  d->con_dist[ci] = dist;
+  for (int k = 0; k < 3; k++) d->con_pos[ci][k] = pos[k];
+  memcpy(d->con_frame[ci], frame, 9 * sizeof(real));
+  d->con_vert[ci] = vert;
+  d->con_body[ci] = m->box_body[g];
+  d->con_body1[ci] = m->pair_body[g];
+  mix_params(m, e, d, g, ci);
+}
+/* collision_primitive._plane_sphere [R] */
+static void plane_sphere_(const real* n, const real* ppos, const real* spos, real radius, real* dist, real* pos) {
+  real rel[3] = {spos[0] - ppos[0], spos[1] - ppos[1], spos[2] - ppos[2]};
+  *dist = dot3(rel, n) - radius;
+  for (int k = 0; k < 3; k++) pos[k] = spos[k] - n[k] * (radius + (real)0.5 * *dist);
+  FL(12);
+}
+/* collision_primitive._sphere_sphere [R]: normal from sphere 1 to sphere 2 */
+static void sphere_sphere_(const real* p1, real r1, const real* p2, real r2, real* dist, real* pos, real* n) {
+  real dl[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  real len = R_SQRT(dot3(dl, dl));
+  real sc = (real)1 / (len + (real)1e-6 * (len == 0));
+  for (int k = 0; k < 3; k++) n[k] = dl[k] * sc;
+  if (len == 0) { n[0] = 1; n[1] = 0; n[2] = 0; }
+  *dist = len - (r1 + r2);
+  for (int k = 0; k < 3; k++) pos[k] = p1[k] + n[k] * (r1 + (real)0.5 * *dist);
+  FL(20);
+}
+/* math.closest_segment_point [R] */
+static void closest_segment_point(const real* a, const real* b, const real* pt, real* out) {
+  real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ap[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+  real t = dot3(ap, ab) / (dot3(ab, ab) + (real)1e-6);
+  t = R_FMIN(R_FMAX(t, (real)0), (real)1);
+  for (int k = 0; k < 3; k++) out[k] = a[k] + t * ab[k];
+  FL(15);
+}
+/* math.closest_segment_to_segment_points [R] */
+static void closest_segment_to_segment(const real* a0, const real* a1, const real* b0, const real* b1, real* best_a, real* best_b) {
+  real da[3] = {a1[0] - a0[0], a1[1] - a0[1], a1[2] - a0[2]}, db[3] = {b1[0] - b0[0], b1[1] - b0[1], b1[2] - b0[2]};
+  real la = R_SQRT(dot3(da, da)), lb = R_SQRT(dot3(db, db));
+  real sa = (real)1 / (la + (real)1e-6 * (la == 0)), sb = (real)1 / (lb + (real)1e-6 * (lb == 0));
+  for (int k = 0; k < 3; k++) { da[k] *= sa; db[k] *= sb; }
+  real ha = la * (real)0.5, hb = lb * (real)0.5;
+  real am[3], bm[3], tr[3];
+  for (int k = 0; k < 3; k++) { am[k] = a0[k] + da[k] * ha; bm[k] = b0[k] + db[k] * hb; tr[k] = am[k] - bm[k]; }
+  real dd = dot3(da, db), dat = dot3(da, tr), dbt = dot3(db, tr);
+  real denom = (real)1 - dd * dd;
+  real ta = (-dat + dd * dbt) / (denom + (real)1e-6);
+  real tb = dbt + ta * dd;
+  ta = R_FMIN(R_FMAX(ta, -ha), ha);
+  tb = R_FMIN(R_FMAX(tb, -hb), hb);
+  real ba[3], bb[3], na[3], nb[3];
+  for (int k = 0; k < 3; k++) { ba[k] = am[k] + da[k] * ta; bb[k] = bm[k] + db[k] * tb; }
+  closest_segment_point(a0, a1, bb, na);
+  closest_segment_point(b0, b1, ba, nb);
+  real e1[3] = {na[0] - bb[0], na[1] - bb[1], na[2] - bb[2]}, e2[3] = {ba[0] - nb[0], ba[1] - nb[1], ba[2] - nb[2]};
+  real d1 = dot3(e1, e1), d2 = dot3(e2, e2);
+  for (int k = 0; k < 3; k++) { best_a[k] = d1 < d2 ? na[k] : ba[k]; best_b[k] = d1 < d2 ? bb[k] : nb[k]; }
+  FL(80);
+}
+/* collision_convex.plane_convex + _manifold_points for a box [R] (A.7): four contacts */
+static void plane_box(const ZbModel* m, const EnvModel* e, ZboData* d, int g, const real* pn, const real* pp) {
     const real* mat = d->box_xmat[g];
     const real* pos = d->box_xpos[g];
     /* plane into the convex frame */
@@ -511,32 +595,78 @@ static void collision(const ZbModel* m, const EnvModel* e, ZboData* d) {
     real frame[9];
     make_frame(frame, pn);
     for (int s = 0; s < 4; s++) {
-      int ci = g * 4 + s, unique = 1;
+      int unique = 1;
       for (int t = 0; t < s; t++)
         if (idx[t] == idx[s]) unique = 0;
       real dist = unique ? -support[idx[s]] : (real)1;
-      real w[3];
+      real w[3], cp[3];
       mat_vec(w, mat, vert[idx[s]]);
-      for (int k = 0; k < 3; k++) d->con_pos[ci][k] = pos[k] + w[k] - (real)0.5 * dist * pn[k];
+      for (int k = 0; k < 3; k++) cp[k] = pos[k] + w[k] - (real)0.5 * dist * pn[k];
       FL(9);
-      d->con_dist[ci] = dist;
-      memcpy(d->con_frame[ci], frame, sizeof(frame));
-      d->con_vert[ci] = idx[s];
-      d->con_body[ci] = m->box_body[g];
-      /* contact parameter mixing: the higher geom_priority wins (floor = 2, train.py:1330 [V]) */
-      real margin = R_FMAX((real)m->floor_margin, (real)m->box_margin[g]);
-      real gap = R_FMAX((real)m->floor_gap, (real)m->box_gap[g]);
-      d->con_includemargin[ci] = margin - gap;
-      const float *sr, *si;
-      if (m->floor_priority > m->box_priority[g]) {
-        d->con_mu[ci] = e->floor_mu; sr = m->floor_solref; si = m->floor_solimp;
-      } else if (m->floor_priority < m->box_priority[g]) {
-        d->con_mu[ci] = (real)m->box_friction[g][0]; sr = m->box_solref[g]; si = m->box_solimp[g];
-      } else { /* equal priority: max friction; solmix default 1:1 -> mean of solref/solimp; floor's used (documented risk) */
-        d->con_mu[ci] = R_FMAX(e->floor_mu, (real)m->box_friction[g][0]); sr = m->floor_solref; si = m->floor_solimp;
+      set_contact(m, e, d, g, s, dist, cp, frame, idx[s]);
+    }
+}
+/* collision_driver.collision over the static candidate list = the collision groups of the model (ZbModel.box_* / pair_*) */
+static void collision(const ZbModel* m, const EnvModel* e, ZboData* d) {
+  STAGE(ZBO_ST_COLLISION);
+  real pn[3] = {(real)m->floor_normal[0], (real)m->floor_normal[1], (real)m->floor_normal[2]};
+  real pp[3] = {(real)m->floor_pos[0], (real)m->floor_pos[1], (real)m->floor_pos[2]};
+  const real zero3[3] = {0, 0, 0};
+  real idf[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int g = 0; g < NBOX; g++) {
+    const real* mat = d->box_xmat[g];
+    const real* pos = d->box_xpos[g];
+    const int t2 = m->box_type[g], world = m->pair_body[g] == 0;
+    real r2 = (real)m->box_size[g][0], h2 = (real)m->box_size[g][1];
+    real ax2[3] = {mat[2], mat[5], mat[8]};
+    for (int s = 0; s < 4; s++) set_contact(m, e, d, g, s, (real)1, zero3, idf, 0); /* inert slots */
+    if (world && t2 == ZB_GEOM_BOX) {
+      plane_box(m, e, d, g, pn, pp);
+    } else if (world && t2 == ZB_GEOM_SPHERE) { /* collision_primitive.plane_sphere [R] */
+      real dist, cp[3], frame[9];
+      plane_sphere_(pn, pp, pos, r2, &dist, cp);
+      make_frame(frame, pn);
+      set_contact(m, e, d, g, 0, dist, cp, frame, 0);
+    } else if (world && t2 == ZB_GEOM_CAPSULE) { /* collision_primitive.plane_capsule [R]: two contacts, frame aligned with the axis */
+      real na = dot3(pn, ax2), bv[3], frame[9];
+      for (int k = 0; k < 3; k++) bv[k] = ax2[k] - pn[k] * na;
+      real bn = R_SQRT(dot3(bv, bv));
+      real sc = (real)1 / (bn + (real)1e-6 * (bn == 0));
+      for (int k = 0; k < 3; k++) bv[k] *= sc;
+      if (bn < (real)0.5) {
+        bv[0] = 0; bv[1] = 0; bv[2] = 0;
+        if ((real)-0.5 < pn[1] && pn[1] < (real)0.5) bv[1] = 1; else bv[2] = 1;
       }
-      for (int k = 0; k < 2; k++) d->con_solref[ci][k] = (real)sr[k];
-      for (int k = 0; k < 5; k++) d->con_solimp[ci][k] = (real)si[k];
+      real cr[3];
+      cross3(cr, pn, bv);
+      for (int k = 0; k < 3; k++) { frame[k] = pn[k]; frame[3 + k] = bv[k]; frame[6 + k] = cr[k]; }
+      FL(30);
+      for (int s = 0; s < 2; s++) {
+        real c[3], dist, cp[3], sg = s == 0 ? (real)1 : (real)-1;
+        for (int k = 0; k < 3; k++) c[k] = pos[k] + sg * ax2[k] * h2;
+        plane_sphere_(pn, pp, c, r2, &dist, cp);
+        set_contact(m, e, d, g, s, dist, cp, frame, s);
+      }
+    } else if (!world) { /* sphere_sphere / sphere_capsule / capsule_capsule [R]: one contact, normal from geom 1 to geom 2 */
+      const real* mat1 = d->pair_xmat[g];
+      const real* pos1 = d->pair_xpos[g];
+      const int t1 = m->pair_type[g];
+      real r1 = (real)m->pair_size[g][0], h1 = (real)m->pair_size[g][1];
+      real ax1[3] = {mat1[2], mat1[5], mat1[8]};
+      real p1[3] = {pos1[0], pos1[1], pos1[2]}, p2[3] = {pos[0], pos[1], pos[2]};
+      if (t1 == ZB_GEOM_SPHERE && t2 == ZB_GEOM_CAPSULE) {
+        real a[3], b[3];
+        for (int k = 0; k < 3; k++) { a[k] = pos[k] - ax2[k] * h2; b[k] = pos[k] + ax2[k] * h2; }
+        closest_segment_point(a, b, pos1, p2);
+      } else if (t1 == ZB_GEOM_CAPSULE && t2 == ZB_GEOM_CAPSULE) {
+        real a0[3], a1[3], b0[3], b1[3];
+        for (int k = 0; k < 3; k++) { a0[k] = pos1[k] - ax1[k] * h1; a1[k] = pos1[k] + ax1[k] * h1; b0[k] = pos[k] - ax2[k] * h2; b1[k] = pos[k] + ax2[k] * h2; }
+        closest_segment_to_segment(a0, a1, b0, b1, p1, p2);
+      }
+      real dist, cp[3], n[3], frame[9];
+      sphere_sphere_(p1, r1, p2, r2, &dist, cp, n);
+      make_frame(frame, n);
+      set_contact(m, e, d, g, 0, dist, cp, frame, 0);
     }
   }
 }
@@ -623,14 +753,17 @@ static void make_constraint(const ZbModel* m, const ZbOpts* o, const EnvModel* e
     real jp[3][NV];
     memset(jp, 0, sizeof(jp));
     real off[3] = {d->con_pos[c][0] - c0[0], d->con_pos[c][1] - c0[1], d->con_pos[c][2] - c0[2]};
-    int b = body;
-    while (b > 0 && m->body_dofadr[b] < 0) b = m->body_parent[b];
-    int dof = b > 0 ? m->body_dofadr[b] + (m->body_jnttype[b] == 1 ? 5 : 0) : -1;
-    for (int j = dof; j >= 0; j = m->dof_parent[j]) {
-      real cr[3];
-      cross3(cr, d->cdof[j], off);
-      for (int k = 0; k < 3; k++) jp[k][j] = cr[k] + d->cdof[j][3 + k];
-      FL(3);
+    for (int side = 0; side < 2; side++) {
+      int b = side == 0 ? body : d->con_body1[c];
+      real sg = side == 0 ? (real)1 : (real)-1;
+      while (b > 0 && m->body_dofadr[b] < 0) b = m->body_parent[b];
+      int dof = b > 0 ? m->body_dofadr[b] + (m->body_jnttype[b] == 1 ? 5 : 0) : -1;
+      for (int j = dof; j >= 0; j = m->dof_parent[j]) {
+        real cr[3];
+        cross3(cr, d->cdof[j], off);
+        for (int k = 0; k < 3; k++) jp[k][j] += sg * (cr[k] + d->cdof[j][3 + k]);
+        FL(3);
+      }
     }
     real dc[3][NV]; /* frame @ diff */
     const real* fr = d->con_frame[c];
@@ -638,7 +771,7 @@ static void make_constraint(const ZbModel* m, const ZbOpts* o, const EnvModel* e
       for (int j = 0; j < NV; j++) dc[k][j] = fr[k * 3] * jp[0][j] + fr[k * 3 + 1] * jp[1][j] + fr[k * 3 + 2] * jp[2][j];
     FL(5 * 3 * 12);
     real mu = d->con_mu[c];
-    real t = (real)m->body_invweight0[0][0] + (real)m->body_invweight0[body][0];
+    real t = (real)m->body_invweight0[d->con_body1[c]][0] + (real)m->body_invweight0[body][0];
     real invweight = (t + mu * mu * t) * 2 * mu * mu / (real)o->impratio;
     FL(8);
     for (int k = 0; k < 4; k++) {
@@ -804,7 +937,8 @@ static void update_constraint(const ZboData* d, Ctx* c) {
     }
   }
   for (int j = 0; j < NV; j++) c->qfrc_c[j] = 0;
-  if (g_variant & 1) {
+  const int matrix_free = (g_variant & 1) && g_model->pair_body[0] == 0 && g_model->pair_body[1] == 0;
+  if (matrix_free) {
     for (int g = 0; g < NBOX; g++) {
       real W[6] = {0, 0, 0, 0, 0, 0};
       int body = g_model->box_body[g];
@@ -818,7 +952,7 @@ static void update_constraint(const ZboData* d, Ctx* c) {
     }
   }
   for (int r = 0; r < NEFC; r++)
-    if (c->force[r] != 0 && !((g_variant & 1) && d->efc_type[r] == 3)) {
+    if (c->force[r] != 0 && !(matrix_free && d->efc_type[r] == 3)) {
       for (int j = 0; j < NV; j++) c->qfrc_c[j] += d->efc_J[r][j] * c->force[r];
       FL(d->efc_type[r] == 3 ? 24 : 2);
     }
@@ -945,7 +1079,7 @@ static void ls_prelude(const ZboData* d, const Ctx* c, real* mv, real* jv, real*
     jv[r] = s;
     g_jvscale[r] = a;
   }
-  if (g_variant & 1) jv_contacts(d, c->search, jv);
+  if ((g_variant & 1) && g_model->pair_body[0] == 0 && g_model->pair_body[1] == 0) jv_contacts(d, c->search, jv);
   qg[0] = c->gauss; qg[1] = 0; qg[2] = 0;
   for (int j = 0; j < NV; j++) {
     qg[1] += c->search[j] * c->Ma[j] - c->search[j] * d->qfrc_smooth[j];
@@ -1040,7 +1174,7 @@ static void linesearch(const ZbModel* m, const ZbOpts* o, ZboData* d, Ctx* c) {
     }
     jv[r] = s;
   }
-  if (g_variant & 1) jv_contacts(d, c->search, jv);
+  if ((g_variant & 1) && g_model->pair_body[0] == 0 && g_model->pair_body[1] == 0) jv_contacts(d, c->search, jv);
   real qg[3] = {c->gauss, 0, 0};
   for (int j = 0; j < NV; j++) {
     qg[1] += c->search[j] * c->Ma[j] - c->search[j] * d->qfrc_smooth[j];
@@ -1212,8 +1346,10 @@ static void sensors(const ZbModel* m, const ZbOpts* o, const EnvModel* e, ZboDat
     matT_vec(fw, d->con_frame[c], fc); /* world force on body2 (the foot) */
     real off[3] = {d->con_pos[c][0] - c0[0], d->con_pos[c][1] - c0[1], d->con_pos[c][2] - c0[2]};
     cross3(tq, off, fw);
-    int b = d->con_body[c];
+    int b = d->con_body[c], b1 = d->con_body1[c];
     for (int k = 0; k < 3; k++) { d->cfrc_ext[b][k] += tq[k]; d->cfrc_ext[b][3 + k] += fw[k]; }
+    if (b1 > 0) /* the reaction on the body of geom 1 */
+      for (int k = 0; k < 3; k++) { d->cfrc_ext[b1][k] -= tq[k]; d->cfrc_ext[b1][3 + k] -= fw[k]; }
     FL(17);
   }
   for (int b = 0; b < NB; b++) {

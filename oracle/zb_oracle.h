@@ -51,7 +51,7 @@ typedef struct ZboData {
   real qM[ZB_NV][ZB_NV], qL[ZB_NV][ZB_NV];
   real qfrc_passive[ZB_NV], qfrc_bias[ZB_NV], qfrc_actuator[ZB_NV], qfrc_smooth[ZB_NV], qacc_smooth[ZB_NV];
   real actuator_force[ZB_NU];
-  real site_xpos[ZB_NSITE][3], site_xmat[ZB_NSITE][9], box_xpos[ZB_NBOX][3], box_xmat[ZB_NBOX][9];
+  real site_xpos[ZB_NSITE][3], site_xmat[ZB_NSITE][9], box_xpos[ZB_NBOX][3], box_xmat[ZB_NBOX][9], pair_xpos[ZB_NBOX][3], pair_xmat[ZB_NBOX][9];
   real con_dist[ZB_MAXCON], con_pos[ZB_MAXCON][3], con_frame[ZB_MAXCON][9], con_mu[ZB_MAXCON];
   real con_includemargin[ZB_MAXCON], con_solref[ZB_MAXCON][2], con_solimp[ZB_MAXCON][5];
   real efc_J[ZBO_NEFC][ZB_NV], efc_pos[ZBO_NEFC], efc_D[ZBO_NEFC], efc_R[ZBO_NEFC], efc_aref[ZBO_NEFC];
@@ -61,7 +61,7 @@ typedef struct ZboData {
   real sensordata[ZB_NSENSORDATA];
   real solver_cost;
   real trace[ZB_NTRACE];
-  int32_t con_body[ZB_MAXCON], con_vert[ZB_MAXCON], con_active[ZB_MAXCON];
+  int32_t con_body[ZB_MAXCON], con_body1[ZB_MAXCON], con_vert[ZB_MAXCON], con_active[ZB_MAXCON]; /* con_body = body of geom 2, con_body1 = body of geom 1 (0 = world) */
   int32_t efc_type[ZBO_NEFC]; /* 0 inert, 1 friction-loss, 2 limit, 3 contact */
   int32_t solver_niter, ls_evals, ls_iters, flags;
 } ZboData;

@@ -36,7 +36,7 @@ _REAL_FIELDS = [
     ("qM", (NV, NV)), ("qL", (NV, NV)),
     ("qfrc_passive", (NV,)), ("qfrc_bias", (NV,)), ("qfrc_actuator", (NV,)), ("qfrc_smooth", (NV,)), ("qacc_smooth", (NV,)),
     ("actuator_force", (NU,)),
-    ("site_xpos", (NSITE, 3)), ("site_xmat", (NSITE, 9)), ("box_xpos", (NBOX, 3)), ("box_xmat", (NBOX, 9)),
+    ("site_xpos", (NSITE, 3)), ("site_xmat", (NSITE, 9)), ("box_xpos", (NBOX, 3)), ("box_xmat", (NBOX, 9)), ("pair_xpos", (NBOX, 3)), ("pair_xmat", (NBOX, 9)),
     ("con_dist", (MAXCON,)), ("con_pos", (MAXCON, 3)), ("con_frame", (MAXCON, 9)), ("con_mu", (MAXCON,)),
     ("con_includemargin", (MAXCON,)), ("con_solref", (MAXCON, 2)), ("con_solimp", (MAXCON, 5)),
     ("efc_J", (NEFC, NV)), ("efc_pos", (NEFC,)), ("efc_D", (NEFC,)), ("efc_R", (NEFC,)), ("efc_aref", (NEFC,)),
@@ -47,7 +47,7 @@ _REAL_FIELDS = [
     ("solver_cost", ()), ("trace", (NTRACE,)),
 ]
 _INT_FIELDS = [
-    ("con_body", (MAXCON,)), ("con_vert", (MAXCON,)), ("con_active", (MAXCON,)), ("efc_type", (NEFC,)),
+    ("con_body", (MAXCON,)), ("con_body1", (MAXCON,)), ("con_vert", (MAXCON,)), ("con_active", (MAXCON,)), ("efc_type", (NEFC,)),
     ("solver_niter", ()), ("ls_evals", ()), ("ls_iters", ()), ("flags", ()),
 ]
 

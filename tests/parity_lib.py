@@ -161,8 +161,11 @@ def compare_single_step(model, opts, state_np, action, params=None, lib_path=Non
 TOL_MATCHED = {"qpos": 1e-5, "qvel": 5e-4, "qacc": 2e-2}
 
 
-def check_report(rep, tag="", flip_slack=0.02, cap_factor=3.0, cap_floor=None, verbose=True):
-    """The three assertions described in the module docstring.  Raises AssertionError with a readable message."""
+def check_report(rep, tag="", flip_slack=0.02, cap_factor=3.0, cap_floor=None, verbose=True, check_matched=True):
+    """The three assertions described in the module docstring.  Raises AssertionError with a readable message.
+    check_matched=False skips the path-conditional maximum (TOL_MATCHED was measured on the rollout populations; on violent random
+    states with deep point contacts ~90 % of the paths flip and the few matched environments are stiff — there the flip rate, the
+    quantiles and the cap against fp64 carry the comparison)."""
     cap_floor = cap_floor or {"qpos": 1e-5, "qvel": 1e-4, "qacc": 1e-3, "sensordata": 1e-3, "act_torque": 1e-5}
     n = rep["n"]
     msgs = []
@@ -177,7 +180,7 @@ def check_report(rep, tag="", flip_slack=0.02, cap_factor=3.0, cap_floor=None, v
             msgs.append(f"path flip rate vs fp32 oracle {flip_c:.4f} > perturbed fp32 oracle's {flip_p:.4f} + {flip_slack}")
         for k, tol in TOL_MATCHED.items():
             e = rep["d_cuda_f32_" + k][mc]
-            if e.size and e.max() > tol:
+            if check_matched and e.size and e.max() > tol:
                 msgs.append(f"{k}: max over the {int(mc.sum())} path-matched envs {e.max():.3e} > {tol:.1e} (env {int(np.flatnonzero(mc)[e.argmax()])})")
         if verbose:
             em = {k: rep["d_cuda_f32_" + k][mc].max() if mc.any() else 0 for k in TOL_MATCHED}
