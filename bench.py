@@ -65,6 +65,9 @@ def parse():
     ap.add_argument("--no-obs", action="store_true", help="without the observation epilogue: the launch writes every mjx.Data array the task reads "
                     "(xpos xquat cinert cvel ...) instead of the actor [50] / critic [484] input vectors (train.py:1624-1681) + the reward inputs")
     ap.add_argument("--obs", action="store_true", help=argparse.SUPPRESS)  # (the default since round 2; kept so that old command lines still run)
+    ap.add_argument("--flush", default="write", choices=["write", "write+read"],
+                    help="L2 flush between timed steps: memset of 256 MiB; write+read adds a read pass over it, so that the step starts on a "
+                         "cold AND clean L2 (after a bare memset the L2 holds ~126 MB of dirty lines whose write-back ncu books on the step kernel)")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -132,6 +135,7 @@ class Spec:
         self.solver, self.iterations, self.ls_iterations = a.solver, a.solver_iterations, a.ls_iterations
         self.obs = not a.no_obs
         self.seed = a.seed
+        self.flush = a.flush
         self.randomized = self.workload in ("c3", "c5")
 
     def opts(self):
@@ -151,7 +155,8 @@ class Spec:
             "terminations": "z in [0.05,0.5], tilt<60deg, episode length 80 s -> in-place reset",
             "observations": "actor [50] + critic [484] input vectors (train.py:1624-1681) + reward inputs per control step" if self.obs
                             else "every mjx.Data array the task reads",
-            "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+            "l2": "flushed between timed steps (256 MiB memset" + (" + read-back of it" if self.flush == "write+read" else "")
+                  + ", outside the event pair)",
             "parallelism": f"dp{world} (envs sharded, no collective in the physics step)",
         }
 
@@ -326,6 +331,7 @@ def measure(a, spec: Spec, model, K: int, W: int, rank: int, world: int, local: 
     ps = eng.reset(ep, reset_qpos=rq, reset_qvel=rv, reset_t_rem=rt, obs=obs, reset_imu_lag=obs_lag)
     done = torch.zeros((n_env,), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
     n_done = torch.zeros((), dtype=torch.int64, device=dev)
     niter_acc = torch.zeros((), dtype=torch.float64, device=dev)
 
@@ -350,6 +356,8 @@ def measure(a, spec: Spec, model, K: int, W: int, rank: int, world: int, local: 
     for i in range(K):
         t = W + i
         flush.zero_()  # L2 flush, outside the event pair
+        if spec.flush == "write+read":
+            flush_sink.add_(flush.view(torch.int64).sum())  # read pass: the memset's dirty lines are written back HERE, not during the step
         ev[i][0].record()
         ctrl_step(t, actions[t])
         ev[i][1].record()

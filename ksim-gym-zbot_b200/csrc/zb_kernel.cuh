@@ -50,6 +50,12 @@
 #ifndef ZB_RECOLLIDE
 #define ZB_RECOLLIDE 0 /* 1: sensors() re-run collision() instead of keeping contact point + frame live across the solve (more code, no gain measured) */
 #endif
+#ifndef ZB_LS_FIRST
+#define ZB_LS_FIRST 1 /* line search: the first Newton point reuses point(0)'s summed quadratic when every row sits on the same piece there (vote instead of a reduction; bit-exact) */
+#endif
+#ifndef ZB_PRED
+#define ZB_PRED 1 /* lane-masked updates as predicated FFMA (inline PTX; ptxas otherwise emits FFMA + FSEL) and lane masks folded into one factor instead of one select per product */
+#endif
 #ifndef ZB_LS_SAME
 #define ZB_LS_SAME 2 /* line search: 1 = no zone evaluation while both bracket ends share one active set, 2 = + the one-sided loop (see linesearch) */
 #endif
@@ -545,7 +551,7 @@ struct WarpEnv {
 #pragma unroll
     for (int k = 0; k < CHD - 1; k++) {
       const float yk = shf(x, gs + k);
-      if (hinge) x = fmaf(-F.lc[k], yk, x);
+      x = pfnma(hinge, F.lc[k], yk, x);
     }
     // base right-hand side: r_b - sum_i G_i y_i
     {
@@ -562,14 +568,14 @@ struct WarpEnv {
 #pragma unroll
     for (int k = 0; k < 5; k++) {
       const float yk = shf(x, BL0 + k);
-      if (bdof) x = fmaf(-F.lc[k], yk, x);
+      x = pfnma(bdof, F.lc[k], yk, x);
     }
     x *= F.inv;
     float xbv[6];
 #pragma unroll
     for (int k = 5; k >= 0; k--) {
       xbv[k] = shf(x, BL0 + k);
-      if (bdof) x = fmaf(-F.lt[k], xbv[k], x);
+      x = pfnma(bdof, F.lt[k], xbv[k], x);
     }
     // chains: Lt_c^T x_c = D_c^-1 y_c - G x_b, unit backward substitution
 #pragma unroll
@@ -577,7 +583,7 @@ struct WarpEnv {
 #pragma unroll
     for (int k = CHD - 1; k >= 1; k--) {
       const float xk = shf(x, gs + k);
-      if (hinge) x = fmaf(-F.lt[k], xk, x);
+      x = pfnma(hinge, F.lt[k], xk, x);
     }
     return x;
   }
@@ -599,7 +605,14 @@ struct WarpEnv {
     }
     float p[8];
 #pragma unroll
+#if ZB_PRED
+    const float vh = hinge ? v : 0.f;  // (base lanes hold A in Bm: must stay masked)
+#pragma unroll
+    for (int a = 0; a < 6; a++) p[a] = Bm[a] * vh;
+#else
+#pragma unroll
     for (int a = 0; a < 6; a++) p[a] = hinge ? Bm[a] * v : 0.f;  // (base lanes hold A in Bm: must stay masked)
+#endif
     p[6] = p[7] = 0.f;
     reduce_scatter<8>(p, L);
     const float t = shf(p[0], bdof ? 4 * (L - BL0) : 0);
@@ -718,7 +731,14 @@ struct WarpEnv {
     // sum_r J[r, d] f_r over the 16 row lanes of each box as a transpose-reduce inside the half-warp: total t lands in lane 16 g + t
     float p[16];
 #pragma unroll
+#if ZB_PRED
+    const float fm = c_on ? f : 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; k++) p[k] = fm * cj[k];
+#else
+#pragma unroll
     for (int k = 0; k < 12; k++) p[k] = c_on ? f * cj[k] : 0.f;
+#endif
     p[12] = p[13] = p[14] = p[15] = 0.f;
     int m = 8;
 #pragma unroll
@@ -1341,6 +1361,11 @@ struct WarpEnv {
     const float gtol = o.tolerance * o.ls_tolerance * (sqrtf(snorm) * meaninertia * (float)NV);
     al[0] = p0.alpha - p0.d0 / S0.d1;
     zz[0] = zone_at(r, al[0]);
+#if ZB_LS_FIRST
+    // every row on the same piece as at step size 0: the summed quadratic of this point is S0's, bit for bit (same rows, same order)
+    if (!(TRACE && trace && niter == 0) && !__any_sync(ZB_FULL, zz[0] != S0.z)) { st[0] = S0; pt[0] = ls_make_point(al[0], S0); }
+    else
+#endif
     ls_eval<1>(r, al, zz, pt, st);  // lo = point(newton(p0)); order the bracket
     if (pt[0].d0 < p0.d0) { lo = pt[0]; Slo = st[0]; hi = p0; Shi = S0; } else { hi = pt[0]; Shi = st[0]; lo = p0; Slo = S0; }
     if (TRACE && trace && niter == 0 && hasdof) trace[ZB_TRACE_SEARCH + dof] = search;

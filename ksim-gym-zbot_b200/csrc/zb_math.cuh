@@ -10,6 +10,16 @@
 ZB_DI float shf(float v, int src) { return __shfl_sync(ZB_FULL, v, src); }
 ZB_DI int shfi(int v, int src) { return __shfl_sync(ZB_FULL, v, src); }
 ZB_DI float shx(float v, int m) { return __shfl_xor_sync(ZB_FULL, v, m); }
+// x <- x - a*b on the lanes where p holds, untouched elsewhere: ONE predicated FFMA (ptxas turns `if (p) x = fmaf(-a, b, x)` into
+// FFMA + FSEL, the select on the half-rate ALU pipe)
+ZB_DI float pfnma(bool p, float a, float b, float x) {
+#if !defined(ZB_PRED) || ZB_PRED
+  asm("{\n .reg .pred q;\n setp.ne.u32 q, %1, 0;\n @q fma.rn.f32 %0, %2, %3, %0;\n}" : "+f"(x) : "r"((unsigned)p), "f"(-a), "f"(b));
+  return x;
+#else
+  return p ? fmaf(-a, b, x) : x;
+#endif
+}
 ZB_DI float wsum(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(ZB_FULL, v, o);
