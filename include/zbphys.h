@@ -386,6 +386,45 @@ int zb_feet_airtime_f32(void* cuda_stream, const float* left_contact, const floa
                         float* carry, float* reward, long long reward_time_stride, long long reward_env_stride, int n_envs,
                         int n_steps, float ctrl_dt, float touchdown_penalty);
 
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Policy inference in the rollout loop: the reference's Actor (/root/reference/train.py:885-968) evaluated for
+ * every environment of a control step by one kernel — input_proj Linear(n_in, 128) -> depth x GRUCell(128, 128) -> output_proj
+ * Linear(128, 20 * 3 * num_mixtures) -> mixture-of-Gaussians head (mean + JOINT_BIASES, std = clip((softplus + min_std) * var_scale,
+ * max_std), logits) -> action.  It is what run_actor / sample_action (train.py:1624-1648, 1737-1763) do per control step, reading the
+ * [N, 50] vector the observation epilogue wrote (ZbObs.actor_obs).
+ * Weights are device pointers in kernel layout (k-major; ksim-gym-zbot_b200/policy.py packs them from the equinox layout):
+ *   in_wt     [n_in][128]            = input_proj.weight[f][k] transposed          in_b  [128]
+ *   gru_wih_t [depth][128][3][128]   = rnns[l].weight_ih[g * 128 + f][k]   (gate order r, z, n as in equinox / PyTorch)
+ *   gru_whh_t [depth][128][3][128]   = rnns[l].weight_hh[g * 128 + f][k]
+ *   gru_b     [depth][3][128]        = rnns[l].bias        gru_bn [depth][128] = rnns[l].bias_n
+ *   out_wt    [128][n_out]           = output_proj.weight[j][k] transposed         out_b [n_out],  n_out = 20 * 3 * num_mixtures
+ *   mean_bias [20]                   = JOINT_BIASES (train.py:59-82, added at train.py:963), may be NULL */
+#define ZB_ACTOR_HIDDEN 128
+#define ZB_ACTOR_MAX_IN 128
+#define ZB_ACTOR_MAX_MIXTURES 5
+typedef struct ZbActor {
+  int32_t n_in;          /* NUM_ACTOR_INPUTS = 50 (train.py:53) */
+  int32_t depth;         /* GRU layers (train.py:1069-1072: 5) */
+  int32_t num_mixtures;  /* train.py:1073-1076: 5 */
+  float min_std, max_std, var_scale; /* train.py:1609-1610: 0.01, 1.0; Model passes var_scale = 1.0 (train.py:1046) */
+  const float *in_wt, *in_b, *gru_wih_t, *gru_whh_t, *gru_b, *gru_bn, *out_wt, *out_b, *mean_bias;
+} ZbActor;
+/* One control step of the actor for n_envs environments.
+ *   actor_obs   [N, n_in]          in
+ *   carry_in    [N, depth, 128]    in   the actor half of the model carry (train.py:1731-1735); carry_out may alias it (in place)
+ *   carry_out   [N, depth, 128]    out
+ *   carry_reset [N] or NULL        in   non-zero: this environment starts from the initial carry (zeros) — the `done` of the previous
+ *                                       control step, as the rollout re-initialises the carry of finished episodes [R]
+ *   noise_u, noise_eps [N, 20] or NULL  pre-sampled U[0,1) / N(0,1): mixture component by inverse CDF of softmax(logits) at u, action =
+ *                                       mean_k + std_k * eps  (`sample`); both NULL: the mean of the most probable component (`mode`,
+ *                                       sample_action(argmax=True), train.py:1757).  The reference draws them from a JAX PRNG key.
+ *   action      [N, 20]            out
+ *   dist        [N, 3, 20, M] or NULL  out: means (incl. JOINT_BIASES), stds, logits as handed to ksim.MixtureOfGaussians (train.py:965)
+ * fp32 on the CUDA cores, one CTA per 32 environments.  Errors: ZB_EINVAL (NULL / sizes), ZB_EUNSUP (limits above), ZB_ECUDA. */
+int zb_actor_f32(void* cuda_stream, const ZbActor* actor, const float* actor_obs, const float* carry_in, float* carry_out,
+                 const uint8_t* carry_reset, const float* noise_u, const float* noise_eps, float* action, float* dist, int n_envs);
+int zb_sizeof_actor(void);
+
 /* FP32 FFMA throughput probe (bench.py: the FP32 roofline denominator).  Enqueues grid x 256 threads doing
  * iters x 16 independent FMAs each; scratch needs grid * 256 floats.  flops = grid * 256 * iters * 32. */
 int zb_bench_ffma(void* cuda_stream, float* scratch, int grid, int iters);

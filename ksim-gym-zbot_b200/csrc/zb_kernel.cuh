@@ -50,6 +50,9 @@
 #ifndef ZB_RECOLLIDE
 #define ZB_RECOLLIDE 0 /* 1: sensors() re-run collision() instead of keeping contact point + frame live across the solve (more code, no gain measured) */
 #endif
+#ifndef ZB_CJ_SMEM
+#define ZB_CJ_SMEM 0 /* throughput profile: the 12 Jacobian-row entries of a lane's contact row in shared memory too (43 instead of 31 floats per lane) */
+#endif
 #ifndef ZB_LS_FIRST
 #define ZB_LS_FIRST 1 /* line search: the first Newton point reuses point(0)'s summed quadratic when every row sits on the same piece there (vote instead of a reduction; bit-exact) */
 #endif
@@ -154,7 +157,7 @@ struct WarpEnv {
   // exactly these (17 local loads in front of every solve, profiles/r1_final_hotspots.txt) and the 666 KB of stack per SM
   // thrash the L1; there they live in shared memory instead (fsm: lane column, element i at fsm[32 i], conflict-free).
   // F0 = factor of M, replaced by the Newton Hessian's / by the factor of M + dt D when those are needed (solve_all).
-  enum { F_LC = 0, F_LT = 6, F_INV = 12, F_W = 13, F_BM = 19, F_C = 25, F_N = 31 };
+  enum { F_LC = 0, F_LT = 6, F_INV = 12, F_W = 13, F_BM = 19, F_C = 25, F_CJ = 31, F_N = 31 + (ZB_CJ_SMEM ? 12 : 0) };
   float fst[FSM ? 1 : F_N];
   float* fsm;
   ZB_DI float fget(int i) const { return FSM ? fsm[32 * i] : fst[FSM ? 0 : i]; }
@@ -176,7 +179,9 @@ struct WarpEnv {
   // leg chain and the 6 base dofs, J[r, d] = w_r . cdof_d.  cj[0..5]: chain dofs of the box (lanes jsrc + k, zero for non-ancestors),
   // cj[6..11]: base dofs.  With it J v is 6 shuffles + 12 FMAs (instead of a 6-vector chain prefix scan + the base motion) and
   // neither cdof, w nor the base pose are read inside the solver loop.
-  float cj[12];
+  float cjst[(FSM && ZB_CJ_SMEM) ? 1 : 12];
+  ZB_DI float cjget(int k) const { return (FSM && ZB_CJ_SMEM) ? fsm[32 * (F_CJ + k)] : cjst[(FSM && ZB_CJ_SMEM) ? 0 : k]; }
+  ZB_DI void cjput(int k, float v) { if (FSM && ZB_CJ_SMEM) fsm[32 * (F_CJ + k)] = v; else cjst[(FSM && ZB_CJ_SMEM) ? 0 : k] = v; }
   int jsrc, jsrc2;      // first lane of the chain of geom 2 / of geom 1 (BL0: the base dofs, geom 1 = the floor)
   int pairlane;         // body lane of geom 1 of my group (0 = world)
   float cn[3], ct[3];   // contact normal and the tangent of this lane's pyramid edge (collision())
@@ -604,7 +609,6 @@ struct WarpEnv {
       y = fmaf(C[k], vk, y);  // C is zero outside the lane's chain block
     }
     float p[8];
-#pragma unroll
 #if ZB_PRED
     const float vh = hinge ? v : 0.f;  // (base lanes hold A in Bm: must stay masked)
 #pragma unroll
@@ -625,13 +629,13 @@ struct WarpEnv {
 #if ZB_EXPLICIT_J
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < CHD; k++) s = fmaf(cj[k], shf(v, jsrc + k), s);
+    for (int k = 0; k < CHD; k++) s = fmaf(cjget(k), shf(v, jsrc + k), s);
     if (any_pair) {  // (kernel-uniform) some group has geom 1 on a body: its second block are that chain's dofs
 #pragma unroll
-      for (int k = 0; k < CHD; k++) s = fmaf(cj[6 + k], shf(v, jsrc2 + k), s);
+      for (int k = 0; k < CHD; k++) s = fmaf(cjget(6 + k), shf(v, jsrc2 + k), s);
     } else {
 #pragma unroll
-      for (int a = 0; a < 6; a++) s = fmaf(cj[6 + a], vb[a], s);
+      for (int a = 0; a < 6; a++) s = fmaf(cjget(6 + a), vb[a], s);
     }
     return s;
 #else
@@ -669,7 +673,7 @@ struct WarpEnv {
       for (int j = 0; j < 3; j++) { ax[j] = shf(cdof[j], jsrc + k); rel[j] = cpos[j] - shf(anc[j], jsrc + k); }
       const int hk = __shfl_sync(ZB_FULL, (int)hinge, jsrc + k);
       cross3(c, ax, rel);
-      cj[k] = (hk && jsrc + k <= boxlane) ? dot3(dir, c) : 0.f;
+      cjput(k, (hk && jsrc + k <= boxlane) ? dot3(dir, c) : 0.f);
     }
     // second block: base dofs (geom 1 = the floor plane: translations J = dir, rotations about the body-frame axes through the base origin)
     const float rel[3] = {cpos[0] - xb[0], cpos[1] - xb[1], cpos[2] - xb[2]};
@@ -678,8 +682,8 @@ struct WarpEnv {
       const float col[3] = {Rb[a], Rb[3 + a], Rb[6 + a]};
       float c[3];
       cross3(c, col, rel);
-      cj[6 + a] = dir[a];
-      cj[9 + a] = dot3(dir, c);
+      cjput(6 + a, dir[a]);
+      cjput(9 + a, dot3(dir, c));
     }
     jsrc2 = BL0;
     if (any_pair) {
@@ -696,8 +700,8 @@ struct WarpEnv {
         cross3(c, ax, rl);
         const float v = (hk && j2 + k <= pairlane) ? -dot3(dir, c) : 0.f;
         if (pair) {
-          if (j2 == jsrc) { cj[k] += v; cj[6 + k] = 0.f; }  // both geoms hang on the same chain
-          else cj[6 + k] = v;
+          if (j2 == jsrc) { cjput(k, cjget(k) + v); cjput(6 + k, 0.f); }  // both geoms hang on the same chain
+          else cjput(6 + k, v);
         }
       }
       jsrc2 = j2;
@@ -730,14 +734,13 @@ struct WarpEnv {
 #if ZB_EXPLICIT_J
     // sum_r J[r, d] f_r over the 16 row lanes of each box as a transpose-reduce inside the half-warp: total t lands in lane 16 g + t
     float p[16];
-#pragma unroll
 #if ZB_PRED
     const float fm = c_on ? f : 0.f;
 #pragma unroll
-    for (int k = 0; k < 12; k++) p[k] = fm * cj[k];
+    for (int k = 0; k < 12; k++) p[k] = fm * cjget(k);
 #else
 #pragma unroll
-    for (int k = 0; k < 12; k++) p[k] = c_on ? f * cj[k] : 0.f;
+    for (int k = 0; k < 12; k++) p[k] = c_on ? f * cjget(k) : 0.f;
 #endif
     p[12] = p[13] = p[14] = p[15] = 0.f;
     int m = 8;

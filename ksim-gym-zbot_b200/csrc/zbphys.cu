@@ -14,9 +14,12 @@
 
 #include "../../include/zbphys.h"
 #include "zb_kernel.cuh"
+#if ZB_TU == 0
+#include "zb_policy.cuh"
+#endif
 
 #define ZB_ABI_VERSION 5
-#define ZB_FSM_BYTES_PER_WARP (31 * 32 * 4) /* WarpEnv::F_N floats per lane */
+#define ZB_FSM_BYTES_PER_WARP ((31 + (ZB_CJ_SMEM ? 12 : 0)) * 32 * 4) /* WarpEnv::F_N floats per lane */
 
 // auto-reset pass of the step kernel (zb_step_autoreset_f32)
 struct ZbAutoReset {
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(WPB * 32, 1) zb_kernel(const ZbDev* __restrict
   extern __shared__ float dyn_smem[];
   WarpEnv<TRACE, FSM, GEN> E;
   E.init_topology(D, o, meaninertia, scratch[wib], L, cflags);
-  E.fsm = FSM ? dyn_smem + (size_t)wib * (32 * 31) + L : nullptr;
+  E.fsm = FSM ? dyn_smem + (size_t)wib * (ZB_FSM_BYTES_PER_WARP / 4) + L : nullptr;
   const int b = E.isbody ? L : 0;
   const int d = E.hasdof ? E.dof : 0;
   // ---- per-environment model (randomizers, train.py:1439-1455) ----
@@ -930,6 +933,32 @@ int zb_feet_airtime_f32(void* stream, const float* left_contact, const float* ri
                                                                           n_envs, n_steps, ctrl_dt, touchdown_penalty);
   return after_launch("zb_feet_airtime_f32 launch: %s");
 }
+
+/* Actor network of the reference for one control step (zb_policy.cuh). */
+int zb_actor_f32(void* stream, const ZbActor* A, const float* actor_obs, const float* carry_in, float* carry_out, const uint8_t* carry_reset,
+                 const float* noise_u, const float* noise_eps, float* action, float* dist, int n_envs) {
+  if (!A || !actor_obs || !carry_in || !carry_out || !action || n_envs < 0) return fail(ZB_EINVAL, "zb_actor_f32: bad argument%s");
+  if (!A->in_wt || !A->in_b || !A->gru_wih_t || !A->gru_whh_t || !A->gru_b || !A->gru_bn || !A->out_wt || !A->out_b)
+    return fail(ZB_EINVAL, "zb_actor_f32: NULL weight pointer%s");
+  if ((((uintptr_t)A->in_wt | (uintptr_t)A->gru_wih_t | (uintptr_t)A->gru_whh_t | (uintptr_t)A->out_wt) & 15) != 0)
+    return fail(ZB_EINVAL, "zb_actor_f32: weight matrices must be 16-byte aligned (they are fetched by TMA bulk copies)%s");
+  if ((noise_u == nullptr) != (noise_eps == nullptr)) return fail(ZB_EINVAL, "zb_actor_f32: noise_u and noise_eps come together (both NULL = mode)%s");
+  if (A->n_in < 1 || A->n_in > ZB_ACTOR_MAX_IN || A->depth < 1 || A->num_mixtures < 1 || A->num_mixtures > ZB_ACTOR_MAX_MIXTURES)
+    return fail(ZB_EUNSUP, "zb_actor_f32: n_in <= 128, depth >= 1, 1 <= num_mixtures <= 5 (hidden size 128 is built in)%s");
+  if (n_envs == 0) return ZB_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(ZB_ENODEV, "zb_actor_f32: no CUDA device%s");
+  static std::atomic<unsigned long long> attr_set{0};
+  if (dev < 64 && !((attr_set.load() >> dev) & 1ull)) {
+    cudaError_t ce = cudaFuncSetAttribute(zb_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbpSmem));
+    if (ce != cudaSuccess) return fail(ZB_ECUDA, "zb_actor_f32: cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(ce));
+    attr_set.fetch_or(1ull << dev);
+  }
+  zb_actor_kernel<<<(n_envs + ZBP_TE - 1) / ZBP_TE, ZBP_THREADS, sizeof(ZbpSmem), (cudaStream_t)stream>>>(*A, actor_obs, carry_in, carry_out, carry_reset, noise_u,
+                                                                                                      noise_eps, action, dist, n_envs);
+  return after_launch("zb_actor_f32 launch: %s");
+}
+int zb_sizeof_actor(void) { return (int)sizeof(ZbActor); }
 
 /* Launches the FFMA probe: grid x 256 threads, `iters` x 16 FMAs per thread.  The caller times it with CUDA events;
  * flops = grid * 256 * iters * 16 * 2. */
