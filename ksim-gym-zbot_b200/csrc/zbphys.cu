@@ -945,7 +945,6 @@ int zb_actor_f32(void* stream, const ZbActor* A, const float* actor_obs, const f
   if ((noise_u == nullptr) != (noise_eps == nullptr)) return fail(ZB_EINVAL, "zb_actor_f32: noise_u and noise_eps come together (both NULL = mode)%s");
   if (A->n_in < 1 || A->n_in > ZB_ACTOR_MAX_IN || A->depth < 1 || A->num_mixtures < 1 || A->num_mixtures > ZB_ACTOR_MAX_MIXTURES)
     return fail(ZB_EUNSUP, "zb_actor_f32: n_in <= 128, depth >= 1, 1 <= num_mixtures <= 5 (hidden size 128 is built in)%s");
-  if (n_envs == 0) return ZB_OK;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(ZB_ENODEV, "zb_actor_f32: no CUDA device%s");
   static std::atomic<unsigned long long> attr_set{0};
@@ -954,6 +953,7 @@ int zb_actor_f32(void* stream, const ZbActor* A, const float* actor_obs, const f
     if (ce != cudaSuccess) return fail(ZB_ECUDA, "zb_actor_f32: cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(ce));
     attr_set.fetch_or(1ull << dev);
   }
+  if (n_envs == 0) return ZB_OK;  // (a call with n_envs = 0 only prepares the kernel: do one before capturing launches into a CUDA graph)
   zb_actor_kernel<<<(n_envs + ZBP_TE - 1) / ZBP_TE, ZBP_THREADS, sizeof(ZbpSmem), (cudaStream_t)stream>>>(*A, actor_obs, carry_in, carry_out, carry_reset, noise_u,
                                                                                                       noise_eps, action, dist, n_envs);
   return after_launch("zb_actor_f32 launch: %s");

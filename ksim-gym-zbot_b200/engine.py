@@ -74,7 +74,7 @@ MAX_EPISODE_SEC = 80.0  # ksim.EpisodeLengthTermination(max_length_sec=80), trai
 ZB_OK, ZB_EINVAL, ZB_ENODEV, ZB_ECUDA, ZB_EUNSUP = 0, -1, -2, -3, -4
 EXPORTS = ["zb_engine_create", "zb_engine_destroy", "zb_engine_set_opts", "zb_step_f32", "zb_forward_f32", "zb_reset_f32",
            "zb_abi_version", "zb_sizeof_model", "zb_sizeof_opts", "zb_last_error", "zb_launch_count", "zb_bench_ffma", "zb_terminations_f32", "zb_step_autoreset_f32",
-           "zb_step_obs_f32", "zb_reset_obs_f32", "zb_feet_airtime_f32", "zb_cta_shape"]
+           "zb_step_obs_f32", "zb_reset_obs_f32", "zb_feet_airtime_f32", "zb_cta_shape", "zb_actor_f32", "zb_sizeof_actor"]
 
 
 def _term_ptrs(terminal):

@@ -87,6 +87,11 @@ class ActorPolicy:
                             *[self.weights[k].data_ptr() for k in ("in_wt", "in_b", "gru_wih_t", "gru_whh_t", "gru_b", "gru_bn", "out_wt", "out_b", "mean_bias")])
         self.carry = torch.zeros((self.n, params.depth, HIDDEN), dtype=torch.float32, device=self.device)  # get_initial_model_carry, train.py:1731
         self.action = torch.zeros((self.n, M.NU), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):  # n_envs = 0: sets the kernel's shared-memory attribute, so that later launches can be graph-captured
+            z = ctypes.c_void_p(self.carry.data_ptr())
+            rc = self.lib.zb_actor_f32(None, ctypes.byref(self.desc), z, z, z, None, None, None, z, None, 0)
+        if rc != 0:
+            raise ZbError(rc, self.lib.zb_last_error().decode())
 
     def reset_carry(self) -> None:
         self.carry.zero_()

@@ -5,8 +5,10 @@
 Here every control step is ONE launch (zb_step_obs_f32: S fused substeps + terminations + partial reset + observation epilogue)
 whose output pointers are slices of the time-major trajectory arrays, so the launch itself is the trajectory writer: no gather,
 no copy.  With the actions given up front (random-action rollouts, BASELINE.json configs[1-2]) the T launches of a chunk are
-captured into one CUDA graph; with a policy in the loop the launches are issued step by step and the policy reads
-``trajectory.actor_obs[t]`` directly.
+captured into one CUDA graph.  With the reference's actor in the loop (``unroll_actor``: ``ActorPolicy`` = zb_actor_f32, SURVEY.md §8f
+rank 4) a control step is TWO launches — actor (reads ``trajectory.actor_obs[t]``, writes ``trajectory.action[t]``, carries its GRU state,
+restarts it where ``done[t-1]``) and physics — and the 2T launches of a chunk are again one CUDA graph: the whole ``jax.lax.scan`` of
+``RLTask._single_unroll`` [R] runs on the device without the host.  Any other ``policy`` callable is issued step by step.
 
 Index alignment (as ksim's rollout stores it [R]):
   state-like  [T, N, ...]    qpos, qvel, xpos, xquat, done : `next_physics_state` of step t BEFORE the done -> reset select (the
@@ -76,6 +78,9 @@ class Rollout:
         self.ps = eng.new_state(self.n)
         self._graph = None
         self._plans = None
+        self._actor_graphs = {}
+        self.prev_done = torch.zeros((self.n,), dtype=torch.uint8, device=dev)  # `done` of the last step of the previous chunk
+        self.noise_u = self.noise_eps = self.pushes = None
 
     def _obs_slot(self, t: int) -> Observations:
         tr, c = self.traj, self.carry_obs
@@ -127,6 +132,54 @@ class Rollout:
                 self.d_push.copy_(pushes[t] if pushes is not None else self.eng.sample_push(self.n))
             plans[t](tr.action[t], self.d_push)
         return tr
+
+    def unroll_actor(self, policy, argmax: bool = True, graph: bool = True) -> Trajectory:
+        """One chunk with the reference's actor in the loop (``sample_action``, train.py:1737-1763): per control step
+        ``policy.enqueue`` (zb_actor_f32) then the physics launch, nothing else — no host round trip, no copy.  ``argmax=False``
+        samples with the numbers in ``self.noise_u`` / ``self.noise_eps`` [T, N, 20] (refill them in place before every chunk:
+        ``sample_noise()``); a configured PushEvent reads ``self.pushes`` [T, N, 7] (``sample_pushes()``).  The carry of an
+        environment restarts at the step after its ``done`` (``prev_done`` carries that across chunks).  With ``graph=True`` the 2T
+        launches are captured once per (argmax) and replayed."""
+        tr, plans, T, dev = self.traj, self.plans(), self.T, self.eng.device
+        if not argmax and self.noise_u is None:
+            self.noise_u = torch.zeros((T, self.n, M.NU), dtype=torch.float32, device=dev)
+            self.noise_eps = torch.zeros((T, self.n, M.NU), dtype=torch.float32, device=dev)
+            self.sample_noise()
+        if self.eng.push is not None and self.pushes is None:
+            self.pushes = torch.zeros((T, self.n, 7), dtype=torch.float32, device=dev)
+            self.sample_pushes()
+
+        def issue():
+            for t in range(T):
+                policy.enqueue(tr.actor_obs[t], tr.action[t], carry_reset=self.prev_done if t == 0 else tr.done[t - 1],
+                               noise_u=None if argmax else self.noise_u[t], noise_eps=None if argmax else self.noise_eps[t])
+                plans[t](tr.action[t], None if self.pushes is None else self.pushes[t])
+            self.prev_done.copy_(tr.done[T - 1])
+
+        if not graph:
+            issue()
+            return tr
+        key = (id(policy), bool(argmax))
+        if key not in self._actor_graphs:
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    issue()
+            torch.cuda.current_stream(dev).wait_stream(s)
+            self._actor_graphs[key] = g
+        self._actor_graphs[key].replay()
+        return tr
+
+    def sample_noise(self, generator: torch.Generator | None = None) -> None:
+        """Refill the action-sampling numbers of a chunk in place: U[0,1) for the mixture component, N(0,1) for the Gaussian."""
+        self.noise_u.uniform_(0.0, 1.0, generator=generator)
+        self.noise_eps.normal_(0.0, 1.0, generator=generator)
+
+    def sample_pushes(self) -> None:
+        for t in range(self.T):
+            self.pushes[t].copy_(self.eng.sample_push(self.n))
 
     def next_chunk(self) -> None:
         """Carry the last observation slot over to slot 0 (five small device copies per chunk)."""

@@ -157,8 +157,6 @@ def test_actor_recurrence_reset_and_errors():
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
         gr = torch.cuda.CUDAGraph()
-        pol.enqueue(o, pol.action)  # warm (sets the function attribute outside the capture)
-        pol.carry.copy_(torch.tensor(carry.astype(np.float32)))
         with torch.cuda.graph(gr, stream=s):
             pol.enqueue(o, pol.action)
     torch.cuda.current_stream().wait_stream(s)

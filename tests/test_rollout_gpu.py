@@ -124,3 +124,59 @@ def test_chunk_graph_replay_and_reference_rewards(zmodel):
     ro.next_chunk()
     assert torch.equal(tr.actor_obs[0], last)
     eng.close()
+
+
+def test_actor_in_the_loop_rollout(zmodel):
+    """unroll_actor (zb_actor_f32 + physics per control step, the chunk as ONE CUDA graph) == the same chunk driven step by step with
+    the actions the CPU restatement of Actor.forward computes from the observations the kernels wrote (closed loop: every step's action
+    feeds the next state), incl. carry restarts after terminations and a second chunk."""
+    import zb_policy_oracle as PO
+    from ksim_gym_zbot_b200.policy import ActorParams, ActorPolicy
+
+    n, T = 256, 30
+    eng, ep, ro, _ = _setup(zmodel, n, T, push=True, seed=5)  # strong pushes: environments fall inside the chunk (ro.pushes, sampled once)
+    prm = ActorParams.random(seed=9)
+    prm.arrays["output_proj.weight"] *= 4.0  # livelier actions
+    pol = ActorPolicy(prm, n, eng.device)
+    ro.reset()
+    ro.unroll_actor(pol, argmax=True)           # capture + first replay
+    torch.cuda.synchronize()
+    tr = ro.traj
+    g1 = {k: getattr(tr, k).clone() for k in ("qpos", "qvel", "done", "action", "actor_obs")}
+    carry1 = pol.carry.clone()
+    # ---- the same chunk launch by launch (graph=False): identical bits
+    ro.reset(); pol.reset_carry(); ro.prev_done.zero_()
+    ro.unroll_actor(pol, argmax=True, graph=False)
+    torch.cuda.synchronize()
+    for k, v in g1.items():
+        assert torch.equal(getattr(tr, k), v), f"graph vs launch-by-launch: trajectory.{k}"
+    assert torch.equal(pol.carry, carry1)
+    # ---- teacher-forced check of every actor launch against the oracle: action[t] from (actor_obs[t], carry, done[t-1])
+    obs, act, done = tr.actor_obs.cpu().numpy(), tr.action.cpu().numpy(), tr.done.cpu().numpy()
+    carry = np.zeros((n, prm.depth, 128))
+    for t in range(T):
+        if t > 0:
+            carry[done[t - 1] != 0] = 0.0
+        mean, std, logits, carry = PO.actor_forward(prm.oracle_dict(), obs[t], carry)
+        np.testing.assert_allclose(act[t], PO.select_action(mean, std, logits), rtol=0, atol=2e-4, err_msg=f"step {t}")
+    np.testing.assert_allclose(pol.carry.cpu().numpy(), carry, rtol=0, atol=5e-5)
+    assert int((done != 0).sum()) > 0, "no termination inside the chunk: the carry restart is not exercised"
+    # ---- second chunk: continues from the last observation slot, prev_done carries the restart across the chunk boundary
+    last_done = tr.done[T - 1].clone()
+    ro.next_chunk()
+    ro.unroll_actor(pol, argmax=True)
+    torch.cuda.synchronize()
+    assert torch.equal(ro.prev_done, tr.done[T - 1]) and last_done.shape == ro.prev_done.shape
+    carry[last_done.cpu().numpy() != 0] = 0.0
+    mean, std, logits, _ = PO.actor_forward(prm.oracle_dict(), tr.actor_obs[0].cpu().numpy(), carry)
+    np.testing.assert_allclose(tr.action[0].cpu().numpy(), PO.select_action(mean, std, logits), rtol=0, atol=2e-4)
+    # ---- sampled actions: the chunk's noise buffers are consumed (different numbers -> different actions), finite states
+    ro.reset(); pol.reset_carry(); ro.prev_done.zero_()
+    ro.unroll_actor(pol, argmax=False)
+    torch.cuda.synchronize()
+    a1 = tr.action.clone()
+    ro.reset(); pol.reset_carry(); ro.prev_done.zero_(); ro.sample_noise()
+    ro.unroll_actor(pol, argmax=False)
+    torch.cuda.synchronize()
+    assert not torch.equal(a1, tr.action) and torch.isfinite(tr.qpos).all()
+    eng.close()
