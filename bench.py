@@ -624,6 +624,9 @@ def main():
             if sp_.S == 20:
                 Ke = min(Ke, 20)
             extras.append(measure(a, sp_, model, Ke, We, rank, world, local, primary=False) | {"K": Ke, "W": We})
+    rollout_actor = None
+    if not a.no_extras and a.workload == "c2" and a.substeps == 4:
+        rollout_actor = measure_rollout_actor(a, spec, model, rank, world, local)
 
     if rank != 0:
         if world > 1:
@@ -663,10 +666,70 @@ def main():
                   "ctrl_steps_per_s": res["value"] / spec.S, "solver_niter_mean_flop_sample": niter_cpu, "flops_per_stage": stage},
         "other_workloads": others,
     }
+    if rollout_actor is not None:
+        rollout_actor["actor"]["fp32_frac"] = rollout_actor["actor"]["achieved_tflops"] / fp32_peak if fp32_peak else None
+        line["rollout_actor"] = rollout_actor
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
+
+
+def measure_rollout_actor(a, spec: "Spec", model, rank: int, world: int, local: int, T: int = 200, chunks: int = 3):
+    """BASELINE.json configs[1] with the reference's actor in the loop: per control step zb_actor_f32 (random-init
+    weights of the reference architecture, train.py:885-968, sampled actions) + the physics launch writing the Trajectory; the 2T launches of
+    a T = 200 step chunk (rollout_length 4.0 s / ctrl_dt, train.py:1775) replay as ONE CUDA graph.  Timed: `chunks` replays with CUDA
+    events, max over ranks.  The actor kernel is also timed alone (L2 flushed) for its FP32 roofline fraction."""
+    import torch
+    import torch.distributed as dist
+
+    from ksim_gym_zbot_b200 import model as M
+    from ksim_gym_zbot_b200.engine import ZbotCudaEngine
+    from ksim_gym_zbot_b200.policy import ActorParams, ActorPolicy
+    from ksim_gym_zbot_b200.rollout import Rollout
+    from ksim_gym_zbot_b200.sharding import aggregate_throughput, rank_seed
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zb_policy_oracle as PO
+
+    dev = torch.device("cuda", local)
+    n = spec.n_env
+    eng = ZbotCudaEngine(model, n, device=local, opts=spec.opts(), ctrl_dt=spec.ctrl_dt, seed=rank_seed(spec.seed, rank) + 5)
+    ro = Rollout(eng, T)
+    pol = ActorPolicy(ActorParams.random(seed=spec.seed), n, dev)
+    launches0 = eng.launch_count()
+    ro.reset()
+    ro.unroll_actor(pol, argmax=False)  # capture + first replay (warm-up chunk)
+    ro.next_chunk()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(chunks):
+        ro.sample_noise()
+        ro.unroll_actor(pol, argmax=False)
+        ro.next_chunk()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value, ms_max = aggregate_throughput(n * spec.S * T * chunks, ms, dev)
+    resets = float((ro.traj.done != 0).sum().item()) / T
+    # the actor kernel alone
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(20)]
+    for x, y in ev:
+        flush.zero_()
+        x.record(); pol.enqueue(ro.traj.actor_obs[0], pol.action); y.record()
+    torch.cuda.synchronize()
+    actor_ms = float(np.median([x.elapsed_time(y) for x, y in ev]))
+    eng.close()
+    return {"workload": f"c2 {n} envs/GPU S={spec.S} + actor in the loop", "value": value, "unit": UNIT, "chunks": chunks, "chunk_steps": T,
+            "ms_per_ctrl_step": ms_max / (T * chunks), "launches_per_ctrl_step": 2, "graph": "one CUDA graph per chunk (2T launches + 1 copy)",
+            "actions": "sampled from the mixture (pre-sampled U / N numbers per chunk), random-init weights", "resets_per_step": resets,
+            "trajectory_bytes_per_env_ctrl_step": ro.traj.bytes_per_env_step(),
+            "actor": {"kernel_ms": actor_ms, "flops_per_env": PO.flops_per_env(), "achieved_tflops": n * PO.flops_per_env() / (actor_ms * 1e-3) / 1e12,
+                      "dtype": "f32 (CUDA cores)", "ctas": (n + 31) // 32}}
 
 def run_reference(a, spec: Spec, model, world: int):
     """The reference arm: the reference's algorithm for this path on the host cores (CpuArm), full per-GPU batch, K timed control steps."""
