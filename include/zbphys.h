@@ -407,8 +407,14 @@ typedef struct ZbActor {
   int32_t depth;         /* GRU layers (train.py:1069-1072: 5) */
   int32_t num_mixtures;  /* train.py:1073-1076: 5 */
   float min_std, max_std, var_scale; /* train.py:1609-1610: 0.01, 1.0; Model passes var_scale = 1.0 (train.py:1046) */
+  int32_t precision;     /* ZB_ACTOR_FP32: GRU stack on the CUDA cores in fp32; ZB_ACTOR_TF32X3: on the tensor cores (tcgen05, 3xTF32) */
+  int32_t reserved;
   const float *in_wt, *in_b, *gru_wih_t, *gru_whh_t, *gru_b, *gru_bn, *out_wt, *out_b, *mean_bias;
+  const float* gru_w_tc; /* ZB_ACTOR_TF32X3 only: [depth][16 k-tiles][6 matrices: W_ih r,z,n, W_hh r,z,n][2 k-chunks][128 f][4 k] =
+                            W_m[f][8 t + 4 c + j] — the tcgen05 K-major no-swizzle operand layout, one 24 KB TMA bulk copy per k-tile */
 } ZbActor;
+#define ZB_ACTOR_FP32 0
+#define ZB_ACTOR_TF32X3 1
 /* One control step of the actor for n_envs environments.
  *   actor_obs   [N, n_in]          in
  *   carry_in    [N, depth, 128]    in   the actor half of the model carry (train.py:1731-1735); carry_out may alias it (in place)
@@ -420,7 +426,10 @@ typedef struct ZbActor {
  *                                       sample_action(argmax=True), train.py:1757).  The reference draws them from a JAX PRNG key.
  *   action      [N, 20]            out
  *   dist        [N, 3, 20, M] or NULL  out: means (incl. JOINT_BIASES), stds, logits as handed to ksim.MixtureOfGaussians (train.py:965)
- * fp32 on the CUDA cores, one CTA per 32 environments.  Errors: ZB_EINVAL (NULL / sizes), ZB_EUNSUP (limits above), ZB_ECUDA. */
+ * One CTA per 32 environments.  precision = ZB_ACTOR_FP32: everything in fp32 on the CUDA cores (matches a CPU float32 evaluation to
+ * rounding).  ZB_ACTOR_TF32X3: the GRU stack (92 % of the FLOPs) on the tcgen05 tensor cores with every product issued as
+ * hi.hi + hi.lo + lo.hi of TF32 halves (fp32-level accuracy, ~1e-6 relative), accumulators in TMEM; needs gru_w_tc and n_in <= 96.
+ * Errors: ZB_EINVAL (NULL / sizes / alignment), ZB_EUNSUP (limits above), ZB_ECUDA. */
 int zb_actor_f32(void* cuda_stream, const ZbActor* actor, const float* actor_obs, const float* carry_in, float* carry_out,
                  const uint8_t* carry_reset, const float* noise_u, const float* noise_eps, float* action, float* dist, int n_envs);
 int zb_sizeof_actor(void);

@@ -108,6 +108,48 @@ struct ZbpStream {
   }
 };
 
+// mixture-of-Gaussians head: one (environment, joint) pair per thread; `out` = output_proj result of the tile [env][n_out]
+static __device__ __forceinline__ void zbp_head(const ZbActor& A, float (*outp)[ZBP_OUT_MAX + 1], int env0, int n_envs, const float* __restrict__ noise_u,
+                                                const float* __restrict__ noise_eps, float* __restrict__ action, float* __restrict__ dist) {
+  const int tid = threadIdx.x;
+  const int M = A.num_mixtures, sl = ZB_NU * M;
+  for (int i = tid; i < ZBP_TE * ZB_NU; i += ZBP_THREADS) {
+    const int e = i / ZB_NU, j = i - e * ZB_NU, env = env0 + e;
+    if (env >= n_envs) continue;
+    const float* o = outp[e];
+    const float jb = A.mean_bias ? A.mean_bias[j] : 0.f;
+    float lmax = -INFINITY;
+    int kmax = 0;
+    for (int m = 0; m < M; m++) {
+      const float lg = o[2 * sl + j * M + m];
+      if (lg > lmax) { lmax = lg; kmax = m; }  // first maximum (jnp.argmax)
+    }
+    int kk = kmax;
+    if (noise_eps && noise_u) {  // categorical by inverse CDF of softmax(logits) at u in [0, 1)
+      float tot = 0.f;
+      for (int m = 0; m < M; m++) tot += expf(o[2 * sl + j * M + m] - lmax);
+      const float u = noise_u[(size_t)env * ZB_NU + j] * tot;
+      float cum = 0.f;
+      kk = M - 1;
+      for (int m = 0; m < M; m++) {
+        cum += expf(o[2 * sl + j * M + m] - lmax);
+        if (u < cum) { kk = m; break; }
+      }
+    }
+    const float mean = o[j * M + kk] + jb;
+    const float sd = fminf((zbp_softplus(o[sl + j * M + kk]) + A.min_std) * A.var_scale, A.max_std);
+    action[(size_t)env * ZB_NU + j] = noise_eps ? fmaf(sd, noise_eps[(size_t)env * ZB_NU + j], mean) : mean;
+    if (dist) {  // the distribution parameters as the reference hands them to MixtureOfGaussians: [N, 3, 20, M]
+      for (int m = 0; m < M; m++) {
+        float* d = dist + (size_t)env * 3 * sl;
+        d[j * M + m] = o[j * M + m] + jb;
+        d[sl + j * M + m] = fminf((zbp_softplus(o[sl + j * M + m]) + A.min_std) * A.var_scale, A.max_std);
+        d[2 * sl + j * M + m] = o[2 * sl + j * M + m];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ZBP_THREADS, 1)
 zb_actor_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_in, float* carry_out, const uint8_t* __restrict__ carry_reset,
                 const float* __restrict__ noise_u, const float* __restrict__ noise_eps, float* __restrict__ action, float* __restrict__ dist, int n_envs) {
@@ -252,41 +294,5 @@ zb_actor_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_in,
   __syncthreads();
 #undef ZBP_ACQUIRE
 #undef ZBP_RELEASE
-  // ---- mixture-of-Gaussians head: one (environment, joint) pair per thread ----
-  const int M = A.num_mixtures, sl = ZB_NU * M;
-  for (int i = tid; i < ZBP_TE * ZB_NU; i += ZBP_THREADS) {
-    const int e = i / ZB_NU, j = i - e * ZB_NU, env = env0 + e;
-    if (env >= n_envs) continue;
-    const float* o = S.out[e];
-    const float jb = A.mean_bias ? A.mean_bias[j] : 0.f;
-    float lmax = -INFINITY;
-    int kmax = 0;
-    for (int m = 0; m < M; m++) {
-      const float lg = o[2 * sl + j * M + m];
-      if (lg > lmax) { lmax = lg; kmax = m; }  // first maximum (jnp.argmax)
-    }
-    int kk = kmax;
-    if (noise_eps && noise_u) {  // categorical by inverse CDF of softmax(logits) at u in [0, 1)
-      float tot = 0.f;
-      for (int m = 0; m < M; m++) tot += expf(o[2 * sl + j * M + m] - lmax);
-      const float u = noise_u[(size_t)env * ZB_NU + j] * tot;
-      float cum = 0.f;
-      kk = M - 1;
-      for (int m = 0; m < M; m++) {
-        cum += expf(o[2 * sl + j * M + m] - lmax);
-        if (u < cum) { kk = m; break; }
-      }
-    }
-    const float mean = o[j * M + kk] + jb;
-    const float sd = fminf((zbp_softplus(o[sl + j * M + kk]) + A.min_std) * A.var_scale, A.max_std);
-    action[(size_t)env * ZB_NU + j] = noise_eps ? fmaf(sd, noise_eps[(size_t)env * ZB_NU + j], mean) : mean;
-    if (dist) {  // the distribution parameters as the reference hands them to MixtureOfGaussians: [N, 3, 20, M]
-      for (int m = 0; m < M; m++) {
-        float* d = dist + (size_t)env * 3 * sl;
-        d[j * M + m] = o[j * M + m] + jb;
-        d[sl + j * M + m] = fminf((zbp_softplus(o[sl + j * M + m]) + A.min_std) * A.var_scale, A.max_std);
-        d[2 * sl + j * M + m] = o[2 * sl + j * M + m];
-      }
-    }
-  }
+  zbp_head(A, S.out, env0, n_envs, noise_u, noise_eps, action, dist);
 }

@@ -1,0 +1,320 @@
+// zb_policy_tc.cuh — the actor's GRU stack on the 5th-generation tensor cores (tcgen05 + TMEM), 3xTF32 so that the result keeps fp32
+// accuracy (the fp32 CUDA-core kernel of zb_policy.cuh is the reference implementation and the checker).
+//
+// Per CTA: 32 environments (the MMA N dimension), the 128 hidden units of a gate are the M dimension:
+//     D_gate[128 f x 32 env] (+)= W_gate[128 f x 8 k] . X^T[8 k x 32 env]            tcgen05.mma.cta_group::1.kind::tf32, M128 N32 K8
+// Four fp32 accumulators live in 128 TMEM columns: r (W_ir x + W_hr h), z, i_n (W_in x), h_n (W_hn h).  Every product is issued three
+// times — hi.hi + hi.lo + lo.hi with v_hi = v & 0xffffe000 (exactly representable in TF32), v_lo = v - v_hi — which recovers ~21 of
+// the 24 mantissa bits of each factor (the tensor core accumulates in fp32).  Per layer: 6 gate matrices x 16 K-steps x 3 = 288 MMAs,
+// issued by ONE thread; the other 511 threads feed it:
+//   * weights: host-packed in the UMMA canonical K-major no-swizzle layout (8-row x 16-byte core matrices; ZbActor.gru_w_tc
+//     [layer][k-tile 16][matrix 6][k-chunk 2][f 128][4]) so that a plain TMA bulk copy of 24 KB lands a ready operand tile in shared
+//     memory; a 3-stage ring (full = transaction mbarrier, free again = tcgen05.commit on an mbarrier); the threads split each
+//     landed tile into hi (in place) and lo (second half of the stage);
+//   * activations: the layer input and the carry as hi / lo pairs in the same canonical layout ([k-chunk 32][env 32][4]), written by
+//     the epilogue threads of the previous layer / loaded from the carry;
+//   * epilogue: tcgen05.ld (32 lanes x 8 columns per warp) hands thread (f, eg) the four gate sums of hidden unit f for its 8
+//     environments — the same thread mapping as the CUDA-core kernel — then sigmoid / tanh / blend in fp32, carry out, next operand.
+// input_proj (50 -> 128) and output_proj (128 -> 300) are 8 % of the FLOPs and stay on the CUDA cores (fp32), fed by the same ring.
+#pragma once
+#include "zb_policy.cuh"
+
+#define ZBT_NST 4
+#ifndef ZBT_ROTATE
+#define ZBT_ROTATE 0 /* measured: no effect (the stream is not L2-slice-bound), and a fixed order keeps results independent of the CTA index */
+#endif
+#define ZBT_TILE_FLOATS (6 * 2 * ZBP_H * 4) /* 24 KB: [matrix 6][k-chunk 2][f 128][4 k] */
+#define ZBT_B_FLOATS (32 * ZBP_TE * 4)      /* 16 KB: [k-chunk 32][env 32][4 k] */
+#define ZBT_MAX_IN 96
+#define ZBT_TMEM_COLS 128
+
+struct ZbtSmem {
+  float w[ZBT_NST][ZBT_TILE_FLOATS];     // weight ring: TMA destination, masked to its TF32 hi part in place; the end of the kernel re-uses it for `out`
+  float wlo[2][ZBT_TILE_FLOATS];         // lo parts of the tile being multiplied and of the next one (input_proj: its weights land here)
+  float bx[2][ZBT_B_FLOATS];             // layer input, hi / lo
+  float bh[2][ZBT_B_FLOATS];             // carry of the layer, hi / lo (input_proj: observation scratch; output_proj: its input, k-major)
+  uint64_t full[ZBT_NST], mma_done[ZBT_NST], layer_done, in_full;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(ZbtSmem) <= 232448, "ZbtSmem exceeds the 227 KB of shared memory a CTA can have");
+static_assert(ZBP_TE * (ZBP_OUT_MAX + 1) <= ZBT_NST * ZBT_TILE_FLOATS, "`out` must fit the weight ring it aliases");
+static_assert(ZBP_H * ZBP_LD <= 2 * ZBT_B_FLOATS && ZBT_MAX_IN * ZBP_H <= 2 * ZBT_TILE_FLOATS, "aliased regions");
+
+static __device__ __forceinline__ uint64_t zbt_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: start address, leading (K-chunk) and stride (8-row group) byte offsets in
+  // 16-byte units, version 1 (Blackwell)
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+static __device__ __forceinline__ void zbt_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+static __device__ __forceinline__ void zbt_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(zbp_saddr(bar)) : "memory");
+}
+static __device__ __forceinline__ void zbt_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+static __device__ __forceinline__ int zbt_bidx(int k, int env) { return (k >> 2) * (ZBP_TE * 4) + env * 4 + (k & 3); }
+static __device__ __forceinline__ float zbt_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// tiles of the ring in stream order: T_gru GRU tiles ([layer][k-tile] of gru_w_tc, 24 KB each), then output_proj rows (16 k-rows each)
+struct ZbtStream {
+  int t_gru, t_out, n_out;
+  const float *gru, *out_wt;
+  int rot;  // k-tile rotation of this CTA: the CTAs of a launch walk the 16 k-tiles of a layer from 16 different starting points, so that
+            // they do not all pull the same 24 KB from the same L2 slices at the same moment
+  __device__ void issue(int g, ZbtSmem& S) const {  // one thread
+    const int st = g % ZBT_NST;
+    uint64_t* b = &S.full[st];
+    if (g < t_gru) {
+      const int gg = (g & ~15) | ((g + rot) & 15);
+      zbp_mbar_expect(b, ZBT_TILE_FLOATS * 4);
+      zbp_bulk_load(S.w[st], gru + (size_t)gg * ZBT_TILE_FLOATS, ZBT_TILE_FLOATS * 4, b);
+    } else {
+      const int k0 = (g - t_gru) * ZBP_KT_OUT;
+      const uint32_t bytes = (uint32_t)ZBP_KT_OUT * n_out * 4;
+      zbp_mbar_expect(b, bytes);
+      zbp_bulk_load(S.w[st], out_wt + (size_t)k0 * n_out, bytes, b);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(ZBP_THREADS, 1)
+zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_in, float* carry_out, const uint8_t* __restrict__ carry_reset,
+                   const float* __restrict__ noise_u, const float* __restrict__ noise_eps, float* __restrict__ action, float* __restrict__ dist, int n_envs) {
+  extern __shared__ __align__(128) unsigned char zbt_raw[];
+  ZbtSmem& S = *reinterpret_cast<ZbtSmem*>(zbt_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, f = tid & (ZBP_H - 1), eg = tid >> 7, e0 = eg * ZBP_EPT;
+  const int env0 = blockIdx.x * ZBP_TE;
+  const int n_in = A.n_in, n_out = ZB_NU * 3 * A.num_mixtures;
+  ZbtStream W;
+  W.rot = ZBT_ROTATE ? (int)(blockIdx.x & 15) : 0; W.t_gru = A.depth * (ZBP_H / 8); W.t_out = ZBP_H / ZBP_KT_OUT; W.n_out = n_out; W.gru = A.gru_w_tc; W.out_wt = A.out_wt;
+  const int G = W.t_gru + W.t_out;
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 32, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ZBP_TE >> 3) << 17) | ((uint32_t)(ZBP_H >> 4) << 24);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < ZBT_NST; s++) { zbp_mbar_init(&S.full[s], 1); zbp_mbar_init(&S.mma_done[s], 1); }
+    zbp_mbar_init(&S.layer_done, 1);
+    zbp_mbar_init(&S.in_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(zbp_saddr(&S.tmem_base)), "r"((uint32_t)ZBT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)n_in * ZBP_H * 4;  // input_proj weights, whole, into the two lo buffers (48 KB, contiguous)
+    zbp_mbar_expect(&S.in_full, bytes);
+    zbp_bulk_load(S.wlo[0], A.in_wt, bytes, &S.in_full);
+    for (int g0 = 0; g0 < ZBT_NST - 1; g0++) W.issue(g0, S);
+  }
+  // ---- observations of the tile, transposed ([k][e], CUDA-core layout) into the bh region ----
+  float (*obsT)[ZBP_LD] = reinterpret_cast<float (*)[ZBP_LD]>(&S.bh[0][0]);
+  for (int i = tid; i < ZBP_TE * n_in; i += ZBP_THREADS) {
+    const int e = i / n_in, k = i - e * n_in;
+    obsT[k][e] = (env0 + e < n_envs) ? obs[(size_t)(env0 + e) * n_in + k] : 0.f;
+  }
+  __syncthreads();
+  // ---- input_proj (CUDA cores) -> layer 0's input operand (hi / lo) ----
+  {
+    float acc[ZBP_EPT];
+    const float b = A.in_b[f];
+#pragma unroll
+    for (int e = 0; e < ZBP_EPT; e++) acc[e] = b;
+    zbp_mbar_wait(&S.in_full, 0);
+    const float* w = S.wlo[0] + f;
+    for (int k = 0; k < n_in; k++) {
+      const float wv = w[k * ZBP_H];
+      const float4 a = *reinterpret_cast<const float4*>(&obsT[k][e0]), c = *reinterpret_cast<const float4*>(&obsT[k][e0 + 4]);
+      acc[0] = fmaf(wv, a.x, acc[0]); acc[1] = fmaf(wv, a.y, acc[1]); acc[2] = fmaf(wv, a.z, acc[2]); acc[3] = fmaf(wv, a.w, acc[3]);
+      acc[4] = fmaf(wv, c.x, acc[4]); acc[5] = fmaf(wv, c.y, acc[5]); acc[6] = fmaf(wv, c.z, acc[6]); acc[7] = fmaf(wv, c.w, acc[7]);
+    }
+#pragma unroll
+    for (int e = 0; e < ZBP_EPT; e++) {
+      const float h = zbt_hi(acc[e]);
+      S.bx[0][zbt_bidx(f, e0 + e)] = h;
+      S.bx[1][zbt_bidx(f, e0 + e)] = acc[e] - h;
+    }
+  }
+  __syncthreads();  // the lo buffers and the observation scratch are free
+
+#ifdef ZBT_PROFILE
+  long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long pt = clock64(), pstart = pt;
+#define ZBT_TICK(i) do { const long long n_ = clock64(); pf[i] += n_ - pt; pt = n_; } while (0)
+#else
+#define ZBT_TICK(i)
+#endif
+  ZBT_TICK(0);  // setup + input_proj
+  // ---- GRU stack on the tensor cores ----
+  float (*xT)[ZBP_LD] = reinterpret_cast<float (*)[ZBP_LD]>(&S.bh[0][0]);
+  float hold[ZBP_EPT];
+  for (int g = 0; g < W.t_gru; g++) {
+    const int l = g >> 4, t = g & 15, st = g % ZBT_NST;
+    if (t == 0) {  // layer prologue: the carry of this layer as the second activation operand
+#pragma unroll
+      for (int e = 0; e < ZBP_EPT; e++) {
+        const int env = env0 + e0 + e;
+        const bool live = env < n_envs && !(carry_reset && carry_reset[env]);
+        hold[e] = live ? carry_in[((size_t)env * A.depth + l) * ZBP_H + f] : 0.f;
+        const float h = zbt_hi(hold[e]);
+        S.bh[0][zbt_bidx(f, e0 + e)] = h;
+        S.bh[1][zbt_bidx(f, e0 + e)] = hold[e] - h;
+      }
+    }
+    ZBT_TICK(1);  // layer prologue / loop overhead
+    zbp_mbar_wait(&S.full[st], (uint32_t)((g / ZBT_NST) & 1));
+    ZBT_TICK(2);  // wait: tile landed
+    // the lo buffer of this tile was last read by the MMAs of tile g - 2
+    if (g >= 2) zbp_mbar_wait(&S.mma_done[(g - 2) % ZBT_NST], (uint32_t)(((g - 2) / ZBT_NST) & 1));
+    ZBT_TICK(3);  // wait: MMAs of tile g - 2
+#ifndef ZBT_SKIP_CONVERT
+    {  // split the landed tile: hi in place, lo into the tile's lo buffer (12 floats per thread)
+      float4* hi4 = reinterpret_cast<float4*>(S.w[st]) + tid * 3;
+      float4* lo4 = reinterpret_cast<float4*>(S.wlo[g & 1]) + tid * 3;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const float4 v = hi4[i];
+        const float4 h = make_float4(zbt_hi(v.x), zbt_hi(v.y), zbt_hi(v.z), zbt_hi(v.w));
+        hi4[i] = h;
+        lo4[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      }
+    }
+#endif
+    ZBT_TICK(4);  // convert
+#ifndef ZBT_SKIP_FENCE
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes (operands) -> visible to the tensor core's reads
+#endif
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    ZBT_TICK(5);  // fences + barrier
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = zbp_saddr(S.w[st]), a_lo = zbp_saddr(S.wlo[g & 1]);
+      const uint32_t koff = (uint32_t)(2 * ((t + W.rot) & 15)) * (ZBP_TE * 16);  // two 16-byte k-chunks per K = 8 step (this CTA's t-th k-tile)
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        const bool is_h = m >= 3;
+        const int gate = m % 3;
+        const uint32_t col = gate == 2 ? (is_h ? 96u : 64u) : (uint32_t)gate * 32u;
+        const uint32_t b_hi = zbp_saddr(is_h ? S.bh[0] : S.bx[0]) + koff, b_lo = zbp_saddr(is_h ? S.bh[1] : S.bx[1]) + koff;
+        const uint64_t dA_hi = zbt_desc(a_hi + m * (2 * ZBP_H * 16), ZBP_H * 16, 128), dA_lo = zbt_desc(a_lo + m * (2 * ZBP_H * 16), ZBP_H * 16, 128);
+        const uint64_t dB_hi = zbt_desc(b_hi, ZBP_TE * 16, 128), dB_lo = zbt_desc(b_lo, ZBP_TE * 16, 128);
+        const uint32_t first = (t == 0 && (!is_h || gate == 2)) ? 0u : 1u;  // r, z: W_h h accumulates onto W_i x
+#ifndef ZBT_SKIP_MMA
+        zbt_mma(tmem + col, dA_hi, dB_hi, idesc, first);
+        zbt_mma(tmem + col, dA_hi, dB_lo, idesc, 1u);
+        zbt_mma(tmem + col, dA_lo, dB_hi, idesc, 1u);
+#endif
+      }
+      zbt_commit(&S.mma_done[st]);
+      if (t == 15) zbt_commit(&S.layer_done);
+      if (g + ZBT_NST - 1 < G) {  // tile g + NST - 1 goes into the stage tile g - 1 used: free once that tile's MMAs have completed
+        if (g >= 1) zbp_mbar_wait(&S.mma_done[(g - 1) % ZBT_NST], (uint32_t)(((g - 1) / ZBT_NST) & 1));
+        W.issue(g + ZBT_NST - 1, S);
+      }
+    }
+    ZBT_TICK(6);  // thread 0: MMA issue + commit + refill
+    if (t == 15) {  // layer epilogue
+      zbp_mbar_wait(&S.layer_done, (uint32_t)(l & 1));
+      ZBT_TICK(7);  // wait: layer's MMAs done
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)e0;
+      float ar[8], az[8], ain[8], ahn[8];
+      zbt_ld8(taddr, ar); zbt_ld8(taddr + 32, az); zbt_ld8(taddr + 64, ain); zbt_ld8(taddr + 96, ahn);
+      const float* bl = A.gru_b + (size_t)l * 3 * ZBP_H;
+      const float br = bl[f], bz = bl[ZBP_H + f], bn = bl[2 * ZBP_H + f], bhn = A.gru_bn[(size_t)l * ZBP_H + f];
+      const bool last_layer = l == A.depth - 1;
+#pragma unroll
+      for (int e = 0; e < ZBP_EPT; e++) {
+        const float r = zbp_sigmoid(ar[e] + br), z = zbp_sigmoid(az[e] + bz);
+        const float nn = tanhf(fmaf(r, ahn[e] + bhn, ain[e] + bn));
+        const float hn = fmaf(z, hold[e] - nn, nn);
+        const int env = env0 + e0 + e;
+        if (env < n_envs) carry_out[((size_t)env * A.depth + l) * ZBP_H + f] = hn;
+        if (last_layer) xT[f][e0 + e] = hn;  // (bh: this layer's MMAs, its last readers, have completed)
+        else {
+          const float h = zbt_hi(hn);
+          S.bx[0][zbt_bidx(f, e0 + e)] = h;
+          S.bx[1][zbt_bidx(f, e0 + e)] = hn - h;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();  // TMEM read out, the next layer's input operand / xT complete
+      ZBT_TICK(8);  // epilogue
+    }
+  }
+  // ---- output_proj (CUDA cores), weights through the same ring (raw tiles in the hi half of a stage) ----
+  int g = W.t_gru;
+  float (*outS)[ZBP_OUT_MAX + 1] = reinterpret_cast<float (*)[ZBP_OUT_MAX + 1]>(&S.w[0][0]);
+  {
+    float acc[3][ZBP_EPT];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const int j = f + m * ZBP_H;
+      const float b = j < n_out ? A.out_b[j] : 0.f;
+#pragma unroll
+      for (int e = 0; e < ZBP_EPT; e++) acc[m][e] = b;
+    }
+    for (int t = 0; t < W.t_out; t++, g++) {
+      zbp_mbar_wait(&S.full[g % ZBT_NST], (uint32_t)((g / ZBT_NST) & 1));
+      const float* w = S.w[g % ZBT_NST];
+#pragma unroll 4
+      for (int kk = 0; kk < ZBP_KT_OUT; kk++) {
+        const int k = t * ZBP_KT_OUT + kk;
+        float wv[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) { const int j = f + m * ZBP_H; wv[m] = j < n_out ? w[kk * n_out + j] : 0.f; }
+        const float4 x0 = *reinterpret_cast<const float4*>(&xT[k][e0]), x1 = *reinterpret_cast<const float4*>(&xT[k][e0 + 4]);
+        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+          for (int e = 0; e < ZBP_EPT; e++) acc[m][e] = fmaf(wv[m], xv[e], acc[m][e]);
+      }
+      __syncthreads();  // tile g + NST - 1 goes into the stage tile g - 1 used (released by the previous barrier / layer_done)
+      if (tid == 0 && g + ZBT_NST - 1 < G) W.issue(g + ZBT_NST - 1, S);
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const int j = f + m * ZBP_H;
+      if (j < n_out)
+#pragma unroll
+        for (int e = 0; e < ZBP_EPT; e++) outS[e0 + e][j] = acc[m][e];  // (the ring is drained: every tile has been consumed)
+    }
+  }
+  __syncthreads();
+  zbp_head(A, outS, env0, n_envs, noise_u, noise_eps, action, dist);
+  ZBT_TICK(9);  // output_proj + head
+#ifdef ZBT_PROFILE
+  __syncthreads();
+  if (blockIdx.x == 0 && (tid == 0 || tid == 200) && dist) {
+    float* o = dist + (tid == 0 ? 0 : 16);
+    for (int i = 0; i < 10; i++) o[i] = (float)pf[i];
+    o[10] = (float)(clock64() - pstart);
+  }
+#endif
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)ZBT_TMEM_COLS) : "memory");
+}

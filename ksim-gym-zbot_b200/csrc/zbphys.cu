@@ -16,6 +16,7 @@
 #include "zb_kernel.cuh"
 #if ZB_TU == 0
 #include "zb_policy.cuh"
+#include "zb_policy_tc.cuh"
 #endif
 
 #define ZB_ABI_VERSION 5
@@ -945,17 +946,25 @@ int zb_actor_f32(void* stream, const ZbActor* A, const float* actor_obs, const f
   if ((noise_u == nullptr) != (noise_eps == nullptr)) return fail(ZB_EINVAL, "zb_actor_f32: noise_u and noise_eps come together (both NULL = mode)%s");
   if (A->n_in < 1 || A->n_in > ZB_ACTOR_MAX_IN || A->depth < 1 || A->num_mixtures < 1 || A->num_mixtures > ZB_ACTOR_MAX_MIXTURES)
     return fail(ZB_EUNSUP, "zb_actor_f32: n_in <= 128, depth >= 1, 1 <= num_mixtures <= 5 (hidden size 128 is built in)%s");
+  const bool tc = A->precision == ZB_ACTOR_TF32X3;
+  if (A->precision != ZB_ACTOR_FP32 && !tc) return fail(ZB_EINVAL, "zb_actor_f32: unknown ZbActor.precision%s");
+  if (tc && (!A->gru_w_tc || ((uintptr_t)A->gru_w_tc & 15) != 0)) return fail(ZB_EINVAL, "zb_actor_f32: ZB_ACTOR_TF32X3 needs gru_w_tc (16-byte aligned)%s");
+  if (tc && A->n_in > ZBT_MAX_IN) return fail(ZB_EUNSUP, "zb_actor_f32: ZB_ACTOR_TF32X3 is built for n_in <= 96%s");
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(ZB_ENODEV, "zb_actor_f32: no CUDA device%s");
   static std::atomic<unsigned long long> attr_set{0};
   if (dev < 64 && !((attr_set.load() >> dev) & 1ull)) {
     cudaError_t ce = cudaFuncSetAttribute(zb_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbpSmem));
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(zb_actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbtSmem));
     if (ce != cudaSuccess) return fail(ZB_ECUDA, "zb_actor_f32: cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(ce));
     attr_set.fetch_or(1ull << dev);
   }
-  if (n_envs == 0) return ZB_OK;  // (a call with n_envs = 0 only prepares the kernel: do one before capturing launches into a CUDA graph)
-  zb_actor_kernel<<<(n_envs + ZBP_TE - 1) / ZBP_TE, ZBP_THREADS, sizeof(ZbpSmem), (cudaStream_t)stream>>>(*A, actor_obs, carry_in, carry_out, carry_reset, noise_u,
-                                                                                                      noise_eps, action, dist, n_envs);
+  if (n_envs == 0) return ZB_OK;  // (a call with n_envs = 0 only prepares the kernels: do one before capturing launches into a CUDA graph)
+  const int grid = (n_envs + ZBP_TE - 1) / ZBP_TE;
+  if (tc)
+    zb_actor_tc_kernel<<<grid, ZBP_THREADS, sizeof(ZbtSmem), (cudaStream_t)stream>>>(*A, actor_obs, carry_in, carry_out, carry_reset, noise_u, noise_eps, action, dist, n_envs);
+  else
+    zb_actor_kernel<<<grid, ZBP_THREADS, sizeof(ZbpSmem), (cudaStream_t)stream>>>(*A, actor_obs, carry_in, carry_out, carry_reset, noise_u, noise_eps, action, dist, n_envs);
   return after_launch("zb_actor_f32 launch: %s");
 }
 int zb_sizeof_actor(void) { return (int)sizeof(ZbActor); }

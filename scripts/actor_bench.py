@@ -15,8 +15,8 @@ from ksim_gym_zbot_b200.policy import ActorParams, ActorPolicy  # noqa: E402
 
 out = {}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for n in (1024, 4096, 8192, 16384, 65536):
-    pol = ActorPolicy(ActorParams.random(0), n, "cuda:0")
+for prec, n in [(p_, n_) for p_ in (0, 1) for n_ in (1024, 4096, 8192, 16384, 65536)]:
+    pol = ActorPolicy(ActorParams.random(0), n, "cuda:0", precision=prec)
     obs = torch.randn((n, 50), device="cuda")
     for _ in range(5):
         pol(obs)
@@ -26,5 +26,5 @@ for n in (1024, 4096, 8192, 16384, 65536):
         a.record(); pol(obs); b.record()
     torch.cuda.synchronize()
     ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
-    out[n] = {"ms": round(ms, 4), "TFLOP/s": round(n * PO.flops_per_env() / (ms * 1e-3) / 1e12, 2), "actor_evals/s": round(n / (ms * 1e-3))}
+    out[("fp32 " if prec == 0 else "tf32x3-tcgen05 ") + str(n)] = {"ms": round(ms, 4), "TFLOP/s": round(n * PO.flops_per_env() / (ms * 1e-3) / 1e12, 2), "actor_evals/s": round(n / (ms * 1e-3))}
 print(json.dumps(out))

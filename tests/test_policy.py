@@ -78,6 +78,12 @@ def test_pack_layout_and_abi():
         assert pk["gru_whh_t"][2, k, g, f] == w[g * HIDDEN + f, k]
     assert pk["in_wt"].shape == (50, HIDDEN) and pk["in_wt"][3, 9] == prm.arrays["input_proj.weight"][9, 3]
     assert pk["out_wt"].shape == (HIDDEN, 300) and pk["gru_b"].shape == (3, 3, HIDDEN)
+    # tensor-core operand tiles: [layer][k-tile t][matrix m][k-chunk c][f][j] = W_m[f][8 t + 4 c + j], m = (W_ih r, z, n, W_hh r, z, n)
+    assert pk["gru_w_tc"].shape == (3, 16, 6, 2, HIDDEN, 4)
+    wi = prm.arrays["rnns.1.weight_ih"]
+    for (t, m, c, f, j) in ((0, 0, 0, 0, 0), (3, 2, 1, 17, 2), (15, 4, 1, 127, 3), (7, 5, 0, 64, 1)):
+        src = (wi if m < 3 else prm.arrays["rnns.1.weight_hh"])[(m % 3) * HIDDEN + f, 8 * t + 4 * c + j]
+        assert pk["gru_w_tc"][1, t, m, c, f, j] == src
     lib = ctypes.CDLL(ksim_gym_zbot_b200.engine.LIB_PATH)
     assert lib.zb_sizeof_actor() == ctypes.sizeof(ZbActor)
     assert hasattr(lib, "zb_actor_f32")
@@ -89,15 +95,18 @@ def test_pack_layout_and_abi():
 # GPU: kernel vs oracle
 # ---------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "tf32x3-tcgen05"])
 @pytest.mark.parametrize("n,depth,mix", [(1, 5, 5), (33, 5, 5), (1000, 5, 5), (4096, 5, 5), (77, 2, 3), (40, 1, 1)])
-def test_actor_kernel_matches_oracle(n, depth, mix):
+def test_actor_kernel_matches_oracle(n, depth, mix, precision):
+    """Both GRU paths — fp32 on the CUDA cores, 3xTF32 on the tcgen05 tensor cores — against the fp64 restatement, with the fp32
+    restatement's own deviation as the yard-stick (the 3xTF32 products keep ~21 mantissa bits per factor: same bound)."""
     import torch
     import zb_policy_oracle as PO
     from ksim_gym_zbot_b200.policy import ActorPolicy
 
     prm = ActorParams.random(seed=11 + depth, depth=depth, num_mixtures=mix)
     obs, carry, u, eps = _inputs(n, depth, 100 + n)
-    pol = ActorPolicy(prm, n, "cuda:0")
+    pol = ActorPolicy(prm, n, "cuda:0", precision=precision)
     pol.carry.copy_(torch.tensor(carry))
     dist = torch.zeros((n, 3, M.NU, mix), device="cuda:0")
     act = torch.zeros((n, M.NU), device="cuda:0")
@@ -127,7 +136,8 @@ def test_actor_kernel_matches_oracle(n, depth, mix):
 
 
 @pytest.mark.gpu
-def test_actor_recurrence_reset_and_errors():
+@pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "tf32x3-tcgen05"])
+def test_actor_recurrence_reset_and_errors(precision):
     import torch
     import zb_policy_oracle as PO
     from ksim_gym_zbot_b200.engine import ZB_EINVAL, ZB_EUNSUP, ZbError
@@ -135,7 +145,7 @@ def test_actor_recurrence_reset_and_errors():
 
     n, T = 96, 12
     prm = ActorParams.random(seed=2)
-    pol = ActorPolicy(prm, n, "cuda:0")
+    pol = ActorPolicy(prm, n, "cuda:0", precision=precision)
     g = np.random.default_rng(4)
     obs = g.normal(0, 1, (T, n, 50)).astype(np.float32)
     done = (g.uniform(size=(T, n)) < 0.1).astype(np.uint8)
