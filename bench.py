@@ -667,7 +667,9 @@ def main():
         "other_workloads": others,
     }
     if rollout_actor is not None:
-        rollout_actor["actor"]["fp32_frac"] = rollout_actor["actor"]["achieved_tflops"] / fp32_peak if fp32_peak else None
+        a_ = rollout_actor["actor"]
+        a_["achieved_tflops_note"] = "useful fp32-equivalent FLOPs (2 x MACs of the three matrix stages) per second; the 3xTF32 path executes 3x the tensor-core MACs"
+        a_["fp32_cuda_core_kernel_frac_of_fp32_peak"] = (spec.n_env * a_["flops_per_env"] / (a_["kernel_ms_fp32_cuda_cores"] * 1e-3) / 1e12) / fp32_peak if fp32_peak else None
         line["rollout_actor"] = rollout_actor
     print(json.dumps(line))
     if world > 1:
@@ -696,7 +698,10 @@ def measure_rollout_actor(a, spec: "Spec", model, rank: int, world: int, local: 
     n = spec.n_env
     eng = ZbotCudaEngine(model, n, device=local, opts=spec.opts(), ctrl_dt=spec.ctrl_dt, seed=rank_seed(spec.seed, rank) + 5)
     ro = Rollout(eng, T)
-    pol = ActorPolicy(ActorParams.random(seed=spec.seed), n, dev)
+    from ksim_gym_zbot_b200.policy import PRECISION_FP32, PRECISION_TF32X3
+
+    prm = ActorParams.random(seed=spec.seed)
+    pol = ActorPolicy(prm, n, dev, precision=PRECISION_TF32X3)  # GRU stack on the tcgen05 tensor cores (3xTF32: fp32-level accuracy)
     launches0 = eng.launch_count()
     ro.reset()
     ro.unroll_actor(pol, argmax=False)  # capture + first replay (warm-up chunk)
@@ -715,21 +720,28 @@ def measure_rollout_actor(a, spec: "Spec", model, rank: int, world: int, local: 
     ms = e0.elapsed_time(e1)
     value, ms_max = aggregate_throughput(n * spec.S * T * chunks, ms, dev)
     resets = float((ro.traj.done != 0).sum().item()) / T
-    # the actor kernel alone
+    # the actor kernel alone, both precisions (L2 flushed between launches)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(20)]
-    for x, y in ev:
-        flush.zero_()
-        x.record(); pol.enqueue(ro.traj.actor_obs[0], pol.action); y.record()
-    torch.cuda.synchronize()
-    actor_ms = float(np.median([x.elapsed_time(y) for x, y in ev]))
+    actor_ms = {}
+    for name, pr in (("tf32x3_tcgen05", PRECISION_TF32X3), ("fp32_cuda_cores", PRECISION_FP32)):
+        p2 = pol if pr == PRECISION_TF32X3 else ActorPolicy(prm, n, dev, precision=pr)
+        for _ in range(3):
+            p2.enqueue(ro.traj.actor_obs[0], p2.action)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(20)]
+        for x, y in ev:
+            flush.zero_()
+            x.record(); p2.enqueue(ro.traj.actor_obs[0], p2.action); y.record()
+        torch.cuda.synchronize()
+        actor_ms[name] = float(np.median([x.elapsed_time(y) for x, y in ev]))
     eng.close()
     return {"workload": f"c2 {n} envs/GPU S={spec.S} + actor in the loop", "value": value, "unit": UNIT, "chunks": chunks, "chunk_steps": T,
             "ms_per_ctrl_step": ms_max / (T * chunks), "launches_per_ctrl_step": 2, "graph": "one CUDA graph per chunk (2T launches + 1 copy)",
             "actions": "sampled from the mixture (pre-sampled U / N numbers per chunk), random-init weights", "resets_per_step": resets,
             "trajectory_bytes_per_env_ctrl_step": ro.traj.bytes_per_env_step(),
-            "actor": {"kernel_ms": actor_ms, "flops_per_env": PO.flops_per_env(), "achieved_tflops": n * PO.flops_per_env() / (actor_ms * 1e-3) / 1e12,
-                      "dtype": "f32 (CUDA cores)", "ctas": (n + 31) // 32}}
+            "actor": {"kernel_ms": actor_ms["tf32x3_tcgen05"], "kernel_ms_fp32_cuda_cores": actor_ms["fp32_cuda_cores"], "flops_per_env": PO.flops_per_env(),
+                      "achieved_tflops": n * PO.flops_per_env() / (actor_ms["tf32x3_tcgen05"] * 1e-3) / 1e12,
+                      "dtype": "GRU stack: 3xTF32 tcgen05.mma (fp32-level accuracy, accumulators in TMEM); input / output projections: f32 CUDA cores",
+                      "ctas": (n + 31) // 32}}
 
 def run_reference(a, spec: Spec, model, world: int):
     """The reference arm: the reference's algorithm for this path on the host cores (CpuArm), full per-GPU batch, K timed control steps."""

@@ -3,9 +3,11 @@
 //
 // Per CTA: 32 environments (the MMA N dimension), the 128 hidden units of a gate are the M dimension:
 //     D_gate[128 f x 32 env] (+)= W_gate[128 f x 8 k] . X^T[8 k x 32 env]            tcgen05.mma.cta_group::1.kind::tf32, M128 N32 K8
-// Four fp32 accumulators live in 128 TMEM columns: r (W_ir x + W_hr h), z, i_n (W_in x), h_n (W_hn h).  Every product is issued three
-// times — hi.hi + hi.lo + lo.hi with v_hi = v & 0xffffe000 (exactly representable in TF32), v_lo = v - v_hi — which recovers ~21 of
-// the 24 mantissa bits of each factor (the tensor core accumulates in fp32).  Per layer: 6 gate matrices x 16 K-steps x 3 = 288 MMAs,
+// Four fp32 accumulators live in TMEM: r (W_ir x + W_hr h), z, i_n (W_in x), h_n (W_hn h).  Every product is formed as
+// hi.hi + hi.lo + lo.hi with v_hi = v & 0xffffe000 (exactly representable in TF32), v_lo = v - v_hi — which recovers ~21 of the 24
+// mantissa bits of each factor (the tensor core accumulates in fp32).  The activation operand holds [hi rows | lo rows], so ONE N = 64
+// MMA gives A_hi.B_hi and A_hi.B_lo (in two column halves of the accumulator, summed in the epilogue: the 4 KB weight tile is read
+// once for both) and one N = 32 MMA adds A_lo.B_hi.  Per layer: 6 gate matrices x 16 K-steps x 2 = 192 MMAs, 256 TMEM columns,
 // issued by ONE thread; the other 511 threads feed it:
 //   * weights: host-packed in the UMMA canonical K-major no-swizzle layout (8-row x 16-byte core matrices; ZbActor.gru_w_tc
 //     [layer][k-tile 16][matrix 6][k-chunk 2][f 128][4]) so that a plain TMA bulk copy of 24 KB lands a ready operand tile in shared
@@ -20,25 +22,25 @@
 #include "zb_policy.cuh"
 
 #define ZBT_NST 4
-#ifndef ZBT_ROTATE
-#define ZBT_ROTATE 0 /* measured: no effect (the stream is not L2-slice-bound), and a fixed order keeps results independent of the CTA index */
-#endif
 #define ZBT_TILE_FLOATS (6 * 2 * ZBP_H * 4) /* 24 KB: [matrix 6][k-chunk 2][f 128][4 k] */
-#define ZBT_B_FLOATS (32 * ZBP_TE * 4)      /* 16 KB: [k-chunk 32][env 32][4 k] */
+#define ZBT_B_FLOATS (32 * 2 * ZBP_TE * 4)  /* 32 KB: [k-chunk 32][row 64 = hi of env 0..31 | lo of env 0..31][4 k] */
 #define ZBT_MAX_IN 96
-#define ZBT_TMEM_COLS 128
+#define ZBT_TMEM_COLS 512 /* 4 accumulators x 64 columns + 2 x 48 columns of weight lo parts (A operand of the lo.hi MMAs) */
+#define ZBT_TMEM_LO 256  /* first column of the lo parts: [slot 2][matrix 6][8 k] */
+#define ZBT_CONV_WARPS 12 /* warps 1..12 split the weight tiles (6144 floats = 12 x 32 threads x 4 float4); warp 0 issues the MMAs */
+static_assert(ZBT_TILE_FLOATS % (4 * ZBT_CONV_WARPS * 32) == 0, "converter split");
 
 struct ZbtSmem {
   float w[ZBT_NST][ZBT_TILE_FLOATS];     // weight ring: TMA destination, masked to its TF32 hi part in place; the end of the kernel re-uses it for `out`
-  float wlo[2][ZBT_TILE_FLOATS];         // lo parts of the tile being multiplied and of the next one (input_proj: its weights land here)
-  float bx[2][ZBT_B_FLOATS];             // layer input, hi / lo
-  float bh[2][ZBT_B_FLOATS];             // carry of the layer, hi / lo (input_proj: observation scratch; output_proj: its input, k-major)
-  uint64_t full[ZBT_NST], mma_done[ZBT_NST], layer_done, in_full;
+  float wlo[2][ZBT_TILE_FLOATS];         // input_proj: its weights land here (the lo parts of the GRU weight tiles live in TMEM)
+  float bx[ZBT_B_FLOATS];                // layer input: hi rows | lo rows (one N = 64 operand, or N = 32 = the hi rows alone)
+  float bh[ZBT_B_FLOATS];                // carry of the layer, same layout (input_proj: observation scratch; output_proj: its input, k-major)
+  uint64_t full[ZBT_NST], conv[ZBT_NST], mma_done[ZBT_NST], layer_done, in_full;
   uint32_t tmem_base;
 };
 static_assert(sizeof(ZbtSmem) <= 232448, "ZbtSmem exceeds the 227 KB of shared memory a CTA can have");
 static_assert(ZBP_TE * (ZBP_OUT_MAX + 1) <= ZBT_NST * ZBT_TILE_FLOATS, "`out` must fit the weight ring it aliases");
-static_assert(ZBP_H * ZBP_LD <= 2 * ZBT_B_FLOATS && ZBT_MAX_IN * ZBP_H <= 2 * ZBT_TILE_FLOATS, "aliased regions");
+static_assert(ZBP_H * ZBP_LD <= ZBT_B_FLOATS && ZBT_MAX_IN * ZBP_H <= 2 * ZBT_TILE_FLOATS && ZBT_MAX_IN * ZBP_LD <= ZBT_B_FLOATS, "aliased regions");
 
 static __device__ __forceinline__ uint64_t zbt_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: start address, leading (K-chunk) and stride (8-row group) byte offsets in
@@ -55,8 +57,32 @@ static __device__ __forceinline__ void zbt_mma(uint32_t d_tmem, uint64_t da, uin
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
+static __device__ __forceinline__ void zbt_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {  // A from TMEM
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+static __device__ __forceinline__ void zbt_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 static __device__ __forceinline__ void zbt_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(zbp_saddr(bar)) : "memory");
+}
+static __device__ __forceinline__ void zbp_mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(zbp_saddr(b)) : "memory");
+}
+static __device__ __forceinline__ bool zbt_elect() {  // one lane of a converged warp
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p));
+  return p != 0;
 }
 static __device__ __forceinline__ void zbt_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
@@ -67,22 +93,19 @@ static __device__ __forceinline__ void zbt_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
-static __device__ __forceinline__ int zbt_bidx(int k, int env) { return (k >> 2) * (ZBP_TE * 4) + env * 4 + (k & 3); }
+static __device__ __forceinline__ int zbt_bidx(int k, int env, int lo) { return (k >> 2) * (2 * ZBP_TE * 4) + (lo * ZBP_TE + env) * 4 + (k & 3); }
 static __device__ __forceinline__ float zbt_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 // tiles of the ring in stream order: T_gru GRU tiles ([layer][k-tile] of gru_w_tc, 24 KB each), then output_proj rows (16 k-rows each)
 struct ZbtStream {
   int t_gru, t_out, n_out;
   const float *gru, *out_wt;
-  int rot;  // k-tile rotation of this CTA: the CTAs of a launch walk the 16 k-tiles of a layer from 16 different starting points, so that
-            // they do not all pull the same 24 KB from the same L2 slices at the same moment
   __device__ void issue(int g, ZbtSmem& S) const {  // one thread
     const int st = g % ZBT_NST;
     uint64_t* b = &S.full[st];
     if (g < t_gru) {
-      const int gg = (g & ~15) | ((g + rot) & 15);
       zbp_mbar_expect(b, ZBT_TILE_FLOATS * 4);
-      zbp_bulk_load(S.w[st], gru + (size_t)gg * ZBT_TILE_FLOATS, ZBT_TILE_FLOATS * 4, b);
+      zbp_bulk_load(S.w[st], gru + (size_t)g * ZBT_TILE_FLOATS, ZBT_TILE_FLOATS * 4, b);
     } else {
       const int k0 = (g - t_gru) * ZBP_KT_OUT;
       const uint32_t bytes = (uint32_t)ZBP_KT_OUT * n_out * 4;
@@ -101,14 +124,15 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
   const int env0 = blockIdx.x * ZBP_TE;
   const int n_in = A.n_in, n_out = ZB_NU * 3 * A.num_mixtures;
   ZbtStream W;
-  W.rot = ZBT_ROTATE ? (int)(blockIdx.x & 15) : 0; W.t_gru = A.depth * (ZBP_H / 8); W.t_out = ZBP_H / ZBP_KT_OUT; W.n_out = n_out; W.gru = A.gru_w_tc; W.out_wt = A.out_wt;
+  W.t_gru = A.depth * (ZBP_H / 8); W.t_out = ZBP_H / ZBP_KT_OUT; W.n_out = n_out; W.gru = A.gru_w_tc; W.out_wt = A.out_wt;
   const int G = W.t_gru + W.t_out;
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 32, M = 128
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ZBP_TE >> 3) << 17) | ((uint32_t)(ZBP_H >> 4) << 24);
+  const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ZBP_TE >> 3) << 17) | ((uint32_t)(ZBP_H >> 4) << 24);
+  const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * ZBP_TE) >> 3) << 17) | ((uint32_t)(ZBP_H >> 4) << 24);
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < ZBT_NST; s++) { zbp_mbar_init(&S.full[s], 1); zbp_mbar_init(&S.mma_done[s], 1); }
+    for (int s = 0; s < ZBT_NST; s++) { zbp_mbar_init(&S.full[s], 1); zbp_mbar_init(&S.mma_done[s], 1); zbp_mbar_init(&S.conv[s], ZBT_CONV_WARPS); }
     zbp_mbar_init(&S.layer_done, 1);
     zbp_mbar_init(&S.in_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -122,6 +146,8 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = S.tmem_base;
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);      // (provably warp-uniform copies for the issuing warp)
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   if (tid == 0) {
     const uint32_t bytes = (uint32_t)n_in * ZBP_H * 4;  // input_proj weights, whole, into the two lo buffers (48 KB, contiguous)
     zbp_mbar_expect(&S.in_full, bytes);
@@ -129,7 +155,7 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
     for (int g0 = 0; g0 < ZBT_NST - 1; g0++) W.issue(g0, S);
   }
   // ---- observations of the tile, transposed ([k][e], CUDA-core layout) into the bh region ----
-  float (*obsT)[ZBP_LD] = reinterpret_cast<float (*)[ZBP_LD]>(&S.bh[0][0]);
+  float (*obsT)[ZBP_LD] = reinterpret_cast<float (*)[ZBP_LD]>(&S.bh[0]);
   for (int i = tid; i < ZBP_TE * n_in; i += ZBP_THREADS) {
     const int e = i / n_in, k = i - e * n_in;
     obsT[k][e] = (env0 + e < n_envs) ? obs[(size_t)(env0 + e) * n_in + k] : 0.f;
@@ -152,8 +178,8 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
 #pragma unroll
     for (int e = 0; e < ZBP_EPT; e++) {
       const float h = zbt_hi(acc[e]);
-      S.bx[0][zbt_bidx(f, e0 + e)] = h;
-      S.bx[1][zbt_bidx(f, e0 + e)] = acc[e] - h;
+      S.bx[zbt_bidx(f, e0 + e, 0)] = h;
+      S.bx[zbt_bidx(f, e0 + e, 1)] = acc[e] - h;
     }
   }
   __syncthreads();  // the lo buffers and the observation scratch are free
@@ -167,7 +193,7 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
 #endif
   ZBT_TICK(0);  // setup + input_proj
   // ---- GRU stack on the tensor cores ----
-  float (*xT)[ZBP_LD] = reinterpret_cast<float (*)[ZBP_LD]>(&S.bh[0][0]);
+  float (*xT)[ZBP_LD] = reinterpret_cast<float (*)[ZBP_LD]>(&S.bh[0]);
   float hold[ZBP_EPT];
   for (int g = 0; g < W.t_gru; g++) {
     const int l = g >> 4, t = g & 15, st = g % ZBT_NST;
@@ -178,61 +204,79 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
         const bool live = env < n_envs && !(carry_reset && carry_reset[env]);
         hold[e] = live ? carry_in[((size_t)env * A.depth + l) * ZBP_H + f] : 0.f;
         const float h = zbt_hi(hold[e]);
-        S.bh[0][zbt_bidx(f, e0 + e)] = h;
-        S.bh[1][zbt_bidx(f, e0 + e)] = hold[e] - h;
+        S.bh[zbt_bidx(f, e0 + e, 0)] = h;
+        S.bh[zbt_bidx(f, e0 + e, 1)] = hold[e] - h;
       }
+    }
+    if (t == 0) {  // the layer's activation operands (bx: previous epilogue / input_proj, bh: just written) -> visible to the tensor core
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
     }
     ZBT_TICK(1);  // layer prologue / loop overhead
-    zbp_mbar_wait(&S.full[st], (uint32_t)((g / ZBT_NST) & 1));
-    ZBT_TICK(2);  // wait: tile landed
-    // the lo buffer of this tile was last read by the MMAs of tile g - 2
-    if (g >= 2) zbp_mbar_wait(&S.mma_done[(g - 2) % ZBT_NST], (uint32_t)(((g - 2) / ZBT_NST) & 1));
-    ZBT_TICK(3);  // wait: MMAs of tile g - 2
-#ifndef ZBT_SKIP_CONVERT
-    {  // split the landed tile: hi in place, lo into the tile's lo buffer (12 floats per thread)
-      float4* hi4 = reinterpret_cast<float4*>(S.w[st]) + tid * 3;
-      float4* lo4 = reinterpret_cast<float4*>(S.wlo[g & 1]) + tid * 3;
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const float4 v = hi4[i];
-        const float4 h = make_float4(zbt_hi(v.x), zbt_hi(v.y), zbt_hi(v.z), zbt_hi(v.w));
-        hi4[i] = h;
-        lo4[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-      }
-    }
-#endif
-    ZBT_TICK(4);  // convert
-#ifndef ZBT_SKIP_FENCE
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes (operands) -> visible to the tensor core's reads
-#endif
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    ZBT_TICK(5);  // fences + barrier
-    if (tid == 0) {
+    if (warp_u == 0) {
+      // ===== issuing warp: waits for the tile's hi / lo operands, issues its 12 MMAs (one elected lane; descriptors are formed
+      // warp-uniformly, in uniform registers), frees stages, keeps the TMA stream going =====
+      zbp_mbar_wait(&S.conv[st], (uint32_t)((g / ZBT_NST) & 1));
+      ZBT_TICK(2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = zbp_saddr(S.w[st]), a_lo = zbp_saddr(S.wlo[g & 1]);
-      const uint32_t koff = (uint32_t)(2 * ((t + W.rot) & 15)) * (ZBP_TE * 16);  // two 16-byte k-chunks per K = 8 step (this CTA's t-th k-tile)
+      const uint32_t a_hi = zbp_saddr(S.w[st]);
+      const uint32_t koff = (uint32_t)(2 * t) * (2 * ZBP_TE * 16);  // two 16-byte k-chunks per K = 8 step
+      const uint64_t dBx = zbt_desc(zbp_saddr(S.bx) + koff, 2 * ZBP_TE * 16, 128), dBh = zbt_desc(zbp_saddr(S.bh) + koff, 2 * ZBP_TE * 16, 128);
+      const uint64_t dA_hi0 = zbt_desc(a_hi, ZBP_H * 16, 128);
+      const uint32_t acc0 = t == 0 ? 0u : 1u;
+      const bool lead = zbt_elect();
+      if (lead) {
 #pragma unroll
-      for (int m = 0; m < 6; m++) {
-        const bool is_h = m >= 3;
-        const int gate = m % 3;
-        const uint32_t col = gate == 2 ? (is_h ? 96u : 64u) : (uint32_t)gate * 32u;
-        const uint32_t b_hi = zbp_saddr(is_h ? S.bh[0] : S.bx[0]) + koff, b_lo = zbp_saddr(is_h ? S.bh[1] : S.bx[1]) + koff;
-        const uint64_t dA_hi = zbt_desc(a_hi + m * (2 * ZBP_H * 16), ZBP_H * 16, 128), dA_lo = zbt_desc(a_lo + m * (2 * ZBP_H * 16), ZBP_H * 16, 128);
-        const uint64_t dB_hi = zbt_desc(b_hi, ZBP_TE * 16, 128), dB_lo = zbt_desc(b_lo, ZBP_TE * 16, 128);
-        const uint32_t first = (t == 0 && (!is_h || gate == 2)) ? 0u : 1u;  // r, z: W_h h accumulates onto W_i x
+        for (int m = 0; m < 6; m++) {
+          const bool is_h = m >= 3;
+          const int gate = m % 3;
+          const uint32_t col = (gate == 2 ? (is_h ? 3u : 2u) : (uint32_t)gate) * 64u;  // accumulator: columns [col, col+32) += hi.hi and lo.hi, [col+32, col+64) += hi.lo
+          const uint64_t dstep = (uint64_t)(m * ((2 * ZBP_H * 16) >> 4));         // next matrix of the tile: + 4 KB in the address field
+          const uint32_t first = (!is_h || gate == 2) ? acc0 : 1u;                   // r, z: W_h h accumulates onto W_i x
 #ifndef ZBT_SKIP_MMA
-        zbt_mma(tmem + col, dA_hi, dB_hi, idesc, first);
-        zbt_mma(tmem + col, dA_hi, dB_lo, idesc, 1u);
-        zbt_mma(tmem + col, dA_lo, dB_hi, idesc, 1u);
+          zbt_mma(tmem_u + col, dA_hi0 + dstep, is_h ? dBh : dBx, idesc64, first);  // A_hi . [B_hi | B_lo]  (N = 64: the weight tile is read once for both)
+          zbt_mma_ts(tmem_u + col, tmem_u + ZBT_TMEM_LO + (uint32_t)((g & 1) * 48 + m * 8), is_h ? dBh : dBx, idesc32, 1u);  // A_lo (TMEM) . B_hi  (N = 32: the hi rows)
 #endif
+        }
+        zbt_commit(&S.mma_done[st]);
+        if (t == 15) zbt_commit(&S.layer_done);
+        if (g + ZBT_NST - 1 < G) {  // tile g + NST - 1 goes into the stage tile g - 1 used: free once that tile's MMAs have completed
+          if (g >= 1) zbp_mbar_wait(&S.mma_done[(g - 1) % ZBT_NST], (uint32_t)(((g - 1) / ZBT_NST) & 1));
+          W.issue(g + ZBT_NST - 1, S);
+        }
       }
-      zbt_commit(&S.mma_done[st]);
-      if (t == 15) zbt_commit(&S.layer_done);
-      if (g + ZBT_NST - 1 < G) {  // tile g + NST - 1 goes into the stage tile g - 1 used: free once that tile's MMAs have completed
-        if (g >= 1) zbp_mbar_wait(&S.mma_done[(g - 1) % ZBT_NST], (uint32_t)(((g - 1) / ZBT_NST) & 1));
-        W.issue(g + ZBT_NST - 1, S);
+      __syncwarp();
+    } else if (warp_u <= ZBT_CONV_WARPS) {
+      // ===== converter warps: split the landed tile into its TF32 hi part (in place) and the remainder (the tile's lo buffer, last read by
+      // the MMAs of tile g - 2), one tile ahead of the MMAs =====
+      zbp_mbar_wait(&S.full[st], (uint32_t)((g / ZBT_NST) & 1));
+      ZBT_TICK(2);  // wait: tile landed
+      if (g >= 2) zbp_mbar_wait(&S.mma_done[(g - 2) % ZBT_NST], (uint32_t)(((g - 2) / ZBT_NST) & 1));
+      ZBT_TICK(3);  // wait: MMAs of tile g - 2
+#ifndef ZBT_SKIP_CONVERT
+      {  // thread = (row f of its warp's TMEM lane quadrant, two of the six matrices): 8 k values per matrix -> lo parts -> 8 TMEM columns
+        // converter warps 1..12: quadrant = warp & 3 (a warp can only store to the TMEM lanes of its own quadrant); the three warps of a
+        // quadrant (1-4, 5-8, 9-12) take matrices {0,1}, {2,3}, {4,5}
+        const int q = warp & 3, fr = 32 * q + (tid & 31), grp = (warp - 1) >> 2;
+#pragma unroll
+        for (int mm = 0; mm < 2; mm++) {
+          const int m = 2 * grp + mm;
+          const float4 v0 = *reinterpret_cast<const float4*>(S.w[st] + (m * 2 + 0) * (ZBP_H * 4) + fr * 4);
+          const float4 v1 = *reinterpret_cast<const float4*>(S.w[st] + (m * 2 + 1) * (ZBP_H * 4) + fr * 4);
+          const float lo[8] = {v0.x - zbt_hi(v0.x), v0.y - zbt_hi(v0.y), v0.z - zbt_hi(v0.z), v0.w - zbt_hi(v0.w),
+                               v1.x - zbt_hi(v1.x), v1.y - zbt_hi(v1.y), v1.z - zbt_hi(v1.z), v1.w - zbt_hi(v1.w)};
+          zbt_st8(tmem + ((uint32_t)(32 * q) << 16) + ZBT_TMEM_LO + (uint32_t)((g & 1) * 48 + m * 8), lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
+#endif
+      ZBT_TICK(4);  // convert
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes (operands) -> visible to the tensor core's reads
+      __syncwarp();
+      if ((tid & 31) == 0) zbp_mbar_arrive(&S.conv[st]);
+      ZBT_TICK(5);
     }
     ZBT_TICK(6);  // thread 0: MMA issue + commit + refill
     if (t == 15) {  // layer epilogue
@@ -241,7 +285,21 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)e0;
       float ar[8], az[8], ain[8], ahn[8];
-      zbt_ld8(taddr, ar); zbt_ld8(taddr + 32, az); zbt_ld8(taddr + 64, ain); zbt_ld8(taddr + 96, ahn);
+      {
+        float t2[8];
+        zbt_ld8(taddr, ar); zbt_ld8(taddr + 32, t2);
+#pragma unroll
+        for (int e = 0; e < 8; e++) ar[e] += t2[e];
+        zbt_ld8(taddr + 64, az); zbt_ld8(taddr + 96, t2);
+#pragma unroll
+        for (int e = 0; e < 8; e++) az[e] += t2[e];
+        zbt_ld8(taddr + 128, ain); zbt_ld8(taddr + 160, t2);
+#pragma unroll
+        for (int e = 0; e < 8; e++) ain[e] += t2[e];
+        zbt_ld8(taddr + 192, ahn); zbt_ld8(taddr + 224, t2);
+#pragma unroll
+        for (int e = 0; e < 8; e++) ahn[e] += t2[e];
+      }
       const float* bl = A.gru_b + (size_t)l * 3 * ZBP_H;
       const float br = bl[f], bz = bl[ZBP_H + f], bn = bl[2 * ZBP_H + f], bhn = A.gru_bn[(size_t)l * ZBP_H + f];
       const bool last_layer = l == A.depth - 1;
@@ -255,8 +313,8 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
         if (last_layer) xT[f][e0 + e] = hn;  // (bh: this layer's MMAs, its last readers, have completed)
         else {
           const float h = zbt_hi(hn);
-          S.bx[0][zbt_bidx(f, e0 + e)] = h;
-          S.bx[1][zbt_bidx(f, e0 + e)] = hn - h;
+          S.bx[zbt_bidx(f, e0 + e, 0)] = h;
+          S.bx[zbt_bidx(f, e0 + e, 1)] = hn - h;
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -13,7 +13,7 @@ g = np.random.default_rng(0)
 obs = g.normal(0, 1, (n, 50)).astype(np.float32); carry = g.uniform(-1, 1, (n, 5, 128)).astype(np.float32)
 mean, std, logits, nc = PO.actor_forward(prm.oracle_dict(), obs, carry)
 for prec in (0, 1):
-    pol = ActorPolicy(prm, n, "cuda:0", precision=prec)
+    pol = ActorPolicy(prm, n, "cuda:0", precision=prec, lib_path=os.environ.get("ZBPHYS_LIB_PROBE"))
     pol.carry.copy_(torch.tensor(carry))
     dist = torch.zeros((n, 3, 20, 5), device="cuda")
     pol.enqueue(torch.tensor(obs, device="cuda"), pol.action, dist_out=dist)
