@@ -412,6 +412,8 @@ typedef struct ZbActor {
   const float *in_wt, *in_b, *gru_wih_t, *gru_whh_t, *gru_b, *gru_bn, *out_wt, *out_b, *mean_bias;
   const float* gru_w_tc; /* ZB_ACTOR_TF32X3 only: [depth][16 k-tiles][6 matrices: W_ih r,z,n, W_hh r,z,n][2 k-chunks][128 f][4 k] =
                             W_m[f][8 t + 4 c + j] — the tcgen05 K-major no-swizzle operand layout, one 24 KB TMA bulk copy per k-tile */
+  const float* out_w_tc; /* ZB_ACTOR_TF32X3 only: output_proj in the same layout, [16 k-tiles][3 m-tiles][2 k-chunks][128 rows][4 k] =
+                            output_proj.weight[128 mt + row][8 t + 4 c + j], rows beyond n_out zero (12 KB per k-tile) */
 } ZbActor;
 #define ZB_ACTOR_FP32 0
 #define ZB_ACTOR_TF32X3 1
@@ -428,7 +430,8 @@ typedef struct ZbActor {
  *   dist        [N, 3, 20, M] or NULL  out: means (incl. JOINT_BIASES), stds, logits as handed to ksim.MixtureOfGaussians (train.py:965)
  * One CTA per 32 environments.  precision = ZB_ACTOR_FP32: everything in fp32 on the CUDA cores (matches a CPU float32 evaluation to
  * rounding).  ZB_ACTOR_TF32X3: the GRU stack (92 % of the FLOPs) on the tcgen05 tensor cores with every product issued as
- * hi.hi + hi.lo + lo.hi of TF32 halves (fp32-level accuracy, ~1e-6 relative), accumulators in TMEM; needs gru_w_tc and n_in <= 96.
+ * hi.hi + hi.lo + lo.hi of TF32 halves (fp32-level accuracy, ~1e-6 relative), accumulators in TMEM — the GRU stack and output_proj;
+ * needs gru_w_tc, out_w_tc and n_in <= 96.
  * Errors: ZB_EINVAL (NULL / sizes / alignment), ZB_EUNSUP (limits above), ZB_ECUDA. */
 int zb_actor_f32(void* cuda_stream, const ZbActor* actor, const float* actor_obs, const float* carry_in, float* carry_out,
                  const uint8_t* carry_reset, const float* noise_u, const float* noise_eps, float* action, float* dist, int n_envs);

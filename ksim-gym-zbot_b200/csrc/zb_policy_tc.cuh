@@ -23,7 +23,9 @@
 
 #define ZBT_NST 4
 #define ZBT_TILE_FLOATS (6 * 2 * ZBP_H * 4) /* 24 KB: [matrix 6][k-chunk 2][f 128][4 k] */
-#define ZBT_B_FLOATS (32 * 2 * ZBP_TE * 4)  /* 32 KB: [k-chunk 32][row 64 = hi of env 0..31 | lo of env 0..31][4 k] */
+#define ZBT_B_CHUNK (2 * ZBP_TE * 4 + 4)     /* floats between k-chunks of an activation operand: 64 rows x 4 k + 16 bytes of padding, so that the 32
+                                               hidden units of a warp (8 chunks x 4 k) write to 32 different banks (the chunk stride is the descriptor's LBO) */
+#define ZBT_B_FLOATS (32 * ZBT_B_CHUNK)      /* [k-chunk 32][row 64 = hi of env 0..31 | lo of env 0..31][4 k] */
 #define ZBT_MAX_IN 96
 #define ZBT_TMEM_COLS 512 /* 4 accumulators x 64 columns + 2 x 48 columns of weight lo parts (A operand of the lo.hi MMAs) */
 #define ZBT_TMEM_LO 256  /* first column of the lo parts: [slot 2][matrix 6][8 k] */
@@ -33,8 +35,8 @@ static_assert(ZBT_TILE_FLOATS % (4 * ZBT_CONV_WARPS * 32) == 0, "converter split
 struct ZbtSmem {
   float w[ZBT_NST][ZBT_TILE_FLOATS];     // weight ring: TMA destination, masked to its TF32 hi part in place; the end of the kernel re-uses it for `out`
   float wlo[2][ZBT_TILE_FLOATS];         // input_proj: its weights land here (the lo parts of the GRU weight tiles live in TMEM)
-  float bx[ZBT_B_FLOATS];                // layer input: hi rows | lo rows (one N = 64 operand, or N = 32 = the hi rows alone)
-  float bh[ZBT_B_FLOATS];                // carry of the layer, same layout (input_proj: observation scratch; output_proj: its input, k-major)
+  __align__(16) float bx[ZBT_B_FLOATS];  // layer input: hi rows | lo rows (one N = 64 operand, or N = 32 = the hi rows alone)
+  __align__(16) float bh[ZBT_B_FLOATS];  // carry of the layer, same layout (input_proj: observation scratch; output_proj: its input, k-major)
   uint64_t full[ZBT_NST], conv[ZBT_NST], mma_done[ZBT_NST], layer_done, in_full;
   uint32_t tmem_base;
 };
@@ -93,7 +95,7 @@ static __device__ __forceinline__ void zbt_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
-static __device__ __forceinline__ int zbt_bidx(int k, int env, int lo) { return (k >> 2) * (2 * ZBP_TE * 4) + (lo * ZBP_TE + env) * 4 + (k & 3); }
+static __device__ __forceinline__ int zbt_bidx(int k, int env, int lo) { return (k >> 2) * ZBT_B_CHUNK + (lo * ZBP_TE + env) * 4 + (k & 3); }
 static __device__ __forceinline__ float zbt_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 // tiles of the ring in stream order: T_gru GRU tiles ([layer][k-tile] of gru_w_tc, 24 KB each), then output_proj rows (16 k-rows each)
@@ -106,11 +108,9 @@ struct ZbtStream {
     if (g < t_gru) {
       zbp_mbar_expect(b, ZBT_TILE_FLOATS * 4);
       zbp_bulk_load(S.w[st], gru + (size_t)g * ZBT_TILE_FLOATS, ZBT_TILE_FLOATS * 4, b);
-    } else {
-      const int k0 = (g - t_gru) * ZBP_KT_OUT;
-      const uint32_t bytes = (uint32_t)ZBP_KT_OUT * n_out * 4;
-      zbp_mbar_expect(b, bytes);
-      zbp_bulk_load(S.w[st], out_wt + (size_t)k0 * n_out, bytes, b);
+    } else {  // output_proj as a sixth layer: 3 M-tiles of 128 output rows (ZbActor.out_w_tc [k-tile 16][m-tile 3][k-chunk 2][row 128][4], 12 KB per k-tile)
+      zbp_mbar_expect(b, ZBT_TILE_FLOATS * 2);
+      zbp_bulk_load(S.w[st], out_wt + (size_t)(g - t_gru) * (ZBT_TILE_FLOATS / 2), ZBT_TILE_FLOATS * 2, b);
     }
   }
 };
@@ -118,13 +118,20 @@ struct ZbtStream {
 __global__ void __launch_bounds__(ZBP_THREADS, 1)
 zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_in, float* carry_out, const uint8_t* __restrict__ carry_reset,
                    const float* __restrict__ noise_u, const float* __restrict__ noise_eps, float* __restrict__ action, float* __restrict__ dist, int n_envs) {
+#ifdef ZBT_PROFILE
+  long long pf[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long pt = clock64(), pstart = pt;
+#define ZBT_TICK(i) do { const long long n_ = clock64(); pf[i] += n_ - pt; pt = n_; } while (0)
+#else
+#define ZBT_TICK(i)
+#endif
   extern __shared__ __align__(128) unsigned char zbt_raw[];
   ZbtSmem& S = *reinterpret_cast<ZbtSmem*>(zbt_raw);
   const int tid = threadIdx.x, warp = tid >> 5, f = tid & (ZBP_H - 1), eg = tid >> 7, e0 = eg * ZBP_EPT;
   const int env0 = blockIdx.x * ZBP_TE;
   const int n_in = A.n_in, n_out = ZB_NU * 3 * A.num_mixtures;
   ZbtStream W;
-  W.t_gru = A.depth * (ZBP_H / 8); W.t_out = ZBP_H / ZBP_KT_OUT; W.n_out = n_out; W.gru = A.gru_w_tc; W.out_wt = A.out_wt;
+  W.t_gru = A.depth * (ZBP_H / 8); W.t_out = ZBP_H / 8; W.n_out = n_out; W.gru = A.gru_w_tc; W.out_wt = A.out_w_tc;
   const int G = W.t_gru + W.t_out;
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 32, M = 128
   const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ZBP_TE >> 3) << 17) | ((uint32_t)(ZBP_H >> 4) << 24);
@@ -146,6 +153,7 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = S.tmem_base;
+  ZBT_TICK(10);  // mbarrier init + TMEM alloc + barrier
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);      // (provably warp-uniform copies for the issuing warp)
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   if (tid == 0) {
@@ -161,6 +169,7 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
     obsT[k][e] = (env0 + e < n_envs) ? obs[(size_t)(env0 + e) * n_in + k] : 0.f;
   }
   __syncthreads();
+  ZBT_TICK(11);  // observations -> shared memory
   // ---- input_proj (CUDA cores) -> layer 0's input operand (hi / lo) ----
   {
     float acc[ZBP_EPT];
@@ -168,6 +177,7 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
 #pragma unroll
     for (int e = 0; e < ZBP_EPT; e++) acc[e] = b;
     zbp_mbar_wait(&S.in_full, 0);
+    ZBT_TICK(12);  // wait: input_proj weights landed
     const float* w = S.wlo[0] + f;
     for (int k = 0; k < n_in; k++) {
       const float wv = w[k * ZBP_H];
@@ -184,34 +194,41 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
   }
   __syncthreads();  // the lo buffers and the observation scratch are free
 
-#ifdef ZBT_PROFILE
-  long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long pt = clock64(), pstart = pt;
-#define ZBT_TICK(i) do { const long long n_ = clock64(); pf[i] += n_ - pt; pt = n_; } while (0)
-#else
-#define ZBT_TICK(i)
-#endif
-  ZBT_TICK(0);  // setup + input_proj
+  ZBT_TICK(13);  // input_proj
   // ---- GRU stack on the tensor cores ----
-  float (*xT)[ZBP_LD] = reinterpret_cast<float (*)[ZBP_LD]>(&S.bh[0]);
-  float hold[ZBP_EPT];
-  for (int g = 0; g < W.t_gru; g++) {
+  float hold[ZBP_EPT], hnext[ZBP_EPT], br = 0.f, bz = 0.f, bn = 0.f, bhn = 0.f;
+  bool live[ZBP_EPT];
+#pragma unroll
+  for (int e = 0; e < ZBP_EPT; e++) {  // layer 0's carry (a reset carry is the initial carry: zeros, train.py:1731-1735)
+    const int env = env0 + e0 + e;
+    live[e] = env < n_envs && !(carry_reset && carry_reset[env]);
+    hnext[e] = live[e] ? carry_in[((size_t)env * A.depth) * ZBP_H + f] : 0.f;
+  }
+  for (int g = 0; g < G; g++) {
     const int l = g >> 4, t = g & 15, st = g % ZBT_NST;
-    if (t == 0) {  // layer prologue: the carry of this layer as the second activation operand
+    const bool out_layer = l == A.depth;  // (warp-uniform) output_proj: 3 M-tiles of W_out against the last layer's output, no carry operand
+    if (t == 0 && !out_layer) {  // layer prologue: the carry of this layer (loaded during the previous layer's MMAs) as the second activation operand
 #pragma unroll
       for (int e = 0; e < ZBP_EPT; e++) {
-        const int env = env0 + e0 + e;
-        const bool live = env < n_envs && !(carry_reset && carry_reset[env]);
-        hold[e] = live ? carry_in[((size_t)env * A.depth + l) * ZBP_H + f] : 0.f;
+        hold[e] = hnext[e];
         const float h = zbt_hi(hold[e]);
         S.bh[zbt_bidx(f, e0 + e, 0)] = h;
         S.bh[zbt_bidx(f, e0 + e, 1)] = hold[e] - h;
       }
     }
     if (t == 0) {  // the layer's activation operands (bx: previous epilogue / input_proj, bh: just written) -> visible to the tensor core
+      // (also for the output_proj layer: bx = the last GRU layer's output)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
+      if (!out_layer) {  // loads that are needed 16 tiles from now: this layer's biases (epilogue) and the next layer's carry (its prologue)
+        const float* bl = A.gru_b + (size_t)l * 3 * ZBP_H;
+        br = bl[f]; bz = bl[ZBP_H + f]; bn = bl[2 * ZBP_H + f]; bhn = A.gru_bn[(size_t)l * ZBP_H + f];
+        if (l + 1 < A.depth) {
+#pragma unroll
+          for (int e = 0; e < ZBP_EPT; e++) hnext[e] = live[e] ? carry_in[((size_t)(env0 + e0 + e) * A.depth + l + 1) * ZBP_H + f] : 0.f;
+        }
+      }
     }
     ZBT_TICK(1);  // layer prologue / loop overhead
     if (warp_u == 0) {
@@ -221,26 +238,35 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
       ZBT_TICK(2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = zbp_saddr(S.w[st]);
-      const uint32_t koff = (uint32_t)(2 * t) * (2 * ZBP_TE * 16);  // two 16-byte k-chunks per K = 8 step
-      const uint64_t dBx = zbt_desc(zbp_saddr(S.bx) + koff, 2 * ZBP_TE * 16, 128), dBh = zbt_desc(zbp_saddr(S.bh) + koff, 2 * ZBP_TE * 16, 128);
+      const uint32_t koff = (uint32_t)(2 * t) * (ZBT_B_CHUNK * 4);  // two 16-byte k-chunks per K = 8 step
+      const uint64_t dBx = zbt_desc(zbp_saddr(S.bx) + koff, ZBT_B_CHUNK * 4, 128), dBh = zbt_desc(zbp_saddr(S.bh) + koff, ZBT_B_CHUNK * 4, 128);
       const uint64_t dA_hi0 = zbt_desc(a_hi, ZBP_H * 16, 128);
       const uint32_t acc0 = t == 0 ? 0u : 1u;
       const bool lead = zbt_elect();
       if (lead) {
+        if (!out_layer) {
 #pragma unroll
-        for (int m = 0; m < 6; m++) {
-          const bool is_h = m >= 3;
-          const int gate = m % 3;
-          const uint32_t col = (gate == 2 ? (is_h ? 3u : 2u) : (uint32_t)gate) * 64u;  // accumulator: columns [col, col+32) += hi.hi and lo.hi, [col+32, col+64) += hi.lo
-          const uint64_t dstep = (uint64_t)(m * ((2 * ZBP_H * 16) >> 4));         // next matrix of the tile: + 4 KB in the address field
-          const uint32_t first = (!is_h || gate == 2) ? acc0 : 1u;                   // r, z: W_h h accumulates onto W_i x
+          for (int m = 0; m < 6; m++) {
+            const bool is_h = m >= 3;
+            const int gate = m % 3;
+            const uint32_t col = (gate == 2 ? (is_h ? 3u : 2u) : (uint32_t)gate) * 64u;  // accumulator: columns [col, col+32) += hi.hi and lo.hi, [col+32, col+64) += hi.lo
+            const uint64_t dstep = (uint64_t)(m * ((2 * ZBP_H * 16) >> 4));         // next matrix of the tile: + 4 KB in the address field
+            const uint32_t first = (!is_h || gate == 2) ? acc0 : 1u;                   // r, z: W_h h accumulates onto W_i x
 #ifndef ZBT_SKIP_MMA
-          zbt_mma(tmem_u + col, dA_hi0 + dstep, is_h ? dBh : dBx, idesc64, first);  // A_hi . [B_hi | B_lo]  (N = 64: the weight tile is read once for both)
-          zbt_mma_ts(tmem_u + col, tmem_u + ZBT_TMEM_LO + (uint32_t)((g & 1) * 48 + m * 8), is_h ? dBh : dBx, idesc32, 1u);  // A_lo (TMEM) . B_hi  (N = 32: the hi rows)
+            zbt_mma(tmem_u + col, dA_hi0 + dstep, is_h ? dBh : dBx, idesc64, first);  // A_hi . [B_hi | B_lo]  (N = 64: the weight tile is read once for both)
+            zbt_mma_ts(tmem_u + col, tmem_u + ZBT_TMEM_LO + (uint32_t)((g & 1) * 48 + m * 8), is_h ? dBh : dBx, idesc32, 1u);  // A_lo (TMEM) . B_hi  (N = 32: the hi rows)
 #endif
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < 3; m++) {  // output rows 128 m .. 128 m + 127
+            const uint64_t dstep = (uint64_t)(m * ((2 * ZBP_H * 16) >> 4));
+            zbt_mma(tmem_u + (uint32_t)m * 64u, dA_hi0 + dstep, dBx, idesc64, acc0);
+            zbt_mma_ts(tmem_u + (uint32_t)m * 64u, tmem_u + ZBT_TMEM_LO + (uint32_t)((g & 1) * 48 + m * 8), dBx, idesc32, 1u);
+          }
         }
         zbt_commit(&S.mma_done[st]);
-        if (t == 15) zbt_commit(&S.layer_done);
+        if (t == 15) zbt_commit(&S.layer_done);  // (the output_proj layer is completion number depth + 1)
         if (g + ZBT_NST - 1 < G) {  // tile g + NST - 1 goes into the stage tile g - 1 used: free once that tile's MMAs have completed
           if (g >= 1) zbp_mbar_wait(&S.mma_done[(g - 1) % ZBT_NST], (uint32_t)(((g - 1) / ZBT_NST) & 1));
           W.issue(g + ZBT_NST - 1, S);
@@ -261,7 +287,8 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
         const int q = warp & 3, fr = 32 * q + (tid & 31), grp = (warp - 1) >> 2;
 #pragma unroll
         for (int mm = 0; mm < 2; mm++) {
-          const int m = 2 * grp + mm;
+          const int m = out_layer ? grp : 2 * grp + mm;
+          if (out_layer && mm == 1) break;
           const float4 v0 = *reinterpret_cast<const float4*>(S.w[st] + (m * 2 + 0) * (ZBP_H * 4) + fr * 4);
           const float4 v1 = *reinterpret_cast<const float4*>(S.w[st] + (m * 2 + 1) * (ZBP_H * 4) + fr * 4);
           const float lo[8] = {v0.x - zbt_hi(v0.x), v0.y - zbt_hi(v0.y), v0.z - zbt_hi(v0.z), v0.w - zbt_hi(v0.w),
@@ -279,7 +306,7 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
       ZBT_TICK(5);
     }
     ZBT_TICK(6);  // thread 0: MMA issue + commit + refill
-    if (t == 15) {  // layer epilogue
+    if (t == 15 && !out_layer) {  // layer epilogue
       zbp_mbar_wait(&S.layer_done, (uint32_t)(l & 1));
       ZBT_TICK(7);  // wait: layer's MMAs done
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -300,9 +327,6 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
 #pragma unroll
         for (int e = 0; e < 8; e++) ahn[e] += t2[e];
       }
-      const float* bl = A.gru_b + (size_t)l * 3 * ZBP_H;
-      const float br = bl[f], bz = bl[ZBP_H + f], bn = bl[2 * ZBP_H + f], bhn = A.gru_bn[(size_t)l * ZBP_H + f];
-      const bool last_layer = l == A.depth - 1;
 #pragma unroll
       for (int e = 0; e < ZBP_EPT; e++) {
         const float r = zbp_sigmoid(ar[e] + br), z = zbp_sigmoid(az[e] + bz);
@@ -310,55 +334,31 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
         const float hn = fmaf(z, hold[e] - nn, nn);
         const int env = env0 + e0 + e;
         if (env < n_envs) carry_out[((size_t)env * A.depth + l) * ZBP_H + f] = hn;
-        if (last_layer) xT[f][e0 + e] = hn;  // (bh: this layer's MMAs, its last readers, have completed)
-        else {
-          const float h = zbt_hi(hn);
-          S.bx[zbt_bidx(f, e0 + e, 0)] = h;
-          S.bx[zbt_bidx(f, e0 + e, 1)] = hn - h;
-        }
+        const float h = zbt_hi(hn);  // the next layer's (or output_proj's) input operand
+        S.bx[zbt_bidx(f, e0 + e, 0)] = h;
+        S.bx[zbt_bidx(f, e0 + e, 1)] = hn - h;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();  // TMEM read out, the next layer's input operand / xT complete
       ZBT_TICK(8);  // epilogue
     }
   }
-  // ---- output_proj (CUDA cores), weights through the same ring (raw tiles in the hi half of a stage) ----
-  int g = W.t_gru;
+  // ---- output_proj epilogue: accumulators (3 M-tiles x [hi.hi + lo.hi | hi.lo]) + bias -> `out` of the tile (aliases the drained ring) ----
   float (*outS)[ZBP_OUT_MAX + 1] = reinterpret_cast<float (*)[ZBP_OUT_MAX + 1]>(&S.w[0][0]);
   {
-    float acc[3][ZBP_EPT];
+    zbp_mbar_wait(&S.layer_done, (uint32_t)(A.depth & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)e0;
 #pragma unroll
     for (int m = 0; m < 3; m++) {
       const int j = f + m * ZBP_H;
-      const float b = j < n_out ? A.out_b[j] : 0.f;
+      float a[8], b2[8];
+      zbt_ld8(taddr + m * 64, a); zbt_ld8(taddr + m * 64 + 32, b2);
+      if (j < n_out) {
+        const float bj = A.out_b[j];
 #pragma unroll
-      for (int e = 0; e < ZBP_EPT; e++) acc[m][e] = b;
-    }
-    for (int t = 0; t < W.t_out; t++, g++) {
-      zbp_mbar_wait(&S.full[g % ZBT_NST], (uint32_t)((g / ZBT_NST) & 1));
-      const float* w = S.w[g % ZBT_NST];
-#pragma unroll 4
-      for (int kk = 0; kk < ZBP_KT_OUT; kk++) {
-        const int k = t * ZBP_KT_OUT + kk;
-        float wv[3];
-#pragma unroll
-        for (int m = 0; m < 3; m++) { const int j = f + m * ZBP_H; wv[m] = j < n_out ? w[kk * n_out + j] : 0.f; }
-        const float4 x0 = *reinterpret_cast<const float4*>(&xT[k][e0]), x1 = *reinterpret_cast<const float4*>(&xT[k][e0 + 4]);
-        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-#pragma unroll
-          for (int e = 0; e < ZBP_EPT; e++) acc[m][e] = fmaf(wv[m], xv[e], acc[m][e]);
+        for (int e = 0; e < ZBP_EPT; e++) outS[e0 + e][j] = a[e] + b2[e] + bj;
       }
-      __syncthreads();  // tile g + NST - 1 goes into the stage tile g - 1 used (released by the previous barrier / layer_done)
-      if (tid == 0 && g + ZBT_NST - 1 < G) W.issue(g + ZBT_NST - 1, S);
-    }
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-      const int j = f + m * ZBP_H;
-      if (j < n_out)
-#pragma unroll
-        for (int e = 0; e < ZBP_EPT; e++) outS[e0 + e][j] = acc[m][e];  // (the ring is drained: every tile has been consumed)
     }
   }
   __syncthreads();
@@ -368,8 +368,8 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
   __syncthreads();
   if (blockIdx.x == 0 && (tid == 0 || tid == 200) && dist) {
     float* o = dist + (tid == 0 ? 0 : 16);
-    for (int i = 0; i < 10; i++) o[i] = (float)pf[i];
-    o[10] = (float)(clock64() - pstart);
+    for (int i = 0; i < 14; i++) o[i] = (float)pf[i];
+    o[14] = (float)(clock64() - pstart);
   }
 #endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

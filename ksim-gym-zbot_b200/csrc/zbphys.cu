@@ -948,7 +948,8 @@ int zb_actor_f32(void* stream, const ZbActor* A, const float* actor_obs, const f
     return fail(ZB_EUNSUP, "zb_actor_f32: n_in <= 128, depth >= 1, 1 <= num_mixtures <= 5 (hidden size 128 is built in)%s");
   const bool tc = A->precision == ZB_ACTOR_TF32X3;
   if (A->precision != ZB_ACTOR_FP32 && !tc) return fail(ZB_EINVAL, "zb_actor_f32: unknown ZbActor.precision%s");
-  if (tc && (!A->gru_w_tc || ((uintptr_t)A->gru_w_tc & 15) != 0)) return fail(ZB_EINVAL, "zb_actor_f32: ZB_ACTOR_TF32X3 needs gru_w_tc (16-byte aligned)%s");
+  if (tc && (!A->gru_w_tc || !A->out_w_tc || (((uintptr_t)A->gru_w_tc | (uintptr_t)A->out_w_tc) & 15) != 0))
+    return fail(ZB_EINVAL, "zb_actor_f32: ZB_ACTOR_TF32X3 needs gru_w_tc and out_w_tc (16-byte aligned)%s");
   if (tc && A->n_in > ZBT_MAX_IN) return fail(ZB_EUNSUP, "zb_actor_f32: ZB_ACTOR_TF32X3 is built for n_in <= 96%s");
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(ZB_ENODEV, "zb_actor_f32: no CUDA device%s");

@@ -22,7 +22,7 @@ HIDDEN = 128  # ZB_ACTOR_HIDDEN (train.py:1065-1068)
 class ZbActor(ctypes.Structure):
     _fields_ = [("n_in", ctypes.c_int32), ("depth", ctypes.c_int32), ("num_mixtures", ctypes.c_int32), ("min_std", ctypes.c_float),
                 ("max_std", ctypes.c_float), ("var_scale", ctypes.c_float), ("precision", ctypes.c_int32), ("reserved", ctypes.c_int32)] + \
-               [(k, ctypes.c_void_p) for k in ("in_wt", "in_b", "gru_wih_t", "gru_whh_t", "gru_b", "gru_bn", "out_wt", "out_b", "mean_bias", "gru_w_tc")]
+               [(k, ctypes.c_void_p) for k in ("in_wt", "in_b", "gru_wih_t", "gru_whh_t", "gru_b", "gru_bn", "out_wt", "out_b", "mean_bias", "gru_w_tc", "out_w_tc")]
 
 
 PRECISION_FP32, PRECISION_TF32X3 = 0, 1  # ZB_ACTOR_FP32 / ZB_ACTOR_TF32X3
@@ -72,7 +72,10 @@ class ActorParams:
             w6 = np.concatenate([a[f"rnns.{i}.weight_ih"].reshape(3, H, H), a[f"rnns.{i}.weight_hh"].reshape(3, H, H)])  # [m][f][k]
             return np.ascontiguousarray(w6.reshape(6, H, H // 8, 2, 4).transpose(2, 0, 3, 1, 4))                            # [t][m][c][f][j]
 
-        return {"gru_w_tc": np.stack([tc(i) for i in range(self.depth)]),"in_wt": np.ascontiguousarray(a["input_proj.weight"].T), "in_b": a["input_proj.bias"],
+        wo = np.zeros((3 * H, H), dtype=np.float32)  # output_proj rows padded to 3 M-tiles of 128
+        wo[:a["output_proj.weight"].shape[0]] = a["output_proj.weight"]
+        out_tc = np.ascontiguousarray(wo.reshape(3, H, H // 8, 2, 4).transpose(2, 0, 3, 1, 4))  # [t][mt][c][row][j]
+        return {"gru_w_tc": np.stack([tc(i) for i in range(self.depth)]), "out_w_tc": out_tc,"in_wt": np.ascontiguousarray(a["input_proj.weight"].T), "in_b": a["input_proj.bias"],
                 "gru_wih_t": np.stack([gate_t(a[f"rnns.{i}.weight_ih"]) for i in range(self.depth)]),
                 "gru_whh_t": np.stack([gate_t(a[f"rnns.{i}.weight_hh"]) for i in range(self.depth)]),
                 "gru_b": np.stack([a[f"rnns.{i}.bias"].reshape(3, H) for i in range(self.depth)]),
@@ -93,7 +96,7 @@ class ActorPolicy:
         self.weights = {k: torch.tensor(v, device=self.device) for k, v in params.pack().items()}
         self.desc = ZbActor(params.n_in, params.depth, params.num_mixtures, params.min_std, params.max_std, params.var_scale, int(precision), 0,
                             *[self.weights[k].data_ptr() for k in ("in_wt", "in_b", "gru_wih_t", "gru_whh_t", "gru_b", "gru_bn", "out_wt", "out_b", "mean_bias",
-                                                                   "gru_w_tc")])
+                                                                   "gru_w_tc", "out_w_tc")])
         self.carry = torch.zeros((self.n, params.depth, HIDDEN), dtype=torch.float32, device=self.device)  # get_initial_model_carry, train.py:1731
         self.action = torch.zeros((self.n, M.NU), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):  # n_envs = 0: sets the kernel's shared-memory attribute, so that later launches can be graph-captured

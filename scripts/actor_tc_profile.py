@@ -9,10 +9,10 @@ lib = os.path.join(ROOT, "ksim-gym-zbot_b200/csrc/variants/libzbphys_tcprof.so")
 pol = ActorPolicy(ActorParams.random(0), n, "cuda:0", lib_path=lib, precision=1)
 obs = torch.randn((n, 50), device="cuda")
 dist = torch.zeros((n, 3, 20, 5), device="cuda")
-names = ["setup+in_proj", "prologue/loop", "wait tile", "wait mma(g-2)", "convert", "fences+barrier", "t0 issue/refill", "wait layer", "epilogue", "out_proj+head", "TOTAL"]
+names = ["-", "layer prologue", "wait tile/conv", "wait mma(g-2)", "convert", "arrive", "issue/refill", "wait layer", "epilogue", "out epilogue+head", "setup", "obs load", "wait in_w", "in_proj", "TOTAL"]
 for rep in range(3):
     pol.enqueue(obs, pol.action, dist_out=dist)
     torch.cuda.synchronize()
     d = dist.view(-1)[:32].cpu().numpy()
     for who, off in (("thread 0", 0), ("thread 200", 16)):
-        print(rep, who, {k: int(v) for k, v in zip(names, d[off:off + 11])}, flush=True)
+        print(rep, who, {k: int(v) for k, v in zip(names, d[off:off + 15])}, flush=True)

@@ -84,6 +84,9 @@ def test_pack_layout_and_abi():
     for (t, m, c, f, j) in ((0, 0, 0, 0, 0), (3, 2, 1, 17, 2), (15, 4, 1, 127, 3), (7, 5, 0, 64, 1)):
         src = (wi if m < 3 else prm.arrays["rnns.1.weight_hh"])[(m % 3) * HIDDEN + f, 8 * t + 4 * c + j]
         assert pk["gru_w_tc"][1, t, m, c, f, j] == src
+    assert pk["out_w_tc"].shape == (16, 3, 2, HIDDEN, 4)
+    wo = prm.arrays["output_proj.weight"]
+    assert pk["out_w_tc"][5, 2, 1, 43, 2] == wo[2 * HIDDEN + 43, 8 * 5 + 4 * 1 + 2] and pk["out_w_tc"][0, 2, 0, 44, 0] == 0.0  # row 300: padding
     lib = ctypes.CDLL(ksim_gym_zbot_b200.engine.LIB_PATH)
     assert lib.zb_sizeof_actor() == ctypes.sizeof(ZbActor)
     assert hasattr(lib, "zb_actor_f32")
