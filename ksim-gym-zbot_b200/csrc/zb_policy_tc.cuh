@@ -207,21 +207,21 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
   for (int g = 0; g < G; g++) {
     const int l = g >> 4, t = g & 15, st = g % ZBT_NST;
     const bool out_layer = l == A.depth;  // (warp-uniform) output_proj: 3 M-tiles of W_out against the last layer's output, no carry operand
-    if (t == 0 && !out_layer) {  // layer prologue: the carry of this layer (loaded during the previous layer's MMAs) as the second activation operand
+    if (t == 0) {
+      if (l == 0) {  // layer 0: its carry operand is written here (later layers: by the previous layer's epilogue, one barrier less per layer)
 #pragma unroll
-      for (int e = 0; e < ZBP_EPT; e++) {
-        hold[e] = hnext[e];
-        const float h = zbt_hi(hold[e]);
-        S.bh[zbt_bidx(f, e0 + e, 0)] = h;
-        S.bh[zbt_bidx(f, e0 + e, 1)] = hold[e] - h;
+        for (int e = 0; e < ZBP_EPT; e++) {
+          const float h = zbt_hi(hnext[e]);
+          S.bh[zbt_bidx(f, e0 + e, 0)] = h;
+          S.bh[zbt_bidx(f, e0 + e, 1)] = hnext[e] - h;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // bx (input_proj), bh -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
       }
-    }
-    if (t == 0) {  // the layer's activation operands (bx: previous epilogue / input_proj, bh: just written) -> visible to the tensor core
-      // (also for the output_proj layer: bx = the last GRU layer's output)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (!out_layer) {  // loads that are needed 16 tiles from now: this layer's biases (epilogue) and the next layer's carry (its prologue)
+      if (!out_layer) {  // this layer's carry (gate blend), and the loads that are needed 16 tiles from now: its biases and the next layer's carry
+#pragma unroll
+        for (int e = 0; e < ZBP_EPT; e++) hold[e] = hnext[e];
         const float* bl = A.gru_b + (size_t)l * 3 * ZBP_H;
         br = bl[f]; bz = bl[ZBP_H + f]; bn = bl[2 * ZBP_H + f]; bhn = A.gru_bn[(size_t)l * ZBP_H + f];
         if (l + 1 < A.depth) {
@@ -337,9 +337,15 @@ zb_actor_tc_kernel(ZbActor A, const float* __restrict__ obs, const float* carry_
         const float h = zbt_hi(hn);  // the next layer's (or output_proj's) input operand
         S.bx[zbt_bidx(f, e0 + e, 0)] = h;
         S.bx[zbt_bidx(f, e0 + e, 1)] = hn - h;
+        if (l + 1 < A.depth) {       // ... and the next layer's carry operand (bh: this layer's MMAs, its last readers, have completed)
+          const float c = zbt_hi(hnext[e]);
+          S.bh[zbt_bidx(f, e0 + e, 0)] = c;
+          S.bh[zbt_bidx(f, e0 + e, 1)] = hnext[e] - c;
+        }
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the operands just written -> visible to the tensor core
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();  // TMEM read out, the next layer's input operand / xT complete
+      __syncthreads();  // TMEM read out, the next layer's operands complete
       ZBT_TICK(8);  // epilogue
     }
   }
