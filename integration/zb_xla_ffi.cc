@@ -157,6 +157,30 @@ static ffi::Error ZbFeetAirtimeImpl(cudaStream_t stream, float ctrl_dt, float to
 XLA_FFI_DEFINE_HANDLER_SYMBOL(zb_feet_airtime_ffi, ZbFeetAirtimeImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<float>("ctrl_dt").Attr<float>("touchdown_penalty")
                                   .Arg<F32>().Arg<F32>().Arg<U8>().Arg<F32>().Ret<F32>().Ret<F32>());
+// Actor.forward + action selection per control step (train.py:946-968, 1737-1763; zb_actor_f32): weights in the kernel layout
+// (ksim-gym-zbot_b200/policy.py ActorParams.pack; re-packed once per policy update), carry aliased with its result.
+static ffi::Error ZbActorImpl(cudaStream_t stream, int32_t depth, int32_t num_mixtures, int32_t precision, int32_t argmax, float min_std, float max_std,
+                              float var_scale, F32 in_wt, F32 in_b, F32 gru_wih_t, F32 gru_whh_t, F32 gru_b, F32 gru_bn, F32 out_wt, F32 out_b,
+                              F32 mean_bias, F32 gru_w_tc, F32 out_w_tc, F32 actor_obs, F32 carry, U8 carry_reset, F32 noise_u, F32 noise_eps,
+                              RF32 carry_o, RF32 action) {
+  const int n = static_cast<int>(actor_obs.dimensions()[0]);
+  ZbActor a;
+  a.n_in = static_cast<int32_t>(actor_obs.dimensions()[1]);
+  a.depth = depth; a.num_mixtures = num_mixtures; a.min_std = min_std; a.max_std = max_std; a.var_scale = var_scale;
+  a.precision = precision; a.reserved = 0;
+  a.in_wt = in_wt.typed_data(); a.in_b = in_b.typed_data(); a.gru_wih_t = gru_wih_t.typed_data(); a.gru_whh_t = gru_whh_t.typed_data();
+  a.gru_b = gru_b.typed_data(); a.gru_bn = gru_bn.typed_data(); a.out_wt = out_wt.typed_data(); a.out_b = out_b.typed_data();
+  a.mean_bias = mean_bias.typed_data(); a.gru_w_tc = gru_w_tc.typed_data(); a.out_w_tc = out_w_tc.typed_data();
+  return status(zb_actor_f32(stream, &a, actor_obs.typed_data(), carry.typed_data(), carry_o->typed_data(), carry_reset.typed_data(),
+                             argmax ? nullptr : noise_u.typed_data(), argmax ? nullptr : noise_eps.typed_data(), action->typed_data(), nullptr, n));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(zb_actor_ffi, ZbActorImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int32_t>("depth").Attr<int32_t>("num_mixtures").Attr<int32_t>("precision").Attr<int32_t>("argmax")
+                                  .Attr<float>("min_std").Attr<float>("max_std").Attr<float>("var_scale")
+                                  .Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>()  // weights
+                                  .Arg<F32>().Arg<F32>().Arg<U8>().Arg<F32>().Arg<F32>()                                                                      // obs, carry, reset, noise
+                                  .Ret<F32>().Ret<F32>());
 #else
 #error "xla/ffi/api/ffi.h not found: build this file where jaxlib is installed (-I$(python -c 'import jax; print(jax.ffi.include_dir())'))"
 #endif

@@ -51,6 +51,14 @@ _DATA_OUT = (("xpos", (NB, 3), "f32"), ("xquat", (NB, 4), "f32"), ("cinert", (NB
              ("actuator_force", (NU,), "f32"), ("ctrl", (NU,), "f32"), ("sensordata", (18,), "f32"), ("site_xpos", (NSITE, 3), "f32"),
              ("site_xmat", (NSITE, 9), "f32"))
 _OBS_OUT = (("actor_obs", (50,), "f32"), ("critic_obs", (484,), "f32"), ("feet_pos_obs", (6,), "f32"), ("reward_terms", (6,), "f32"))
+# zb_actor (policy inference in the rollout, train.py:946-968, 1737-1763): weights in kernel layout (policy.ActorParams.pack), then the
+# per-step arrays; `carry` is aliased with its result
+_ACTOR_ATTRS = (("depth", "i32"), ("num_mixtures", "i32"), ("precision", "i32"), ("argmax", "i32"), ("min_std", "f32"), ("max_std", "f32"), ("var_scale", "f32"))
+_ACTOR_WEIGHTS = (("in_wt", (50, 128), "f32"), ("in_b", (128,), "f32"), ("gru_wih_t", (5, 128, 3, 128), "f32"), ("gru_whh_t", (5, 128, 3, 128), "f32"),
+                  ("gru_b", (5, 3, 128), "f32"), ("gru_bn", (5, 128), "f32"), ("out_wt", (128, 300), "f32"), ("out_b", (300,), "f32"),
+                  ("mean_bias", (NU,), "f32"), ("gru_w_tc", (5, 16, 6, 2, 128, 4), "f32"), ("out_w_tc", (16, 3, 2, 128, 4), "f32"))
+_ACTOR_INPUTS = (("actor_obs", (50,), "f32"), ("carry", (5, 128), "f32"), ("carry_reset", (), "u8"), ("noise_u", (NU,), "f32"), ("noise_eps", (NU,), "f32"))
+_ACTOR_RESULTS = (("carry", (5, 128), "f32"), ("action", (NU,), "f32"))
 _STEP_RESULTS = _STATE + _DATA_OUT + (("done", (), "u8"),) + _OBS_OUT
 _RESET_RESULTS = _STATE + _DATA_OUT + _OBS_OUT
 _STEP_ATTRS = (("engine", "i64"), ("n_substeps", "i32"), ("z_lo", "f32"), ("z_hi", "f32"), ("max_tilt_rad", "f32"), ("max_episode_sec", "f32"))
@@ -58,7 +66,7 @@ _RESET_ATTRS = (("engine", "i64"),)
 _DT = {"f32": jnp.float32, "u8": jnp.uint8, "i32": jnp.int32}
 
 _lib = ctypes.CDLL("libzb_ffi.so")
-for _name in ("zb_step_obs", "zb_reset_obs", "zb_feet_airtime"):
+for _name in ("zb_step_obs", "zb_reset_obs", "zb_feet_airtime", "zb_actor"):
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_lib, _name + "_ffi")), platform="CUDA")
 
 
@@ -216,3 +224,19 @@ def feet_airtime_reward(left_contact, right_contact, done, carry, ctrl_dt=0.02, 
     call = jax.ffi.ffi_call("zb_feet_airtime", [jax.ShapeDtypeStruct(carry.shape, jnp.float32), jax.ShapeDtypeStruct(left_contact.shape, jnp.float32)],
                             input_output_aliases={3: 0})
     return call(left_contact, right_contact, done, carry, ctrl_dt=np.float32(ctrl_dt), touchdown_penalty=np.float32(touchdown_penalty))
+
+
+def zb_sample_action(packed_actor: dict, observations_actor: "jax.Array", actor_carry: "jax.Array", done_prev: "jax.Array", rng: "jax.Array", argmax: bool,
+                     precision: int = 1, min_std: float = 0.01, max_std: float = 1.0, var_scale: float = 1.0):
+    """Drop-in body for ``ZbotWalkingTask.sample_action`` (train.py:1737-1763): one ``zb_actor`` custom call per control step instead of
+    ``Actor.forward`` + ``MixtureOfGaussians.mode() / .sample()``.  ``packed_actor`` = the eleven weight arrays of ``_ACTOR_WEIGHTS`` in kernel
+    layout (``ksim-gym-zbot_b200/policy.py: ActorParams.pack`` — re-pack after every policy update); the random numbers of the sample path
+    come from ``rng`` here (JAX's PRNG), the kernel only consumes them.  Returns (action, next_actor_carry)."""
+    k1, k2 = jax.random.split(rng)
+    u, eps = jax.random.uniform(k1, (NU,)), jax.random.normal(k2, (NU,))
+    depth, num_mixtures = packed_actor["gru_b"].shape[0], packed_actor["out_b"].shape[0] // (3 * NU)
+    call = jax.ffi.ffi_call("zb_actor", _results(_ACTOR_RESULTS), vmap_method="broadcast_all", input_output_aliases={12: 0})
+    carry, action = call(*[packed_actor[n] for n, _, _ in _ACTOR_WEIGHTS], observations_actor, actor_carry, done_prev.astype(jnp.uint8), u, eps,
+                         depth=np.int32(depth), num_mixtures=np.int32(num_mixtures), precision=np.int32(precision), argmax=np.int32(bool(argmax)),
+                         min_std=np.float32(min_std), max_std=np.float32(max_std), var_scale=np.float32(var_scale))
+    return action, carry

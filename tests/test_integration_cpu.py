@@ -73,6 +73,7 @@ ATTR = {"i64": "int64_t", "i32": "int32_t", "f32": "float"}
 @pytest.mark.parametrize("impl,symbol,attrs,operands,results", [
     ("ZbStepObsImpl", "zb_step_obs_ffi", "_STEP_ATTRS", ("_STATE", "_STEP_INPUTS", "_MODEL_FIELDS"), "_STEP_RESULTS"),
     ("ZbResetObsImpl", "zb_reset_obs_ffi", "_RESET_ATTRS", ("_RESET_INPUTS", "_MODEL_FIELDS"), "_RESET_RESULTS"),
+    ("ZbActorImpl", "zb_actor_ffi", "_ACTOR_ATTRS", ("_ACTOR_WEIGHTS", "_ACTOR_INPUTS"), "_ACTOR_RESULTS"),
 ])
 def test_operand_order_matches_between_cpp_and_python(impl, symbol, attrs, operands, results):
     _, t = _py_tables()
@@ -92,7 +93,7 @@ def test_operand_order_matches_between_cpp_and_python(impl, symbol, attrs, opera
     for name, _, dt in want_ops:
         assert sig[i] == (CT[dt], name), (sig[i], name)
         i += 1
-    state_names = {n for n, _, _ in t["_STATE"]}
+    state_names = {n for n, _, _ in t["_STATE"]} | {"carry"}
     for name, _, dt in want_res:
         cname = name + "_o" if name in state_names else name  # state results are the `_o` twins of the aliased operands
         assert sig[i] == ("R" + CT[dt], cname), (sig[i], cname)
