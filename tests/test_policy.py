@@ -218,3 +218,46 @@ def test_actor_kernel_is_deterministic_and_batch_independent(precision):
     pol2.enqueue(d_obs[n - m:].contiguous(), pol2.action, noise_u=d_u[n - m:].contiguous(), noise_eps=d_eps[n - m:].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(pol2.action, ref_a[n - m:]) and torch.equal(pol2.carry, ref_c[n - m:])
+
+
+def _golden():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "actor_golden.npz"))
+    return g, ActorParams.random(seed=int(g["seed"]))
+
+
+def test_oracle_matches_actor_golden():
+    """tests/golden/actor_golden.npz (written by tests/golden/make_actor_golden.py from torch.nn layers): the restatement reproduces three
+    recurrent steps incl. the carry restarts."""
+    import zb_policy_oracle as PO
+
+    g, prm = _golden()
+    carry = g["carry0"].astype(np.float64)
+    for t in range(g["obs"].shape[0]):
+        carry[g["reset"][t] != 0] = 0.0
+        mean, std, logits, carry = PO.actor_forward(prm.oracle_dict(), g["obs"][t], carry)
+        for got, key in ((mean, "means"), (std, "stds"), (logits, "logits"), (carry, "carries")):
+            np.testing.assert_allclose(got, g[key][t], rtol=0, atol=2e-7, err_msg=f"{key} step {t}")  # (the fixture is stored in float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "tf32x3-tcgen05"])
+def test_actor_kernel_matches_golden(precision):
+    import torch
+    from ksim_gym_zbot_b200.policy import ActorPolicy
+
+    g, prm = _golden()
+    T, n = g["obs"].shape[:2]
+    pol = ActorPolicy(prm, n, "cuda:0", precision=precision)
+    pol.carry.copy_(torch.tensor(g["carry0"]))
+    dist = torch.zeros((n, 3, M.NU, prm.num_mixtures), device="cuda:0")
+    for t in range(T):
+        pol.enqueue(torch.tensor(g["obs"][t], device="cuda:0"), pol.action, carry_reset=torch.tensor(g["reset"][t], device="cuda:0"), dist_out=dist)
+        torch.cuda.synchronize()
+        d = dist.cpu().numpy()
+        tol = 3e-6 if precision == 0 else 1e-5
+        np.testing.assert_allclose(pol.carry.cpu().numpy(), g["carries"][t], rtol=0, atol=tol, err_msg=f"carry step {t}")
+        np.testing.assert_allclose(d[:, 0], g["means"][t], rtol=0, atol=tol, err_msg=f"means step {t}")
+        np.testing.assert_allclose(d[:, 1], g["stds"][t], rtol=0, atol=tol, err_msg=f"stds step {t}")
+        np.testing.assert_allclose(d[:, 2], g["logits"][t], rtol=0, atol=tol, err_msg=f"logits step {t}")
